@@ -1,0 +1,834 @@
+// batch.cu -- host runtime behind the C ABI (include/speexb200.h): owns the CUDA streams,
+// pinned staging, the uploaded filter bank and the device-resident per-stream state
+// (last_sample, samp_frac_num, magic_samples, history) of a batch of streams.
+//
+// This file replaces what src/speex_wasm.js + the WASM heap staging of src/index.ts:59-115
+// do in the reference (malloc'd in/out staging, length cells, state lifetime). There is no
+// CPU fallback: without a CUDA device creation fails with RESAMPLER_ERR_ALLOC_FAILED.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/speexb200.h"
+#include "call_plan.h"
+#include "device_types.h"
+#include "filter_bank.h"
+#include "launch.h"
+
+namespace spxb {
+
+thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+#define SPXB_CUDA(expr)                                                               \
+  do {                                                                                \
+    cudaError_t e__ = (expr);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
+      return RESAMPLER_ERR_ALLOC_FAILED;                                              \
+    }                                                                                 \
+  } while (0)
+
+constexpr int kPipelineDepth = 3;
+
+inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// one in-flight call: device staging + (optional) pinned bounce buffers + events
+struct Slot {
+  int16_t *d_in = nullptr;
+  size_t d_in_cap = 0;  // int16 elements
+  int16_t *d_out = nullptr;
+  size_t d_out_cap = 0;
+  int16_t *h_in = nullptr;  // pinned bounce for pageable / ragged input
+  size_t h_in_cap = 0;
+  int16_t *h_out = nullptr;
+  size_t h_out_cap = 0;
+  StreamCall *h_calls = nullptr;  // pinned, n_streams
+  StreamCall *d_calls = nullptr;
+  cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_done = nullptr;
+  bool busy = false;
+  uint64_t ticket = 0;
+  // deferred copy-out (pageable or ragged output)
+  bool bounce_out = false;
+  int16_t *user_out = nullptr;
+  size_t user_out_stride = 0;  // elements
+  size_t dev_out_stride = 0;   // elements
+  std::vector<uint32_t> out_counts;  // frames per stream (ragged); empty => uniform
+  uint32_t uniform_out = 0;
+};
+
+}  // namespace spxb
+
+using namespace spxb;
+
+struct spxb_batch {
+  int device = 0;
+  int sm_count = 148;
+  FilterSpec spec;
+  uint32_t n_streams = 0, channels = 0;
+  // filter bank in HBM
+  float *d_table = nullptr, *d_taps = nullptr, *d_blend = nullptr;
+  // stream state in HBM
+  int16_t *d_hist[2] = {nullptr, nullptr};
+  int hist_cur = 0;
+  uint32_t hist_frames = 0, hist_stride = 0;
+  int32_t *d_last_sample = nullptr;
+  uint32_t *d_samp_frac = nullptr;
+  uint32_t *d_magic = nullptr;
+  // host shadow of the positions (lengths of a call are a pure function of these)
+  std::vector<StreamPos> pos;
+  bool uniform_pos = true;
+  // streams
+  cudaStream_t s_own = nullptr, s_compute = nullptr, s_in = nullptr, s_out = nullptr;
+  bool external_stream = false;
+  cudaEvent_t ev_state = nullptr;
+  Slot slots[kPipelineDepth];
+  uint64_t next_ticket = 1;
+  int kernel_pref = SPXB_KERNEL_AUTO;
+  int last_kernel = SPXB_KERNEL_AUTO;
+  spxb_counters counters{};
+  // memo of the last uniform plan
+  bool memo_valid = false;
+  StreamPos memo_pos;
+  uint32_t memo_n_in = 0, memo_cap = 0;
+  CallPlan memo_plan;
+};
+
+namespace spxb {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+static CallPlan plan_memo(spxb_batch *b, StreamPos p, uint32_t n_in, uint32_t cap) {
+  if (b->memo_valid && b->memo_pos.last_sample == p.last_sample &&
+      b->memo_pos.samp_frac_num == p.samp_frac_num && b->memo_n_in == n_in &&
+      b->memo_cap == cap)
+    return b->memo_plan;
+  CallPlan pl = plan_call(b->spec.num, b->spec.den, p, n_in, cap);
+  b->memo_valid = true;
+  b->memo_pos = p;
+  b->memo_n_in = n_in;
+  b->memo_cap = cap;
+  b->memo_plan = pl;
+  return pl;
+}
+
+static StreamCall to_stream_call(StreamPos p, uint32_t n_in, const CallPlan &pl) {
+  StreamCall sc;
+  sc.ls0 = p.last_sample;
+  sc.frac0 = p.samp_frac_num;
+  sc.n_in = n_in;
+  sc.n_out = pl.n_out;
+  sc.consumed = pl.consumed;
+  sc.ls1 = pl.next.last_sample;
+  sc.frac1 = pl.next.samp_frac_num;
+  sc.pad_ = 0;
+  return sc;
+}
+
+static bool is_pinned_or_device(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice ||
+         at.type == cudaMemoryTypeManaged;
+}
+
+static int grow_device(int16_t **p, size_t *cap, size_t need) {
+  if (*cap >= need) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  const size_t want = round_up(need + need / 4, 4096);
+  SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(p), want * sizeof(int16_t)));
+  *cap = want;
+  return 0;
+}
+
+static int grow_pinned(int16_t **p, size_t *cap, size_t need) {
+  if (*cap >= need) return 0;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr;
+  *cap = 0;
+  const size_t want = round_up(need + need / 4, 4096);
+  SPXB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(p), want * sizeof(int16_t), cudaHostAllocDefault));
+  *cap = want;
+  return 0;
+}
+
+// Finish a slot: wait for its D2H, run the deferred bounce copy, mark it free.
+static int retire_slot(spxb_batch *b, Slot &sl) {
+  if (!sl.busy) return 0;
+  SPXB_CUDA(cudaEventSynchronize(sl.ev_done));
+  if (sl.bounce_out && sl.user_out) {
+    const size_t ch = b->channels;
+    if (sl.out_counts.empty()) {
+      const size_t row = static_cast<size_t>(sl.uniform_out) * ch;
+      for (uint32_t s = 0; s < b->n_streams; ++s)
+        std::memcpy(sl.user_out + s * sl.user_out_stride, sl.h_out + s * sl.dev_out_stride,
+                    row * sizeof(int16_t));
+    } else {
+      for (uint32_t s = 0; s < b->n_streams; ++s)
+        std::memcpy(sl.user_out + s * sl.user_out_stride, sl.h_out + s * sl.dev_out_stride,
+                    static_cast<size_t>(sl.out_counts[s]) * ch * sizeof(int16_t));
+    }
+  }
+  sl.busy = false;
+  sl.bounce_out = false;
+  sl.user_out = nullptr;
+  return 0;
+}
+
+// Build the kernel arguments for a call whose per-stream plans are already decided, launch
+// the FIR (+ fused history slide) on the compute stream and flip the history ping-pong.
+static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elems, int16_t *d_out,
+                       size_t out_stride_elems, const StreamCall *d_calls,
+                       const StreamCall &uniform, uint32_t max_n_out) {
+  CallArgs a;
+  a.filt.num = b->spec.num;
+  a.filt.den = b->spec.den;
+  a.filt.taps = b->spec.taps;
+  a.filt.oversample = b->spec.oversample;
+  a.filt.direct = b->spec.direct ? 1 : 0;
+  a.filt.wide_accum = b->spec.wide_accum ? 1 : 0;
+  a.filt.table = b->d_table;
+  a.filt.phase_taps = b->d_taps;
+  a.filt.blend = b->d_blend;
+  a.n_streams = b->n_streams;
+  a.channels = b->channels;
+  a.in = d_in;
+  a.in_stride = in_stride_elems;
+  a.out = d_out;
+  a.out_stride = out_stride_elems;
+  a.hist_src = b->d_hist[b->hist_cur];
+  a.hist_dst = b->d_hist[b->hist_cur ^ 1];
+  a.hist_stride = b->hist_stride;
+  a.hist_frames = b->hist_frames;
+  a.last_sample = b->d_last_sample;
+  a.samp_frac = b->d_samp_frac;
+  a.per_stream = d_calls;
+  a.uniform = uniform;
+  a.max_n_out = max_n_out;
+
+  uint32_t launches = 0;
+  cudaError_t ce = cudaSuccess;
+  int used = SPXB_KERNEL_STRICT;
+  TiledConfig cfg;
+  const bool want_tiled = b->kernel_pref != SPXB_KERNEL_STRICT;
+  if (want_tiled && b->d_taps && tiled_qualifies(a, b->sm_count, &cfg)) {
+    ce = launch_tiled(a, cfg, b->s_compute, &launches);
+    used = SPXB_KERNEL_TILED;
+  } else if (b->kernel_pref == SPXB_KERNEL_TILED && max_n_out != 0) {
+    set_error("SPXB_KERNEL_TILED requested but this call does not qualify for the tiled kernel");
+    return RESAMPLER_ERR_BAD_STATE;
+  } else {
+    ce = launch_strict(a, b->s_compute, &launches);
+  }
+  if (ce != cudaSuccess) {
+    set_error(std::string("kernel launch: ") + cudaGetErrorString(ce));
+    return RESAMPLER_ERR_BAD_STATE;
+  }
+  b->last_kernel = used;
+  b->counters.kernel_launches += launches;
+  b->hist_cur ^= 1;
+  return 0;
+}
+
+// Decide every stream's plan for (in_frames, out_frames); fills per-stream StreamCalls into
+// `calls` when the batch is ragged. Updates the host shadow and the in/out length arrays.
+struct Decided {
+  bool uniform = true;
+  StreamCall uni{};
+  uint32_t max_n_in = 0, max_n_out = 0;
+  bool any_work = false;
+};
+
+static Decided decide_uniform(spxb_batch *b, uint32_t n_in, uint32_t cap) {
+  Decided d;
+  const StreamPos p = b->pos[0];
+  const CallPlan pl = plan_memo(b, p, n_in, cap);
+  d.uni = to_stream_call(p, n_in, pl);
+  d.max_n_in = n_in;
+  d.max_n_out = pl.n_out;
+  d.any_work = n_in != 0 && cap != 0;
+  if (d.any_work) {
+    // all shadows advance together; keep only pos[0] exact and mirror lazily
+    for (auto &q : b->pos) q = pl.next;
+  }
+  return d;
+}
+
+static Decided decide(spxb_batch *b, uint32_t *in_frames, uint32_t *out_frames, StreamCall *calls) {
+  const uint32_t S = b->n_streams;
+  bool same = b->uniform_pos;
+  for (uint32_t s = 1; same && s < S; ++s)
+    same = in_frames[s] == in_frames[0] && out_frames[s] == out_frames[0];
+  if (same) {
+    Decided d = decide_uniform(b, in_frames[0], out_frames[0]);
+    for (uint32_t s = 0; s < S; ++s) {
+      in_frames[s] = d.uni.consumed;
+      out_frames[s] = d.uni.n_out;
+    }
+    return d;
+  }
+  Decided d;
+  d.uniform = false;
+  for (uint32_t s = 0; s < S; ++s) {
+    const StreamPos p = b->pos[s];
+    const uint32_t n_in = in_frames[s], cap = out_frames[s];
+    const CallPlan pl = plan_memo(b, p, n_in, cap);
+    calls[s] = to_stream_call(p, n_in, pl);
+    d.max_n_in = std::max(d.max_n_in, n_in);
+    d.max_n_out = std::max(d.max_n_out, pl.n_out);
+    if (n_in != 0 && cap != 0) {
+      d.any_work = true;
+      b->pos[s] = pl.next;
+    }
+    in_frames[s] = pl.consumed;
+    out_frames[s] = pl.n_out;
+  }
+  // positions may have diverged
+  b->uniform_pos = true;
+  for (uint32_t s = 1; s < S && b->uniform_pos; ++s)
+    b->uniform_pos = b->pos[s].last_sample == b->pos[0].last_sample &&
+                     b->pos[s].samp_frac_num == b->pos[0].samp_frac_num;
+  return d;
+}
+
+static void free_batch(spxb_batch *b) {
+  if (!b) return;
+  DeviceGuard g(b->device);
+  cudaDeviceSynchronize();
+  for (auto &sl : b->slots) {
+    if (sl.d_in) cudaFree(sl.d_in);
+    if (sl.d_out) cudaFree(sl.d_out);
+    if (sl.h_in) cudaFreeHost(sl.h_in);
+    if (sl.h_out) cudaFreeHost(sl.h_out);
+    if (sl.h_calls) cudaFreeHost(sl.h_calls);
+    if (sl.d_calls) cudaFree(sl.d_calls);
+    if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+    if (sl.ev_kernel) cudaEventDestroy(sl.ev_kernel);
+    if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+  }
+  if (b->ev_state) cudaEventDestroy(b->ev_state);
+  if (b->d_table) cudaFree(b->d_table);
+  if (b->d_taps) cudaFree(b->d_taps);
+  if (b->d_blend) cudaFree(b->d_blend);
+  if (b->d_hist[0]) cudaFree(b->d_hist[0]);
+  if (b->d_hist[1]) cudaFree(b->d_hist[1]);
+  if (b->d_last_sample) cudaFree(b->d_last_sample);
+  if (b->d_samp_frac) cudaFree(b->d_samp_frac);
+  if (b->d_magic) cudaFree(b->d_magic);
+  if (b->s_own) cudaStreamDestroy(b->s_own);
+  if (b->s_in) cudaStreamDestroy(b->s_in);
+  if (b->s_out) cudaStreamDestroy(b->s_out);
+  cudaGetLastError();
+  delete b;
+}
+
+static int create_batch(spxb_batch *b) {
+  SPXB_CUDA(cudaSetDevice(b->device));
+  cudaDeviceProp prop;
+  SPXB_CUDA(cudaGetDeviceProperties(&prop, b->device));
+  b->sm_count = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    set_error("libspeexb200 is built for sm_100a (B200) only; device is sm_" +
+              std::to_string(prop.major) + std::to_string(prop.minor));
+    return RESAMPLER_ERR_ALLOC_FAILED;
+  }
+  SPXB_CUDA(tiled_prepare_device());
+  SPXB_CUDA(cudaStreamCreateWithFlags(&b->s_own, cudaStreamNonBlocking));
+  SPXB_CUDA(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking));
+  SPXB_CUDA(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
+  b->s_compute = b->s_own;
+  SPXB_CUDA(cudaEventCreateWithFlags(&b->ev_state, cudaEventDisableTiming));
+  for (auto &sl : b->slots) {
+    SPXB_CUDA(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
+    SPXB_CUDA(cudaEventCreateWithFlags(&sl.ev_kernel, cudaEventDisableTiming));
+    SPXB_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+  }
+
+  // filter bank: generated on the host exactly like update_filter, uploaded once
+  const FilterSpec &sp = b->spec;
+  std::vector<float> table = build_reference_table(sp);
+  SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->d_table), table.size() * sizeof(float)));
+  SPXB_CUDA(cudaMemcpy(b->d_table, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice));
+  // per-phase taps only while the den*N table stays modest (64 MiB); beyond that the strict
+  // kernel (which needs only the oversampled prototype) serves the batch
+  const uint64_t phase_floats = static_cast<uint64_t>(sp.den) * sp.taps;
+  if (phase_floats * sizeof(float) <= (64ull << 20)) {
+    std::vector<float> taps = build_phase_taps(sp, table);
+    SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->d_taps), taps.size() * sizeof(float)));
+    SPXB_CUDA(cudaMemcpy(b->d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if (!sp.direct) {
+    std::vector<float> blend(static_cast<size_t>(sp.den) * 4);
+    for (uint32_t ph = 0; ph < sp.den; ++ph) {
+      const uint32_t scaled = ph * sp.oversample;  // uint32 like resample.c:458
+      cubic_weights(static_cast<float>(scaled % sp.den) / sp.den, &blend[static_cast<size_t>(ph) * 4]);
+    }
+    SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->d_blend), blend.size() * sizeof(float)));
+    SPXB_CUDA(cudaMemcpy(b->d_blend, blend.data(), blend.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+
+  // stream state, zeroed: resample.c:721-725 and the calloc'd per-channel arrays :838-843
+  b->hist_frames = static_cast<uint32_t>(round_up(sp.taps - 1, 4));
+  b->hist_stride = static_cast<uint32_t>(round_up(static_cast<size_t>(b->hist_frames) * b->channels, 8));
+  const size_t hist_bytes = static_cast<size_t>(b->n_streams) * b->hist_stride * sizeof(int16_t);
+  for (int i = 0; i < 2; ++i) {
+    SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->d_hist[i]), std::max<size_t>(hist_bytes, 16)));
+    SPXB_CUDA(cudaMemset(b->d_hist[i], 0, std::max<size_t>(hist_bytes, 16)));
+  }
+  const size_t nS = b->n_streams;
+  SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->d_last_sample), nS * sizeof(int32_t)));
+  SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->d_samp_frac), nS * sizeof(uint32_t)));
+  SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->d_magic), nS * sizeof(uint32_t)));
+  SPXB_CUDA(cudaMemset(b->d_last_sample, 0, nS * sizeof(int32_t)));
+  SPXB_CUDA(cudaMemset(b->d_samp_frac, 0, nS * sizeof(uint32_t)));
+  SPXB_CUDA(cudaMemset(b->d_magic, 0, nS * sizeof(uint32_t)));
+  b->pos.assign(nS, StreamPos{});
+  b->uniform_pos = true;
+  SPXB_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+// Shared body of submit(): host buffers in, ticket out.
+static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames, uint32_t *in_frames,
+                       int16_t *out, size_t out_stride_frames, uint32_t *out_frames,
+                       uint64_t *ticket) {
+  DeviceGuard g(b->device);
+  const uint32_t S = b->n_streams;
+  const size_t ch = b->channels;
+  Slot &sl = b->slots[b->next_ticket % kPipelineDepth];
+  if (int e = retire_slot(b, sl)) return e;
+
+  // remember the offered lengths: decide() overwrites the arrays with consumed / written
+  const bool offered_uniform = [&] {
+    for (uint32_t s = 1; s < S; ++s)
+      if (in_frames[s] != in_frames[0] || out_frames[s] != out_frames[0]) return false;
+    return true;
+  }();
+  std::vector<uint32_t> offered_in;
+  if (!offered_uniform) offered_in.assign(in_frames, in_frames + S);
+  const uint32_t offered_in0 = in_frames[0];
+
+  if (!sl.h_calls) {
+    SPXB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_calls), S * sizeof(StreamCall), cudaHostAllocDefault));
+    SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&sl.d_calls), S * sizeof(StreamCall)));
+  }
+  Decided d = decide(b, in_frames, out_frames, sl.h_calls);
+
+  const size_t dev_in_stride = round_up(static_cast<size_t>(d.max_n_in) * ch, 8);
+  const size_t dev_out_stride = round_up(static_cast<size_t>(d.max_n_out) * ch, 8);
+  if (int e = grow_device(&sl.d_in, &sl.d_in_cap, std::max<size_t>(dev_in_stride * S, 8))) return e;
+  if (int e = grow_device(&sl.d_out, &sl.d_out_cap, std::max<size_t>(dev_out_stride * S, 8))) return e;
+
+  sl.ticket = b->next_ticket++;
+  if (ticket) *ticket = sl.ticket;
+  sl.busy = true;
+  sl.bounce_out = false;
+  sl.user_out = nullptr;
+  sl.out_counts.clear();
+
+  if (!d.any_work) {
+    SPXB_CUDA(cudaEventRecord(sl.ev_done, b->s_out));
+    return 0;
+  }
+
+  // ---- H2D ----
+  const size_t in_row_bytes = static_cast<size_t>(d.max_n_in) * ch * sizeof(int16_t);
+  const bool direct_in = d.uniform && is_pinned_or_device(in);
+  if (direct_in) {
+    SPXB_CUDA(cudaMemcpy2DAsync(sl.d_in, dev_in_stride * sizeof(int16_t), in,
+                                in_stride_frames * ch * sizeof(int16_t), in_row_bytes, S,
+                                cudaMemcpyDefault, b->s_in));
+  } else {
+    if (int e = grow_pinned(&sl.h_in, &sl.h_in_cap, dev_in_stride * S)) return e;
+    for (uint32_t s = 0; s < S; ++s) {
+      const uint32_t n = offered_in.empty() ? offered_in0 : offered_in[s];
+      std::memcpy(sl.h_in + s * dev_in_stride, in + s * in_stride_frames * ch, n * ch * sizeof(int16_t));
+    }
+    SPXB_CUDA(cudaMemcpyAsync(sl.d_in, sl.h_in, dev_in_stride * S * sizeof(int16_t),
+                              cudaMemcpyHostToDevice, b->s_in));
+  }
+  b->counters.h2d_bytes += in_row_bytes * S;
+  if (!d.uniform) {
+    SPXB_CUDA(cudaMemcpyAsync(sl.d_calls, sl.h_calls, S * sizeof(StreamCall), cudaMemcpyHostToDevice, b->s_in));
+    b->counters.h2d_bytes += S * sizeof(StreamCall);
+  }
+  SPXB_CUDA(cudaEventRecord(sl.ev_h2d, b->s_in));
+
+  // ---- kernel ----
+  SPXB_CUDA(cudaStreamWaitEvent(b->s_compute, sl.ev_h2d, 0));
+  if (int e = launch_call(b, sl.d_in, dev_in_stride, sl.d_out, dev_out_stride,
+                          d.uniform ? nullptr : sl.d_calls, d.uni, d.max_n_out))
+    return e;
+  SPXB_CUDA(cudaEventRecord(sl.ev_kernel, b->s_compute));
+
+  // ---- D2H ----
+  SPXB_CUDA(cudaStreamWaitEvent(b->s_out, sl.ev_kernel, 0));
+  const size_t out_row_bytes = static_cast<size_t>(d.max_n_out) * ch * sizeof(int16_t);
+  if (d.max_n_out != 0) {
+    const bool direct_out = d.uniform && is_pinned_or_device(out);
+    if (direct_out) {
+      SPXB_CUDA(cudaMemcpy2DAsync(out, out_stride_frames * ch * sizeof(int16_t), sl.d_out,
+                                  dev_out_stride * sizeof(int16_t), out_row_bytes, S,
+                                  cudaMemcpyDefault, b->s_out));
+    } else {
+      if (int e = grow_pinned(&sl.h_out, &sl.h_out_cap, dev_out_stride * S)) return e;
+      SPXB_CUDA(cudaMemcpyAsync(sl.h_out, sl.d_out, dev_out_stride * S * sizeof(int16_t),
+                                cudaMemcpyDeviceToHost, b->s_out));
+      sl.bounce_out = true;
+      sl.user_out = out;
+      sl.user_out_stride = out_stride_frames * ch;
+      sl.dev_out_stride = dev_out_stride;
+      if (d.uniform)
+        sl.uniform_out = d.max_n_out;
+      else
+        sl.out_counts.assign(out_frames, out_frames + S);
+    }
+    b->counters.d2h_bytes += out_row_bytes * S;
+  }
+  SPXB_CUDA(cudaEventRecord(sl.ev_done, b->s_out));
+  b->counters.calls += 1;
+  return 0;
+}
+
+}  // namespace spxb
+
+// ---------------------------------------------------------------------------
+// C ABI, part 2 (batched streams)
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int spxb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char *spxb_last_error(void) { return g_last_error.c_str(); }
+
+const char *spxb_version(void) { return "speexb200 0.1 (sm_100a)"; }
+
+spxb_batch *spxb_batch_create(uint32_t n_streams, uint32_t channels, uint32_t in_rate,
+                              uint32_t out_rate, int quality, int device, int *err) {
+  int e = RESAMPLER_ERR_SUCCESS;
+  spxb_batch *b = nullptr;
+  FilterSpec spec;
+  if (n_streams == 0 || channels == 0) {
+    e = RESAMPLER_ERR_INVALID_ARG;
+  } else {
+    e = derive_filter_spec(in_rate, out_rate, quality, &spec);
+  }
+  if (e == 0) {
+    if (spxb_device_count() <= device || device < 0) {
+      set_error("no CUDA device " + std::to_string(device) + " (libspeexb200 has no CPU path)");
+      e = RESAMPLER_ERR_ALLOC_FAILED;
+    }
+  }
+  if (e == 0) {
+    b = new (std::nothrow) spxb_batch();
+    if (!b) {
+      e = RESAMPLER_ERR_ALLOC_FAILED;
+    } else {
+      b->device = device;
+      b->spec = spec;
+      b->n_streams = n_streams;
+      b->channels = channels;
+      int prev = -1;
+      cudaGetDevice(&prev);
+      e = create_batch(b);
+      if (prev >= 0) cudaSetDevice(prev);
+      if (e != 0) {
+        free_batch(b);
+        b = nullptr;
+      }
+    }
+  }
+  if (err) *err = e;
+  return b;
+}
+
+void spxb_batch_destroy(spxb_batch *b) { free_batch(b); }
+
+int spxb_batch_set_kernel(spxb_batch *b, int kernel) {
+  if (!b || kernel < SPXB_KERNEL_AUTO || kernel > SPXB_KERNEL_TILED) return RESAMPLER_ERR_INVALID_ARG;
+  b->kernel_pref = kernel;
+  return 0;
+}
+
+int spxb_batch_get_kernel(const spxb_batch *b) { return b ? b->last_kernel : 0; }
+
+int spxb_batch_pipeline_depth(const spxb_batch *) { return kPipelineDepth - 1; }
+
+int spxb_batch_submit(spxb_batch *b, const int16_t *in, size_t in_stride_frames, uint32_t *in_frames,
+                      int16_t *out, size_t out_stride_frames, uint32_t *out_frames,
+                      uint64_t *ticket) {
+  if (!b || !in_frames || !out_frames || !in || !out) return RESAMPLER_ERR_INVALID_ARG;
+  return submit_host(b, in, in_stride_frames, in_frames, out, out_stride_frames, out_frames, ticket);
+}
+
+int spxb_batch_wait(spxb_batch *b, uint64_t ticket) {
+  if (!b) return RESAMPLER_ERR_INVALID_ARG;
+  DeviceGuard g(b->device);
+  for (auto &sl : b->slots)
+    if (sl.busy && sl.ticket == ticket) return retire_slot(b, sl);
+  return 0;  // already retired
+}
+
+int spxb_batch_process(spxb_batch *b, const int16_t *in, size_t in_stride_frames, uint32_t *in_frames,
+                       int16_t *out, size_t out_stride_frames, uint32_t *out_frames) {
+  uint64_t t = 0;
+  int e = spxb_batch_submit(b, in, in_stride_frames, in_frames, out, out_stride_frames, out_frames, &t);
+  if (e) return e;
+  return spxb_batch_wait(b, t);
+}
+
+int spxb_batch_process_device(spxb_batch *b, const int16_t *d_in, size_t in_stride_frames,
+                              uint32_t *in_frames, int16_t *d_out, size_t out_stride_frames,
+                              uint32_t *out_frames) {
+  if (!b || !in_frames || !out_frames) return RESAMPLER_ERR_INVALID_ARG;
+  DeviceGuard g(b->device);
+  Slot &sl = b->slots[b->next_ticket % kPipelineDepth];
+  if (int e = retire_slot(b, sl)) return e;
+  const uint32_t S = b->n_streams;
+  if (!sl.h_calls) {
+    SPXB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_calls), S * sizeof(StreamCall), cudaHostAllocDefault));
+    SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&sl.d_calls), S * sizeof(StreamCall)));
+  }
+  Decided d = decide(b, in_frames, out_frames, sl.h_calls);
+  if (!d.any_work) return 0;
+  sl.ticket = b->next_ticket++;
+  if (!d.uniform) {
+    // the plan upload rides the compute stream so it is ordered before the kernel
+    SPXB_CUDA(cudaMemcpyAsync(sl.d_calls, sl.h_calls, S * sizeof(StreamCall), cudaMemcpyHostToDevice, b->s_compute));
+    b->counters.h2d_bytes += S * sizeof(StreamCall);
+    sl.busy = true;  // h_calls must outlive the async copy
+  }
+  int e = launch_call(b, d_in, in_stride_frames * b->channels, d_out, out_stride_frames * b->channels,
+                      d.uniform ? nullptr : sl.d_calls, d.uni, d.max_n_out);
+  if (e) return e;
+  if (!d.uniform) SPXB_CUDA(cudaEventRecord(sl.ev_done, b->s_compute));
+  b->counters.calls += 1;
+  return 0;
+}
+
+int spxb_batch_process_device_uniform(spxb_batch *b, const int16_t *d_in, size_t in_stride_frames,
+                                      uint32_t n_in, int16_t *d_out, size_t out_stride_frames,
+                                      uint32_t out_cap, uint32_t *in_used, uint32_t *out_written) {
+  if (!b) return RESAMPLER_ERR_INVALID_ARG;
+  if (!b->uniform_pos) {
+    set_error("process_device_uniform needs all streams at one position; use process_device");
+    return RESAMPLER_ERR_BAD_STATE;
+  }
+  DeviceGuard g(b->device);
+  Decided d = decide_uniform(b, n_in, out_cap);
+  if (in_used) *in_used = d.uni.consumed;
+  if (out_written) *out_written = d.uni.n_out;
+  if (!d.any_work) return 0;
+  int e = launch_call(b, d_in, in_stride_frames * b->channels, d_out, out_stride_frames * b->channels,
+                      nullptr, d.uni, d.max_n_out);
+  if (e) return e;
+  b->counters.calls += 1;
+  return 0;
+}
+
+int spxb_batch_set_stream(spxb_batch *b, void *cuda_stream) {
+  if (!b) return RESAMPLER_ERR_INVALID_ARG;
+  DeviceGuard g(b->device);
+  SPXB_CUDA(cudaStreamSynchronize(b->s_compute));
+  if (cuda_stream) {
+    b->s_compute = static_cast<cudaStream_t>(cuda_stream);
+    b->external_stream = true;
+  } else {
+    b->s_compute = b->s_own;
+    b->external_stream = false;
+  }
+  return 0;
+}
+
+int spxb_batch_synchronize(spxb_batch *b) {
+  if (!b) return RESAMPLER_ERR_INVALID_ARG;
+  DeviceGuard g(b->device);
+  for (auto &sl : b->slots)
+    if (int e = retire_slot(b, sl)) return e;
+  SPXB_CUDA(cudaStreamSynchronize(b->s_in));
+  SPXB_CUDA(cudaStreamSynchronize(b->s_compute));
+  SPXB_CUDA(cudaStreamSynchronize(b->s_out));
+  return 0;
+}
+
+int spxb_batch_get_state(spxb_batch *b, uint32_t stream, int32_t *last_sample, uint32_t *samp_frac_num,
+                         uint32_t *magic_samples, int16_t *history) {
+  if (!b || stream >= b->n_streams) return RESAMPLER_ERR_INVALID_ARG;
+  if (int e = spxb_batch_synchronize(b)) return e;
+  DeviceGuard g(b->device);
+  if (last_sample)
+    SPXB_CUDA(cudaMemcpy(last_sample, b->d_last_sample + stream, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (samp_frac_num)
+    SPXB_CUDA(cudaMemcpy(samp_frac_num, b->d_samp_frac + stream, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (magic_samples)
+    SPXB_CUDA(cudaMemcpy(magic_samples, b->d_magic + stream, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (history) {
+    const size_t live = static_cast<size_t>(b->spec.taps - 1) * b->channels;
+    const size_t lead = static_cast<size_t>(b->hist_frames - (b->spec.taps - 1)) * b->channels;
+    if (live)
+      SPXB_CUDA(cudaMemcpy(history, b->d_hist[b->hist_cur] + static_cast<size_t>(stream) * b->hist_stride + lead,
+                           live * sizeof(int16_t), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+int spxb_batch_set_state(spxb_batch *b, uint32_t stream, int32_t last_sample, uint32_t samp_frac_num,
+                         const int16_t *history) {
+  if (!b || stream >= b->n_streams || last_sample < 0 || samp_frac_num >= b->spec.den)
+    return RESAMPLER_ERR_INVALID_ARG;
+  if (int e = spxb_batch_synchronize(b)) return e;
+  DeviceGuard g(b->device);
+  SPXB_CUDA(cudaMemcpy(b->d_last_sample + stream, &last_sample, sizeof(int32_t), cudaMemcpyHostToDevice));
+  SPXB_CUDA(cudaMemcpy(b->d_samp_frac + stream, &samp_frac_num, sizeof(uint32_t), cudaMemcpyHostToDevice));
+  if (history) {
+    const size_t live = static_cast<size_t>(b->spec.taps - 1) * b->channels;
+    const size_t lead = static_cast<size_t>(b->hist_frames - (b->spec.taps - 1)) * b->channels;
+    if (live)
+      SPXB_CUDA(cudaMemcpy(b->d_hist[b->hist_cur] + static_cast<size_t>(stream) * b->hist_stride + lead, history,
+                           live * sizeof(int16_t), cudaMemcpyHostToDevice));
+  }
+  b->pos[stream].last_sample = last_sample;
+  b->pos[stream].samp_frac_num = samp_frac_num;
+  b->uniform_pos = true;
+  for (uint32_t s = 1; s < b->n_streams && b->uniform_pos; ++s)
+    b->uniform_pos = b->pos[s].last_sample == b->pos[0].last_sample &&
+                     b->pos[s].samp_frac_num == b->pos[0].samp_frac_num;
+  return 0;
+}
+
+int spxb_batch_reset(spxb_batch *b) {
+  if (!b) return RESAMPLER_ERR_INVALID_ARG;
+  if (int e = spxb_batch_synchronize(b)) return e;
+  DeviceGuard g(b->device);
+  const size_t hist_bytes = static_cast<size_t>(b->n_streams) * b->hist_stride * sizeof(int16_t);
+  SPXB_CUDA(cudaMemset(b->d_hist[b->hist_cur], 0, hist_bytes));
+  SPXB_CUDA(cudaMemset(b->d_last_sample, 0, b->n_streams * sizeof(int32_t)));
+  SPXB_CUDA(cudaMemset(b->d_samp_frac, 0, b->n_streams * sizeof(uint32_t)));
+  SPXB_CUDA(cudaMemset(b->d_magic, 0, b->n_streams * sizeof(uint32_t)));
+  SPXB_CUDA(cudaDeviceSynchronize());
+  b->pos.assign(b->n_streams, StreamPos{});
+  b->uniform_pos = true;
+  return 0;
+}
+
+int spxb_batch_skip_zeros(spxb_batch *b) {
+  if (!b) return RESAMPLER_ERR_INVALID_ARG;
+  if (int e = spxb_batch_synchronize(b)) return e;
+  DeviceGuard g(b->device);
+  std::vector<int32_t> ls(b->n_streams, static_cast<int32_t>(b->spec.taps / 2));
+  SPXB_CUDA(cudaMemcpy(b->d_last_sample, ls.data(), ls.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  for (auto &p : b->pos) p.last_sample = static_cast<int32_t>(b->spec.taps / 2);
+  return 0;
+}
+
+int spxb_batch_counters(const spxb_batch *b, spxb_counters *c) {
+  if (!b || !c) return RESAMPLER_ERR_INVALID_ARG;
+  *c = b->counters;
+  return 0;
+}
+
+void *spxb_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    set_error("cudaHostAlloc failed");
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void spxb_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------------------
+// C ABI, part 3 (host-only introspection)
+// ---------------------------------------------------------------------------
+int spxb_filter_describe(uint32_t in_rate, uint32_t out_rate, int quality, spxb_filter_info *info) {
+  if (!info) return RESAMPLER_ERR_INVALID_ARG;
+  FilterSpec s;
+  if (int e = derive_filter_spec(in_rate, out_rate, quality, &s)) return e;
+  info->num = s.num;
+  info->den = s.den;
+  info->filt_len = s.taps;
+  info->oversample = s.oversample;
+  info->int_advance = s.int_advance;
+  info->frac_advance = s.frac_advance;
+  info->cutoff = s.cutoff;
+  info->use_direct = s.direct;
+  info->use_double = s.wide_accum;
+  info->table_len = s.table_len;
+  return 0;
+}
+
+long spxb_filter_table(uint32_t in_rate, uint32_t out_rate, int quality, float *dst, size_t cap) {
+  FilterSpec s;
+  if (int e = derive_filter_spec(in_rate, out_rate, quality, &s)) return -e;
+  if (!dst || cap < s.table_len) return -RESAMPLER_ERR_INVALID_ARG;
+  std::vector<float> t = build_reference_table(s);
+  std::memcpy(dst, t.data(), t.size() * sizeof(float));
+  return static_cast<long>(t.size());
+}
+
+long spxb_filter_phase_taps(uint32_t in_rate, uint32_t out_rate, int quality, float *dst, size_t cap) {
+  FilterSpec s;
+  if (int e = derive_filter_spec(in_rate, out_rate, quality, &s)) return -e;
+  const size_t n = static_cast<size_t>(s.den) * s.taps;
+  if (!dst || cap < n) return -RESAMPLER_ERR_INVALID_ARG;
+  std::vector<float> t = build_phase_taps(s, build_reference_table(s));
+  std::memcpy(dst, t.data(), n * sizeof(float));
+  return static_cast<long>(n);
+}
+
+int spxb_plan_call(uint32_t in_rate, uint32_t out_rate, int32_t last_sample, uint32_t samp_frac_num,
+                   uint32_t n_in, uint32_t out_cap, spxb_call_plan *plan) {
+  if (!plan || in_rate == 0 || out_rate == 0 || last_sample < 0) return RESAMPLER_ERR_INVALID_ARG;
+  FilterSpec s;
+  if (int e = derive_filter_spec(in_rate, out_rate, 0, &s)) return e;
+  if (samp_frac_num >= s.den) return RESAMPLER_ERR_INVALID_ARG;
+  StreamPos p;
+  p.last_sample = last_sample;
+  p.samp_frac_num = samp_frac_num;
+  const CallPlan pl = plan_call(s.num, s.den, p, n_in, out_cap);
+  plan->n_out = pl.n_out;
+  plan->consumed = pl.consumed;
+  plan->last_sample = pl.next.last_sample;
+  plan->samp_frac_num = pl.next.samp_frac_num;
+  return 0;
+}
+
+}  // extern "C"
+
+// exposed to capi.cpp
+namespace spxb {
+const FilterSpec &batch_spec(const spxb_batch *b) { return b->spec; }
+}

@@ -1,0 +1,116 @@
+// capi.cu -- the five symbols the reference's WASM exports (scripts/build_emscripten.sh:20,
+// bound at src/index.ts:6-16) plus the read-only rest of deps/speex/speex_resampler.h, each
+// implemented over a one-stream device batch. Same signatures, length conventions and error
+// codes as deps/speex/resample.c; the arithmetic runs on the GPU (no CPU path).
+#include <cstdint>
+#include <new>
+#include <vector>
+
+#include "../../include/speexb200.h"
+#include "filter_bank.h"
+
+namespace spxb {
+const FilterSpec &batch_spec(const spxb_batch *b);
+}
+
+struct SpeexResamplerState_ {
+  spxb_batch *batch = nullptr;
+  uint32_t in_rate = 0, out_rate = 0, channels = 0;
+  int quality = 0;
+  std::vector<int16_t> silence;  // stands in for in == NULL (resample.c:1007-1010)
+};
+
+extern "C" {
+
+SpeexResamplerState *speex_resampler_init(uint32_t nb_channels, uint32_t in_rate, uint32_t out_rate,
+                                          int quality, int *err) {
+  // resample.c:804-809: argument check precedes any allocation
+  if (nb_channels == 0 || in_rate == 0 || out_rate == 0 || quality > 10 || quality < 0) {
+    if (err) *err = RESAMPLER_ERR_INVALID_ARG;
+    return nullptr;
+  }
+  SpeexResamplerState *st = new (std::nothrow) SpeexResamplerState_();
+  if (!st) {
+    if (err) *err = RESAMPLER_ERR_ALLOC_FAILED;
+    return nullptr;
+  }
+  int e = 0;
+  int device = 0;
+  st->batch = spxb_batch_create(1, nb_channels, in_rate, out_rate, quality, device, &e);
+  if (!st->batch) {
+    delete st;
+    if (err) *err = e ? e : RESAMPLER_ERR_ALLOC_FAILED;
+    return nullptr;
+  }
+  st->in_rate = in_rate;
+  st->out_rate = out_rate;
+  st->channels = nb_channels;
+  st->quality = quality;
+  if (err) *err = RESAMPLER_ERR_SUCCESS;
+  return st;
+}
+
+void speex_resampler_destroy(SpeexResamplerState *st) {
+  if (!st) return;
+  spxb_batch_destroy(st->batch);
+  delete st;
+}
+
+void speex_resampler_get_rate(SpeexResamplerState *st, uint32_t *in_rate, uint32_t *out_rate) {
+  *in_rate = st->in_rate;
+  *out_rate = st->out_rate;
+}
+
+void speex_resampler_get_ratio(SpeexResamplerState *st, uint32_t *ratio_num, uint32_t *ratio_den) {
+  const spxb::FilterSpec &s = spxb::batch_spec(st->batch);
+  *ratio_num = s.num;
+  *ratio_den = s.den;
+}
+
+void speex_resampler_get_quality(SpeexResamplerState *st, int *quality) { *quality = st->quality; }
+
+int speex_resampler_get_input_latency(SpeexResamplerState *st) {
+  return static_cast<int>(spxb::batch_spec(st->batch).taps / 2);
+}
+
+int speex_resampler_get_output_latency(SpeexResamplerState *st) {
+  const spxb::FilterSpec &s = spxb::batch_spec(st->batch);
+  return static_cast<int>(((s.taps / 2) * s.den + (s.num >> 1)) / s.num);
+}
+
+int speex_resampler_skip_zeros(SpeexResamplerState *st) { return spxb_batch_skip_zeros(st->batch); }
+
+int speex_resampler_reset_mem(SpeexResamplerState *st) { return spxb_batch_reset(st->batch); }
+
+int speex_resampler_process_interleaved_int(SpeexResamplerState *st, const int16_t *in, uint32_t *in_len,
+                                            int16_t *out, uint32_t *out_len) {
+  if (!st || !in_len || !out_len || !out) return RESAMPLER_ERR_INVALID_ARG;
+  if (!in) {
+    st->silence.assign(static_cast<size_t>(*in_len) * st->channels, 0);
+    in = st->silence.data();
+  }
+  // one stream: the strides are irrelevant, the lengths are the in-out cells
+  return spxb_batch_process(st->batch, in, *in_len, in_len, out, *out_len, out_len);
+}
+
+spxb_batch *spxb_resampler_batch(SpeexResamplerState *st) { return st ? st->batch : nullptr; }
+
+const char *speex_resampler_strerror(int err) {
+  // resample.c:1222-1239: five texts and a default (code 5 has no text of its own there)
+  switch (err) {
+    case RESAMPLER_ERR_SUCCESS:
+      return "Success.";
+    case RESAMPLER_ERR_ALLOC_FAILED:
+      return "Memory allocation failed.";
+    case RESAMPLER_ERR_BAD_STATE:
+      return "Bad resampler state.";
+    case RESAMPLER_ERR_INVALID_ARG:
+      return "Invalid argument.";
+    case RESAMPLER_ERR_PTR_OVERLAP:
+      return "Input and output buffers overlap.";
+    default:
+      return "Unknown error. Bad error code or strange version mismatch.";
+  }
+}
+
+}  // extern "C"

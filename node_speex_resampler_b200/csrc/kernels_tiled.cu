@@ -1,0 +1,401 @@
+// kernels_tiled.cu -- register-tiled polyphase FIR for sm_100a (FP32 FMA pipe).
+//
+// The whole path  int16 de-interleave -> per-phase FIR -> WORD2INT -> re-interleave  of
+// speex_resampler_process_interleaved_int (deps/speex/resample.c:1061-1082 over :968-1036
+// and the four resampler_basic_* kernels :331-558) in one launch, for a batch of streams at a
+// common stream position. Both reference table shapes collapse to one form: every output
+// phase has its own N-tap FIR h[phase][j] (the direct table as is; for the interpolating
+// path the cubic blend of :467-476 folded into the taps on the host), so
+//      y(m) = sum_j h[phase(m)][j] * X~[q(m) + j].
+//
+// Work decomposition (a banded GEMM, outputs x series):
+//   CTA   = TM = 8*TR consecutive outputs  x  TS = 32*CW series (series = stream x channel)
+//   warp  = one row-tile of 8 consecutive outputs x all TS series
+//   lane  = CW series, 8 outputs  -> 8 x CW accumulators, fp32
+// Shared memory:
+//   Bs [TS][Wp]   f32  the input windows of the CTA's series, time-major, converted from
+//                      int16 once (history for f < 0, this call's input for f >= 0);
+//                      Wp % 8 == 4 so the 8 lanes of a quarter-warp hit distinct bank quads
+//   As [TR][8][Kp] f32 the row-tile's taps, each row pre-shifted so that column k of every row
+//                      multiplies window sample (a0 + k): As[r][k] = h[phase_r][a0 + k - q_r]
+//                      (0 outside the band); a0 = q_0 rounded down to 4 so that both operands
+//                      are read with 128-bit loads along k
+// Inner loop per 4 k: 8 LDS.128 (taps, warp-broadcast) + CW LDS.128 (window) : 32*CW FFMA.
+// Epilogue: WORD2INT (arch.h:208-209) and 16-byte interleaved int16 stores.
+// The history slide (resample.c:898-899) and the new (last_sample, samp_frac_num) are written
+// by extra blocks of the same grid into the other half of the history ping-pong.
+#include <cstdlib>
+
+#include "kernels_common.cuh"
+#include "launch.h"
+
+namespace spxb {
+
+namespace {
+
+constexpr int kRows = 8;  // outputs per thread
+
+struct TileGeom {
+  uint32_t n_sg;        // series groups
+  uint32_t n_rg;        // row groups
+  uint32_t fir_blocks;  // n_sg * n_rg
+  uint32_t Kp;          // padded taps per row (multiple of 4)
+  uint32_t Wp;          // padded window per series (Wp % 8 == 4)
+};
+
+__device__ __forceinline__ float s16lo(uint32_t w) { return static_cast<float>(static_cast<short>(w & 0xffffu)); }
+__device__ __forceinline__ float s16hi(uint32_t w) { return static_cast<float>(static_cast<int>(w) >> 16); }
+
+template <int CH, int CW, int TR>
+__global__ void __launch_bounds__(TR * 32)
+    tiled_fir_kernel(const CallArgs a, const TileGeom g) {
+  constexpr int NT = TR * 32;
+  constexpr int TS = 32 * CW;        // series per CTA
+  constexpr int TM = kRows * TR;     // outputs per CTA
+  if (blockIdx.x >= g.fir_blocks) {
+    history_block(a, blockIdx.x - g.fir_blocks);
+    return;
+  }
+  extern __shared__ __align__(16) float smem[];
+  float *Bs = smem;
+  float *As = smem + static_cast<size_t>(TS) * g.Wp;
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t sg = blockIdx.x % g.n_sg;
+  const uint32_t rg = blockIdx.x / g.n_sg;
+  const StreamCall sc = a.uniform;
+  const int N = static_cast<int>(a.filt.taps);
+  const uint32_t num = a.filt.num, den = a.filt.den;
+  const uint32_t M0 = rg * TM;
+  const int Wp = static_cast<int>(g.Wp), Kp = static_cast<int>(g.Kp);
+
+  // first frame of output m's window in X~ coordinates
+  auto window_start = [&](uint32_t m, uint32_t *phase) -> int {
+    const unsigned long long t = static_cast<unsigned long long>(sc.frac0) +
+                                 static_cast<unsigned long long>(m) * num;
+    if (phase) *phase = static_cast<uint32_t>(t % den);
+    return sc.ls0 - (N - 1) + static_cast<int>(t / den);
+  };
+  const int W0 = window_start(M0, nullptr) & ~3;
+
+  // ---- stage the windows: int16 (HBM) -> f32 (shared), 4 frames per item ----
+  {
+    const int G4 = Wp >> 2;
+    constexpr int kStreams = TS / CH;  // streams per CTA
+    const int items = kStreams * G4;
+    const int hist_frames = static_cast<int>(a.hist_frames);
+    for (int id = tid; id < items; id += NT) {
+      const int sl = id / G4;
+      const int g4 = id - sl * G4;
+      const int f = W0 + 4 * g4;
+      const uint32_t s = sg * kStreams + sl;
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (s < a.n_streams) {
+        const int16_t *src = nullptr;
+        int avail = 0;  // frames readable from src
+        if (f < 0) {
+          const int hf = f + hist_frames;
+          if (hf >= 0) {
+            src = a.hist_src + static_cast<size_t>(s) * a.hist_stride + static_cast<size_t>(hf) * CH;
+            avail = 4;
+          }
+        } else if (static_cast<uint32_t>(f) < sc.n_in) {
+          src = a.in + static_cast<size_t>(s) * a.in_stride + static_cast<size_t>(f) * CH;
+          avail = min(4, static_cast<int>(sc.n_in) - f);
+        }
+        if (avail == 4) {
+          if (CH == 2) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(src));
+            v0 = make_float4(s16lo(raw.x), s16lo(raw.y), s16lo(raw.z), s16lo(raw.w));
+            v1 = make_float4(s16hi(raw.x), s16hi(raw.y), s16hi(raw.z), s16hi(raw.w));
+          } else {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(src));
+            v0 = make_float4(s16lo(raw.x), s16hi(raw.x), s16lo(raw.y), s16hi(raw.y));
+          }
+        } else if (avail > 0) {
+          float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int i = 0; i < avail; ++i) {
+            t0[i] = static_cast<float>(src[i * CH]);
+            if (CH == 2) t1[i] = static_cast<float>(src[i * CH + 1]);
+          }
+          v0 = make_float4(t0[0], t0[1], t0[2], t0[3]);
+          v1 = make_float4(t1[0], t1[1], t1[2], t1[3]);
+        }
+      }
+      // shared row of (stream sl, channel c): lane = sl % 32, thread column = CH*(sl/32) + c
+      const int rho = (sl & 31) + 32 * CH * (sl >> 5);
+      *reinterpret_cast<float4 *>(Bs + static_cast<size_t>(rho) * Wp + 4 * g4) = v0;
+      if (CH == 2) *reinterpret_cast<float4 *>(Bs + static_cast<size_t>(rho + 32) * Wp + 4 * g4) = v1;
+    }
+  }
+
+  // ---- build this warp's pre-shifted tap tile ----
+  float *Aw = As + static_cast<size_t>(w) * kRows * Kp;
+  const uint32_t m0 = M0 + kRows * w;
+  int q_mine;
+  uint32_t ph_mine;
+  q_mine = window_start(m0 + (lane & 7), &ph_mine);
+  const int a0 = __shfl_sync(0xffffffffu, q_mine, 0) & ~3;
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    const int q_r = __shfl_sync(0xffffffffu, q_mine, r);
+    const uint32_t ph_r = __shfl_sync(0xffffffffu, ph_mine, r);
+    const float *hrow = a.filt.phase_taps + static_cast<size_t>(ph_r) * N;
+    const int shift = a0 - q_r;  // tap index = k + shift
+    for (int k = lane; k < Kp; k += 32) {
+      const int j = k + shift;
+      Aw[r * Kp + k] = (j >= 0 && j < N) ? __ldg(hrow + j) : 0.f;
+    }
+  }
+  __syncthreads();
+  if (m0 >= sc.n_out) return;  // row tile past the end of the call (no barrier follows)
+
+  // ---- the contraction ----
+  float acc[kRows][CW];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r)
+#pragma unroll
+    for (int i = 0; i < CW; ++i) acc[r][i] = 0.f;
+
+  const float4 *A4 = reinterpret_cast<const float4 *>(Aw);
+  const int K4 = Kp >> 2;
+  const float4 *B4[CW];
+#pragma unroll
+  for (int i = 0; i < CW; ++i)
+    B4[i] = reinterpret_cast<const float4 *>(Bs + static_cast<size_t>(lane + 32 * i) * Wp + (a0 - W0));
+
+#pragma unroll 2
+  for (int kk = 0; kk < K4; ++kk) {
+    float4 b[CW];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) b[i] = B4[i][kk];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const float4 av = A4[r * K4 + kk];
+#pragma unroll
+      for (int i = 0; i < CW; ++i) {
+        acc[r][i] = fmaf(av.x, b[i].x, acc[r][i]);
+        acc[r][i] = fmaf(av.y, b[i].y, acc[r][i]);
+        acc[r][i] = fmaf(av.z, b[i].z, acc[r][i]);
+        acc[r][i] = fmaf(av.w, b[i].w, acc[r][i]);
+      }
+    }
+  }
+
+  // ---- WORD2INT + interleaved store ----
+  const bool full_rows = m0 + kRows <= sc.n_out;
+  const bool vec_ok = (a.out_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+  if (CH == 2) {
+#pragma unroll
+    for (int j = 0; j < CW / 2; ++j) {
+      const uint32_t s = sg * (TS / 2) + lane + 32 * j;
+      if (s >= a.n_streams) continue;
+      int16_t *dst = a.out + static_cast<size_t>(s) * a.out_stride + static_cast<size_t>(m0) * 2;
+      uint32_t pk[kRows];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const uint32_t lo = static_cast<uint32_t>(word2int_fast(acc[r][2 * j])) & 0xffffu;
+        const uint32_t hi = static_cast<uint32_t>(word2int_fast(acc[r][2 * j + 1])) << 16;
+        pk[r] = lo | hi;
+      }
+      if (full_rows && vec_ok) {
+        reinterpret_cast<uint4 *>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        reinterpret_cast<uint4 *>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+          if (m0 + r < sc.n_out) reinterpret_cast<uint32_t *>(dst)[r] = pk[r];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      const uint32_t s = sg * TS + lane + 32 * i;
+      if (s >= a.n_streams) continue;
+      int16_t *dst = a.out + static_cast<size_t>(s) * a.out_stride + m0;
+      uint32_t pk[kRows / 2];
+#pragma unroll
+      for (int r = 0; r < kRows; r += 2) {
+        const uint32_t lo = static_cast<uint32_t>(word2int_fast(acc[r][i])) & 0xffffu;
+        const uint32_t hi = static_cast<uint32_t>(word2int_fast(acc[r + 1][i])) << 16;
+        pk[r / 2] = lo | hi;
+      }
+      if (full_rows && vec_ok) {
+        reinterpret_cast<uint4 *>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+          if (m0 + r < sc.n_out)
+            dst[r] = static_cast<int16_t>((r & 1) ? (pk[r / 2] >> 16) : (pk[r / 2] & 0xffffu));
+      }
+    }
+  }
+}
+
+// largest advance of the window start over n outputs
+inline uint32_t max_advance(uint32_t n, uint32_t num, uint32_t den) {
+  return static_cast<uint32_t>((static_cast<uint64_t>(n) * num + den - 1) / den);
+}
+
+inline uint32_t round_up_u32(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+template <int CH, int CW, int TR>
+cudaError_t launch_one(const CallArgs &a, const TileGeom &g, uint32_t smem, cudaStream_t stream) {
+  auto kern = tiled_fir_kernel<CH, CW, TR>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  const uint32_t total = g.fir_blocks + hist_blocks(a, TR * 32);
+  kern<<<total, TR * 32, smem, stream>>>(a, g);
+  return cudaGetLastError();
+}
+
+constexpr int kCW = 4;
+constexpr uint32_t kMaxSmem = 227 * 1024;
+
+// geometry for a given number of row tiles per CTA
+bool geometry(const CallArgs &a, int TR, TileGeom *g, uint32_t *smem) {
+  const uint32_t N = a.filt.taps, num = a.filt.num, den = a.filt.den;
+  const uint32_t TS = 32 * kCW, TM = kRows * TR;
+  const uint32_t n_series = a.n_streams * a.channels;
+  g->Kp = round_up_u32(3 + max_advance(kRows - 1, num, den) + N, 4);
+  uint32_t wp = 3 + max_advance(kRows * (TR - 1), num, den) + g->Kp;
+  wp = round_up_u32(wp, 4);
+  if (wp % 8 != 4) wp += 4;
+  g->Wp = wp;
+  g->n_sg = (n_series + TS - 1) / TS;
+  g->n_rg = (a.uniform.n_out + TM - 1) / TM;
+  const uint64_t blocks = static_cast<uint64_t>(g->n_sg) * g->n_rg;
+  if (blocks > 0x3fffffffull) return false;
+  g->fir_blocks = static_cast<uint32_t>(blocks);
+  const uint64_t bytes = (static_cast<uint64_t>(TS) * g->Wp + static_cast<uint64_t>(TR) * kRows * g->Kp) * 4;
+  if (bytes > kMaxSmem) return false;
+  *smem = static_cast<uint32_t>(bytes);
+  return true;
+}
+
+}  // namespace
+
+cudaError_t tiled_prepare_device() { return cudaSuccess; }
+
+bool tiled_qualifies(const CallArgs &a, int sm_count, TiledConfig *cfg) {
+  if (a.per_stream != nullptr) return false;          // ragged positions -> strict kernel
+  if (a.channels != 1 && a.channels != 2) return false;
+  if (a.filt.phase_taps == nullptr) return false;
+  if (a.uniform.n_out == 0) return false;
+  // 16-byte loads of the input and history
+  if ((reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || a.in_stride % 8 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(a.hist_src) & 15) != 0 || a.hist_stride % 8 != 0) return false;
+  // window positions are handled as int: keep them small enough
+  if (a.uniform.n_in > 0x3fffffffu || a.filt.taps > 4096) return false;
+  // Row tiles per CTA: 4 when two such CTAs fit one SM (8 warps per SM, finer tail), else
+  // the largest shape that fits shared memory. SPXB_TILED_TR overrides (tuning).
+  static const int forced = [] {
+    const char *e = getenv("SPXB_TILED_TR");
+    return e ? atoi(e) : 0;
+  }();
+  (void)sm_count;
+  const int options[3] = {4, 8, 2};
+  int best = -1;
+  TileGeom g;
+  uint32_t smem = 0;
+  for (int i = 0; i < 3 && best < 0; ++i) {
+    if (forced && options[i] != forced) continue;
+    TileGeom gi;
+    uint32_t si;
+    if (!geometry(a, options[i], &gi, &si)) continue;
+    if (!forced && options[i] == 4 && si > kMaxSmem / 2) continue;  // would drop to 1 CTA per SM
+    best = options[i];
+    g = gi;
+    smem = si;
+  }
+  if (best < 0 && !forced) {  // TR=4 alone on an SM as the last resort
+    TileGeom gi;
+    uint32_t si;
+    if (geometry(a, 4, &gi, &si)) {
+      best = 4;
+      g = gi;
+      smem = si;
+    }
+  }
+  if (best < 0) return false;
+  cfg->variant = best;
+  cfg->smem_bytes = smem;
+  cfg->grid = g.fir_blocks;
+  return true;
+}
+
+cudaError_t launch_tiled(const CallArgs &a, const TiledConfig &cfg, cudaStream_t stream, uint32_t *launches) {
+  TileGeom g;
+  uint32_t smem = 0;
+  if (!geometry(a, cfg.variant, &g, &smem)) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaErrorInvalidConfiguration;
+  if (a.channels == 2) {
+    if (cfg.variant == 8) e = launch_one<2, kCW, 8>(a, g, smem, stream);
+    if (cfg.variant == 4) e = launch_one<2, kCW, 4>(a, g, smem, stream);
+    if (cfg.variant == 2) e = launch_one<2, kCW, 2>(a, g, smem, stream);
+  } else {
+    if (cfg.variant == 8) e = launch_one<1, kCW, 8>(a, g, smem, stream);
+    if (cfg.variant == 4) e = launch_one<1, kCW, 4>(a, g, smem, stream);
+    if (cfg.variant == 2) e = launch_one<1, kCW, 2>(a, g, smem, stream);
+  }
+  if (e == cudaSuccess && launches) *launches += 1;
+  return e;
+}
+
+// ---------------------------------------------------------------------------
+// FP32 peak probe: 8 independent FMA chains per thread, register resident
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float *sink, int iters, float seed) {
+  float x0 = seed + threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+  float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+  const float m = 0.999999f, c = 1e-7f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fmaf(x0, m, c); x1 = fmaf(x1, m, c); x2 = fmaf(x2, m, c); x3 = fmaf(x3, m, c);
+      x4 = fmaf(x4, m, c); x5 = fmaf(x5, m, c); x6 = fmaf(x6, m, c); x7 = fmaf(x7, m, c);
+    }
+  }
+  const float r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (r == 123.456f) sink[0] = r;  // keep the chains alive
+}
+}  // namespace
+
+double measure_fp32_peak_flops(int iters) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  float *sink = nullptr;
+  if (cudaMalloc(&sink, 4) != cudaSuccess) return 0.0;
+  const int blocks = sms * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  ffma_probe_kernel<<<blocks, threads>>>(sink, 64, 1.f);  // warm-up
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  ffma_probe_kernel<<<blocks, threads>>>(sink, iters, 1.f);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  if (ms <= 0.f) return 0.0;
+  const double fmas = static_cast<double>(blocks) * threads * static_cast<double>(iters) * 16.0 * 8.0;
+  return 2.0 * fmas / (ms * 1e-3);
+}
+
+}  // namespace spxb
+
+extern "C" __attribute__((visibility("default"))) double spxb_measure_fp32_peak(int iters) {
+  return spxb::measure_fp32_peak_flops(iters > 0 ? iters : 4096);
+}

@@ -1,0 +1,158 @@
+"""CPU-side checks of the shipped library's host logic (no kernel runs here): the C ABI
+loads and exports what include/speexb200.h declares, the filter bank is bit-identical to
+the oracle's, the call planner reproduces the reference's consumed/written/state walk, and
+the error behaviour of the reference wrapper is mirrored."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cases import GOLDEN_CHUNKS, MATRIX, case_id
+from node_speex_resampler_b200 import SpeexResampler, _lib, lib
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VEC = np.load(os.path.join(ROOT, "tests", "golden", "vectors.npz"))
+EXTRA = [(1, 44100, 8000, 6, ""), (1, 8000, 44100, 9, ""), (2, 48000, 48000, 10, ""),
+         (1, 192000, 8000, 5, ""), (1, 8000, 192000, 4, ""), (1, 32000, 48000, 2, ""),
+         (1, 1000, 300000, 3, ""), (1, 300000, 1000, 3, "")]
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "speexb200.h")).read()
+    declared = set(re.findall(r"^SPXB_API[^;(]*?\b(\w+)\s*\(", hdr, flags=re.M))
+    assert declared == set(_lib.DECLARED_SYMBOLS), declared ^ set(_lib.DECLARED_SYMBOLS)
+    L = lib()
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert b"sm_100a" in L.spxb_version()
+
+
+def test_strerror_texts_match_reference():
+    # deps/speex/resample.c:1222-1239 (code 5 has no case there -> default text)
+    want = {0: "Success.", 1: "Memory allocation failed.", 2: "Bad resampler state.",
+            3: "Invalid argument.", 4: "Input and output buffers overlap.",
+            5: "Unknown error. Bad error code or strange version mismatch.",
+            77: "Unknown error. Bad error code or strange version mismatch."}
+    for k, v in want.items():
+        assert _lib.strerror(k) == v
+
+
+@pytest.mark.parametrize("args", [(0, 44100, 48000, 7), (2, 0, 48000, 7), (2, 44100, 0, 7),
+                                  (2, 44100, 48000, 11), (2, 44100, 48000, -1)])
+def test_init_rejects_bad_arguments_like_reference(args):
+    # resample.c:804-809 -> NULL + RESAMPLER_ERR_INVALID_ARG, before any allocation
+    err = C.c_int(-1)
+    assert not lib().speex_resampler_init(*args, C.byref(err))
+    assert err.value == 3
+    r = SpeexResampler(*args)
+    if args[0] == 0:  # JS: length % 0 is NaN -> the chunk-length check throws first
+        with pytest.raises(ValueError, match="Chunk length"):
+            r.processChunk(b"\0" * 4)
+        return
+    with pytest.raises(RuntimeError, match="Invalid argument."):
+        r.processChunk(b"\0" * (4 * args[0]))
+    assert not r._resamplerPtr  # index.ts:61-65: stays falsy, next call retries
+
+
+def test_misaligned_chunk_message():
+    r = SpeexResampler(2, 44100, 48000)
+    with pytest.raises(ValueError, match="Chunk length should be a multiple of channels \\* 2 bytes"):
+        r.processChunk(b"\0" * 6)
+
+
+@pytest.mark.parametrize("c", MATRIX + EXTRA, ids=case_id)
+def test_filter_bank_bit_identical_to_oracle(c):
+    ch, i, o, q, _ = c
+    ref = O.OracleResampler(ch, i, o, q)
+    p = ref.params
+    info = _lib.FilterInfo()
+    assert lib().spxb_filter_describe(i, o, q, C.byref(info)) == 0
+    for f in ("num", "den", "filt_len", "oversample", "int_advance", "frac_advance", "use_direct",
+              "use_double", "table_len"):
+        assert getattr(info, f) == getattr(p, f), f
+    assert info.cutoff == p.cutoff
+    t = np.empty(info.table_len, dtype=np.float32)
+    assert lib().spxb_filter_table(i, o, q, t.ctypes.data, t.size) == t.size
+    assert np.array_equal(t.view(np.uint32), ref.table().view(np.uint32))
+
+
+def phase_taps(i, o, q):
+    info = _lib.FilterInfo()
+    lib().spxb_filter_describe(i, o, q, C.byref(info))
+    h = np.empty(info.den * info.filt_len, dtype=np.float32)
+    assert lib().spxb_filter_phase_taps(i, o, q, h.ctypes.data, h.size) == h.size
+    return info, h.reshape(info.den, info.filt_len)
+
+
+@pytest.mark.parametrize("c", MATRIX[:19] + MATRIX[20:22], ids=case_id)
+def test_phase_taps_reproduce_golden_within_one_lsb(c):
+    """The per-phase formulation the tiled kernel contracts with (cubic blend folded into the
+    taps) evaluated here in numpy f64 on the first golden chunk: must land within 1 LSB of
+    the reference build's output. (A test-side evaluation, not a product code path.)"""
+    ch, i, o, q, _ = c
+    info, h = phase_taps(i, o, q)
+    key = case_id(c)
+    n = GOLDEN_CHUNKS[0]
+    x = VEC[key + "/in"][0][: n * ch].reshape(n, ch).astype(np.float64)
+    n_out = int(VEC[key + "/lens"][0][0])
+    want = VEC[key + "/out0"][: n_out * ch].reshape(n_out, ch)
+    N = info.filt_len
+    X = np.vstack([np.zeros((N - 1, ch)), x, np.zeros((N, ch))])
+    m = np.arange(n_out, dtype=np.int64)
+    t = m * info.num
+    p, ph = t // info.den, t % info.den
+    idx = p[:, None] + np.arange(N)[None, :]
+    y = np.einsum("mj,mjc->mc", h[ph].astype(np.float64), X[idx])
+    got = np.clip(np.floor(y + 0.5), -32768, 32767).astype(np.int64)
+    assert np.max(np.abs(got - want.astype(np.int64))) <= 1
+    assert O.snr_db(want, got) >= 90.0
+
+
+def plan(i, o, ls, fr, n_in, cap):
+    pl = _lib.CallPlan()
+    assert lib().spxb_plan_call(i, o, ls, fr, n_in, cap, C.byref(pl)) == 0
+    return pl
+
+
+@pytest.mark.parametrize("c", MATRIX + EXTRA, ids=case_id)
+def test_call_planner_walks_like_the_reference(c):
+    """Chain spxb_plan_call against the oracle actually processing samples: consumed,
+    written and the (last_sample, samp_frac_num) after every call must agree, including
+    calls whose output capacity binds and ratios whose read position jumps whole blocks."""
+    ch, i, o, q, _ = c
+    ref = O.OracleResampler(1, i, o, q)
+    rng = np.random.default_rng(hash((i, o, q)) & 0xFFFF)
+    ls, fr = 0, 0
+    ratio = o / i
+    for step in range(60):
+        n_in = int(rng.choice([0, 1, 7, 159, 160, 161, 320, 441, 882, 1000, 2047]))
+        mode = step % 4
+        natural = int(np.ceil(n_in * ratio))
+        cap = [natural + 8, max(natural - int(rng.integers(0, 5)), 0), int(rng.integers(0, 40)),
+               natural][mode]
+        if ratio > 8:  # keep the oracle's work bounded for extreme up-sampling
+            n_in = min(n_in, 320)
+            cap = min(cap, 5000)
+        x = rng.integers(-2000, 2000, size=n_in, dtype=np.int16)
+        _, used, made = ref.process(x, cap)
+        pl = plan(i, o, ls, fr, n_in, cap)
+        assert (pl.consumed, pl.n_out) == (used, made), (step, n_in, cap, ls, fr)
+        ls_ref, fr_ref, _ = ref.state(0)
+        assert (pl.last_sample, pl.samp_frac_num) == (ls_ref, fr_ref), (step, n_in, cap)
+        ls, fr = pl.last_sample, pl.samp_frac_num
+
+
+def test_no_gpu_fails_loudly_not_silently():
+    if lib().spxb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    err = C.c_int(0)
+    assert not lib().speex_resampler_init(2, 44100, 48000, 7, C.byref(err))
+    assert err.value == 1
+    assert b"no CUDA device" in lib().spxb_last_error()
+    with pytest.raises(RuntimeError, match="Memory allocation failed"):
+        SpeexResampler(2, 44100, 48000).processChunk(b"\0" * 8)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        SpeexResampler.initPromise.result()
