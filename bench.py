@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Speex resampler hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload C3|C4|C5] [--kernel auto|strict|tiled]
+
+One step = one 20 ms processChunk-equivalent for every stream of the batch (state carried
+step to step). Workload (BASELINE.json): C3 = 1024 stereo streams 44100->48000 q7 per GPU
+(the configuration the headline metric is quoted on), C4 = 4096 mono 48000->16000 q10,
+C5 = 8192 stereo 96000->44100 q10 per GPU (65536 over 8). Streams are independent, so with
+N GPUs every rank owns its own streams (weak scaling, no collective on the data path).
+
+Prints ONE JSON line (rank 0):
+  value      output Msamples/s, inputs already in HBM (hops queued in a ring > L2)
+  e2e        same metric through the C ABI with pinned HOST buffers: H2D + kernel + D2H
+             every step, pipelined with spxb_batch_submit / spxb_batch_wait
+  roofline   FP32-FMA roofline of the FIR kernel (algorithmic 2*N flops per output sample,
+             SURVEY 8d) against an FFMA probe measured in this run; HBM fraction beside it
+  cpu_baseline  the reference's own C (oracle/_ref, kind "reference") or the oracle port on
+             this box's host cores, bounded sample of the same workload
+
+--impl reference times that CPU implementation on the same config instead (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (streams per GPU, channels, in_rate, out_rate, quality, frames in per 20 ms step)
+    "C3": (1024, 2, 44100, 48000, 7, 882),
+    "C4": (4096, 1, 48000, 16000, 10, 960),
+    "C5": (8192, 2, 96000, 44100, 10, 1920),
+}
+L2_BYTES = 126 * 1024 * 1024
+
+
+def describe(wl):
+    S, ch, i, o, q, n = WORKLOADS[wl]
+    return {"workload": f"{wl}: {S} streams/GPU x {ch} ch, {i}->{o} Hz, quality {q}, 20 ms steps "
+                        f"({n} frames in), state carried", "streams_per_gpu": S, "channels": ch,
+            "in_rate": i, "out_rate": o, "quality": q, "frames_in_per_step": n}
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.lines:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.1):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU implementation of the path (reference arm / cpu_baseline)
+# ---------------------------------------------------------------------------
+def cpu_run(wl: str, steps: int, warmup: int, threads: int | None = None):
+    """The reference's CPU path on this box's cores: every step resamples one 20 ms chunk of
+    every stream of the workload, streams spread over `threads` OS threads (ctypes releases
+    the GIL inside the C call). Returns (samples/s, seconds per step, kind, threads)."""
+    from oracle import oracle as O
+    from node_speex_resampler_b200.signals import synth_pcm
+    S, ch, i, o, q, n = WORKLOADS[wl]
+    cls, kind = O.best_cpu_resampler()
+    threads = threads or os.cpu_count() or 1
+    threads = min(threads, S)
+    cap = int(math.ceil(n * o / i)) + 1
+    pcm = synth_pcm(min(S, 64), ch, n, i, seed=0xB200)
+    streams = [cls(ch, i, o, q) for _ in range(S)]
+    made = [0] * threads
+
+    def worker(t, count):
+        tot = 0
+        for _ in range(count):
+            for s in range(t, S, threads):
+                y, _, m = streams[s].process(pcm[s % pcm.shape[0]], cap)
+                tot += m * ch
+        made[t] = tot
+
+    def run(count):
+        ts = [threading.Thread(target=worker, args=(t, count)) for t in range(threads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    if warmup:
+        run(warmup)
+    dt = run(steps)
+    return sum(made) / dt, dt / steps, kind, threads
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    S, ch, i, o, q, n = WORKLOADS[wl]
+    # bound the run: ~0.75 core-seconds per C3 step
+    steps = args.steps
+    rate, sec_per_step, kind, threads = cpu_run(wl, steps, min(args.warmup, 2))
+    sample = f"{steps} steps x {S} streams x 20 ms ({kind} C, one stream per thread, {threads} threads)"
+    line = {"impl": "reference", "metric": "output_msamples_per_sec", "value": rate / 1e6, "unit": "Msamples/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": sec_per_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": describe(wl),
+            "cpu_baseline": {"value": rate / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": rate / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import node_speex_resampler_b200 as pkg
+    from node_speex_resampler_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path "
+                         "(use --impl reference for the CPU implementation)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    L = pkg.lib()
+    wl = args.workload
+    S, ch, i, o, q, n = WORKLOADS[wl]
+    info = _lib.FilterInfo()
+    L.spxb_filter_describe(i, o, q, C.byref(info))
+    N = info.filt_len
+    cap = int(math.ceil(n * o / i))
+    batch = pkg.StreamBatch(S, ch, i, o, q, device=local)
+    batch.set_kernel({"auto": pkg.KERNEL_AUTO, "strict": pkg.KERNEL_STRICT, "tiled": pkg.KERNEL_TILED}[args.kernel])
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)  # events below and the batch's kernels share this stream
+    assert L.spxb_batch_set_stream(batch._h, C.c_void_p(stream.cuda_stream)) == 0
+
+    # ---- inputs resident in HBM: a ring of distinct hops larger than L2 ----
+    # rows padded to 16 bytes so the kernel's vector loads apply (unpadded rows also work,
+    # through a slower frame-by-frame staging path)
+    n_pad = (n * ch + 7) // 8 * 8 // ch
+    cap_pad = (cap * ch + 7) // 8 * 8 // ch
+    in_slot = S * n_pad * ch
+    out_slot = S * cap_pad * ch
+    ring = max(4, int(math.ceil(1.25 * L2_BYTES / (in_slot * 2))))
+    ring = min(ring, 96)
+    hop = pkg.synth_pcm(min(S, 256), ch, n * 4, i, seed=0xB200 + rank)
+    d_in = torch.zeros((ring, S, n_pad * ch), dtype=torch.int16, device="cuda")
+    for r in range(ring):
+        sel = np.resize(np.arange(hop.shape[0]), S) if hop.shape[0] < S else np.arange(S)
+        sl = hop[np.roll(sel, r), (r % 4) * n * ch:((r % 4) + 1) * n * ch]
+        d_in[r, :, : n * ch].copy_(torch.from_numpy(np.ascontiguousarray(sl)))
+    d_out = torch.zeros((ring, S, cap_pad * ch), dtype=torch.int16, device="cuda")
+
+    def run_hops(first, count):
+        e = L.spxb_batch_process_device_ring(batch._h, d_in.data_ptr(), n_pad, in_slot, d_out.data_ptr(), cap_pad,
+                                             out_slot, ring, n, cap, first, count)
+        if e:
+            raise RuntimeError(_lib.strerror(e) + ": " + _lib.last_error())
+
+    K, W = args.steps, max(args.warmup, 3)
+    run_hops(0, W)
+    barrier()
+    # probe one step to size the repetitions (each timed region is EXACTLY K steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_hops(W, K)
+    e1.record()
+    torch.cuda.synchronize()
+    est = max(e0.elapsed_time(e1) * 1e-3, 1e-6)
+    reps = int(min(400, max(3, math.ceil(args.min_seconds / est))))
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    c0 = batch.counters().kernel_launches
+    times = []
+    barrier()
+    t_start = time.perf_counter()
+    step_no = W + K
+    for r in range(reps):
+        barrier()
+        e0.record()
+        run_hops(step_no, K)
+        e1.record()
+        barrier()
+        times.append(e0.elapsed_time(e1) * 1e-3)
+        step_no += K
+    t_end = time.perf_counter()
+    launches = (batch.counters().kernel_launches - c0) // reps
+    clocks = sampler.stop(t_start, t_end) if rank == 0 else None
+    sec = statistics.median(times)
+    if world > 1:
+        t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    out_samples_step = S * cap * ch  # per GPU
+    value = out_samples_step * world * K / sec
+    kernel_used = {0: "auto", 1: "strict", 2: "tiled"}[batch.last_kernel()]
+
+    # ---- roofline of the FIR kernel ----
+    fp32_peak = L.spxb_measure_fp32_peak(8192)
+    flops_per_launch = out_samples_step * 2.0 * N
+    t_launch = sec / K
+    bytes_per_launch = (out_samples_step * 2.0 + S * n * ch * 2.0 + 2.0 * S * ch * (N - 1) * 2.0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roof = {"bound": "fp32_fma", "achieved": flops_per_launch / t_launch / 1e12, "peak": fp32_peak / 1e12,
+            "unit": "TFLOP/s", "frac": (flops_per_launch / t_launch) / fp32_peak if fp32_peak else None,
+            "traffic": None,
+            "peak_source": "FFMA probe measured in this run (MEASURED_PEAKS.json has no fp32 entry); "
+                           "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+            "flops_per_output_sample": 2 * N, "launch_us": t_launch * 1e6,
+            "hbm": {"achieved": bytes_per_launch / t_launch / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": bytes_per_launch / t_launch / 1e9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
+                    "bytes_per_output_sample": bytes_per_launch / out_samples_step}}
+
+    # ---- end to end through the C ABI with pinned host buffers ----
+    L.spxb_batch_use_own_stream(batch._h)
+    hr = min(6, ring)
+    in_bytes, out_bytes = S * n * ch * 2, S * cap * ch * 2
+    hin = [L.spxb_host_alloc(in_bytes) for _ in range(hr)]
+    hout = [L.spxb_host_alloc(out_bytes) for _ in range(hr)]
+    src = np.ascontiguousarray(d_in[:hr, :, : n * ch].cpu().numpy())
+    for k in range(hr):
+        C.memmove(hin[k], src[k].ctypes.data, in_bytes)
+    nin = np.empty(S, np.uint32)
+    nout = np.empty(S, np.uint32)
+    depth = L.spxb_batch_pipeline_depth(batch._h)
+
+    def e2e_steps(count):
+        tickets = []
+        for k in range(count):
+            nin.fill(n)
+            nout.fill(cap)
+            t = C.c_uint64(0)
+            e = L.spxb_batch_submit(batch._h, hin[k % hr], n, nin.ctypes.data, hout[k % hr], cap,
+                                    nout.ctypes.data, C.byref(t))
+            if e:
+                raise RuntimeError(_lib.strerror(e) + ": " + _lib.last_error())
+            tickets.append(t.value)
+            if k >= depth:
+                L.spxb_batch_wait(batch._h, tickets[k - depth])
+        for t in tickets[-depth:]:
+            L.spxb_batch_wait(batch._h, t)
+
+    Ke = max(K, 20)
+    e2e_steps(max(W, 3))
+    batch.synchronize()
+    barrier()
+    e0.record()
+    tw0 = time.perf_counter()
+    e2e_steps(Ke)
+    batch.synchronize()
+    e1.record()
+    barrier()
+    tw1 = time.perf_counter()
+    e2e_sec = max(e0.elapsed_time(e1) * 1e-3, tw1 - tw0)
+    if world > 1:
+        t = torch.tensor([e2e_sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+    e2e_value = out_samples_step * world * Ke / e2e_sec
+    for p in hin + hout:
+        L.spxb_host_free(p)
+
+    # ---- CPU baseline beside it (rank 0, N == 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        S_, ch_, i_, o_, q_, n_ = WORKLOADS[wl]
+        per_step_core_s = {"C3": 0.75, "C4": 0.9, "C5": 30.0}[wl]
+        cores = os.cpu_count() or 1
+        cpu_steps = max(1, int(20.0 * cores / per_step_core_s / cores)) if wl != "C5" else 1
+        cpu_steps = max(1, min(cpu_steps, int(15.0 * cores / per_step_core_s)))
+        rate, sps, kind, threads = cpu_run(wl, cpu_steps, 0)
+        cpu = {"value": rate / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind,
+               "sample": f"{cpu_steps} steps x {S_} streams x 20 ms, one stream per thread, {threads} threads"}
+
+    if rank == 0:
+        line = {"metric": "output_msamples_per_sec", "value": value / 1e6, "unit": "Msamples/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": sec / K * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(describe(wl), timing=f"median of {reps} regions of exactly {K} steps, CUDA events; "
+                               f"inputs: ring of {ring} distinct hops in HBM ({ring * in_slot * 2 >> 20} MiB > L2), "
+                               "no L2 flush needed", kernel=kernel_used, filt_len=N),
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": in_bytes,
+                        "d2h_bytes_per_step": out_bytes, "steps": Ke, "pipeline_depth": depth,
+                        "how": "spxb_batch_submit/wait (C ABI), pinned host buffers, H2D+kernel+D2H per step"},
+                "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--kernel", default="auto", choices=["auto", "strict", "tiled"])
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="clock-sampling window for the timed regions")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -146,12 +146,23 @@ SPXB_API int spxb_batch_process_device_uniform(spxb_batch *b, const int16_t *d_i
                                                uint32_t out_cap, uint32_t *in_used,
                                                uint32_t *out_written);
 
+/* A queue of hops already resident in HBM: step k (first_step <= k < first_step + steps)
+ * reads slot k % ring of d_in (slots in_slot_elems int16 apart) and writes slot k % ring of
+ * d_out, every stream n_in frames in / out_cap capacity, state carried hop to hop. One
+ * uniform call per hop, launched back to back on the compute stream with no host sync. */
+SPXB_API int spxb_batch_process_device_ring(spxb_batch *b, const int16_t *d_in,
+                                            size_t in_stride_frames, size_t in_slot_elems,
+                                            int16_t *d_out, size_t out_stride_frames,
+                                            size_t out_slot_elems, uint32_t ring, uint32_t n_in,
+                                            uint32_t out_cap, uint32_t first_step, uint32_t steps);
+
 /* the one-stream batch behind a SpeexResamplerState (state migration into a larger batch) */
 SPXB_API spxb_batch *spxb_resampler_batch(SpeexResamplerState *st);
 
-/* run the batch's kernels on a caller-owned cudaStream_t (e.g. torch's current stream);
- * NULL restores the batch's own stream */
+/* run the batch's kernels on a caller-owned cudaStream_t (e.g. torch's current stream;
+ * NULL is the legacy default stream); spxb_batch_use_own_stream goes back to the batch's own */
 SPXB_API int spxb_batch_set_stream(spxb_batch *b, void *cuda_stream);
+SPXB_API int spxb_batch_use_own_stream(spxb_batch *b);
 SPXB_API int spxb_batch_synchronize(spxb_batch *b);
 
 /* stream state (checkpoint / resume). history is interleaved

@@ -21,7 +21,7 @@ DECLARED_SYMBOLS = (
     "spxb_device_count", "spxb_last_error", "spxb_batch_create", "spxb_batch_destroy",
     "spxb_batch_set_kernel", "spxb_batch_get_kernel", "spxb_batch_process", "spxb_batch_submit",
     "spxb_batch_wait", "spxb_batch_pipeline_depth", "spxb_batch_process_device",
-    "spxb_batch_process_device_uniform", "spxb_batch_set_stream", "spxb_batch_synchronize",
+    "spxb_batch_process_device_uniform", "spxb_batch_process_device_ring", "spxb_batch_set_stream", "spxb_batch_use_own_stream", "spxb_batch_synchronize",
     "spxb_batch_get_state", "spxb_batch_set_state", "spxb_batch_reset", "spxb_batch_skip_zeros",
     "spxb_batch_counters", "spxb_host_alloc", "spxb_host_free", "spxb_filter_describe",
     "spxb_filter_table", "spxb_filter_phase_taps", "spxb_plan_call", "spxb_version", "spxb_resampler_batch",
@@ -78,7 +78,9 @@ def _bind(L):
     L.spxb_batch_pipeline_depth.argtypes = [vp]
     L.spxb_batch_process_device.argtypes = [vp, vp, sz, vp, vp, sz, vp]
     L.spxb_batch_process_device_uniform.argtypes = [vp, vp, sz, u32, vp, sz, u32, pu32, pu32]
+    L.spxb_batch_process_device_ring.argtypes = [vp, vp, sz, sz, vp, sz, sz, u32, u32, u32, u32, u32]
     L.spxb_batch_set_stream.argtypes = [vp, vp]
+    L.spxb_batch_use_own_stream.argtypes = [vp]
     L.spxb_batch_synchronize.argtypes = [vp]
     L.spxb_batch_get_state.argtypes = [vp, u32, C.POINTER(i32), pu32, pu32, vp]
     L.spxb_batch_set_state.argtypes = [vp, u32, i32, u32, vp]

@@ -655,17 +655,36 @@ int spxb_batch_process_device_uniform(spxb_batch *b, const int16_t *d_in, size_t
   return 0;
 }
 
+int spxb_batch_process_device_ring(spxb_batch *b, const int16_t *d_in, size_t in_stride_frames,
+                                   size_t in_slot_elems, int16_t *d_out, size_t out_stride_frames,
+                                   size_t out_slot_elems, uint32_t ring, uint32_t n_in, uint32_t out_cap,
+                                   uint32_t first_step, uint32_t steps) {
+  if (!b || ring == 0) return RESAMPLER_ERR_INVALID_ARG;
+  for (uint32_t k = first_step; k < first_step + steps; ++k) {
+    const size_t slot = k % ring;
+    int e = spxb_batch_process_device_uniform(b, d_in + slot * in_slot_elems, in_stride_frames, n_in,
+                                              d_out + slot * out_slot_elems, out_stride_frames, out_cap,
+                                              nullptr, nullptr);
+    if (e) return e;
+  }
+  return 0;
+}
+
 int spxb_batch_set_stream(spxb_batch *b, void *cuda_stream) {
   if (!b) return RESAMPLER_ERR_INVALID_ARG;
   DeviceGuard g(b->device);
   SPXB_CUDA(cudaStreamSynchronize(b->s_compute));
-  if (cuda_stream) {
-    b->s_compute = static_cast<cudaStream_t>(cuda_stream);
-    b->external_stream = true;
-  } else {
-    b->s_compute = b->s_own;
-    b->external_stream = false;
-  }
+  b->s_compute = static_cast<cudaStream_t>(cuda_stream);
+  b->external_stream = true;
+  return 0;
+}
+
+int spxb_batch_use_own_stream(spxb_batch *b) {
+  if (!b) return RESAMPLER_ERR_INVALID_ARG;
+  DeviceGuard g(b->device);
+  SPXB_CUDA(cudaStreamSynchronize(b->s_compute));
+  b->s_compute = b->s_own;
+  b->external_stream = false;
   return 0;
 }
 

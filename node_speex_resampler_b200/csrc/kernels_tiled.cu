@@ -22,8 +22,9 @@
 //                      are read with 128-bit loads along k
 // Inner loop per 4 k: 8 LDS.128 (taps, warp-broadcast) + CW LDS.128 (window) : 32*CW FFMA.
 // Epilogue: WORD2INT (arch.h:208-209) and 16-byte interleaved int16 stores.
-// The history slide (resample.c:898-899) and the new (last_sample, samp_frac_num) are written
-// by extra blocks of the same grid into the other half of the history ping-pong.
+// The history slide (resample.c:898-899) is spread over the same CTAs (each row-group CTA
+// copies a slice of its series group's new history into the other half of the ping-pong);
+// the row-group-0 CTAs publish the new (last_sample, samp_frac_num).
 #include <cstdlib>
 
 #include "kernels_common.cuh"
@@ -52,10 +53,6 @@ __global__ void __launch_bounds__(TR * 32)
   constexpr int NT = TR * 32;
   constexpr int TS = 32 * CW;        // series per CTA
   constexpr int TM = kRows * TR;     // outputs per CTA
-  if (blockIdx.x >= g.fir_blocks) {
-    history_block(a, blockIdx.x - g.fir_blocks);
-    return;
-  }
   extern __shared__ __align__(16) float smem[];
   float *Bs = smem;
   float *As = smem + static_cast<size_t>(TS) * g.Wp;
@@ -78,73 +75,163 @@ __global__ void __launch_bounds__(TR * 32)
   };
   const int W0 = window_start(M0, nullptr) & ~3;
 
+  constexpr int kStreams = TS / CH;  // streams per CTA
+
+  // ---- this CTA's slice of the history slide (resample.c:898-899) ----
+  // The group's new history (kStreams x hist_elems int16) is cut into n_rg slices, one per
+  // row-group CTA; loads are issued in batches so their latency overlaps.
+  {
+    const uint32_t hist_elems = a.hist_frames * CH;
+    const uint32_t total = kStreams * hist_elems;
+    const uint32_t per_cta = (total + g.n_rg - 1) / g.n_rg;
+    const uint32_t lo = rg * per_cta;
+    const uint32_t hi = min(total, lo + per_cta);
+    constexpr int U = 4;
+    for (uint32_t base = lo + tid; base < hi; base += NT * U) {
+      int16_t v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t eg = base + u * NT;
+        v[u] = 0;
+        if (eg < hi) {
+          const uint32_t sl = eg / hist_elems, e = eg - sl * hist_elems;
+          const uint32_t s = sg * kStreams + sl;
+          if (s < a.n_streams) {
+            const size_t src = static_cast<size_t>(sc.consumed) * CH + e;
+            v[u] = (src < hist_elems) ? a.hist_src[static_cast<size_t>(s) * a.hist_stride + src]
+                                      : a.in[static_cast<size_t>(s) * a.in_stride + (src - hist_elems)];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t eg = base + u * NT;
+        if (eg < hi) {
+          const uint32_t sl = eg / hist_elems, e = eg - sl * hist_elems;
+          const uint32_t s = sg * kStreams + sl;
+          if (s < a.n_streams) a.hist_dst[static_cast<size_t>(s) * a.hist_stride + e] = v[u];
+        }
+      }
+    }
+    if (rg == 0 && tid < kStreams) {
+      const uint32_t s = sg * kStreams + tid;
+      if (s < a.n_streams) {
+        a.last_sample[s] = sc.ls1;
+        a.samp_frac[s] = sc.frac1;
+      }
+    }
+  }
+
   // ---- stage the windows: int16 (HBM) -> f32 (shared), 4 frames per item ----
+  // Items are taken U at a time: all global loads of a batch are issued before the first
+  // conversion so that U requests per thread are in flight.
   {
     const int G4 = Wp >> 2;
-    constexpr int kStreams = TS / CH;  // streams per CTA
     const int items = kStreams * G4;
     const int hist_frames = static_cast<int>(a.hist_frames);
-    for (int id = tid; id < items; id += NT) {
-      const int sl = id / G4;
-      const int g4 = id - sl * G4;
-      const int f = W0 + 4 * g4;
-      const uint32_t s = sg * kStreams + sl;
-      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-      if (s < a.n_streams) {
-        const int16_t *src = nullptr;
-        int avail = 0;  // frames readable from src
-        if (f < 0) {
-          const int hf = f + hist_frames;
-          if (hf >= 0) {
-            src = a.hist_src + static_cast<size_t>(s) * a.hist_stride + static_cast<size_t>(hf) * CH;
-            avail = 4;
+    // 16-byte (8-byte mono) loads need the caller's rows aligned; otherwise frame by frame
+    const bool in_vec = (a.in_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
+    constexpr int U = 8;
+    for (int base = tid; base < items; base += NT * U) {
+      uint4 raw[U];
+      const int16_t *slow[U];
+      int avail[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int id = base + u * NT;
+        raw[u] = make_uint4(0u, 0u, 0u, 0u);
+        slow[u] = nullptr;
+        avail[u] = 0;
+        if (id < items) {
+          const int sl = id / G4;
+          const int g4 = id - sl * G4;
+          const int f = W0 + 4 * g4;
+          const uint32_t s = sg * kStreams + sl;
+          if (s < a.n_streams) {
+            const int16_t *src = nullptr;
+            bool vec = true;
+            if (f < 0) {
+              const int hf = f + hist_frames;
+              if (hf >= 0) {
+                src = a.hist_src + static_cast<size_t>(s) * a.hist_stride + static_cast<size_t>(hf) * CH;
+                avail[u] = 4;
+              }
+            } else if (static_cast<uint32_t>(f) < sc.n_in) {
+              src = a.in + static_cast<size_t>(s) * a.in_stride + static_cast<size_t>(f) * CH;
+              avail[u] = min(4, static_cast<int>(sc.n_in) - f);
+              vec = in_vec;
+            }
+            if (avail[u] == 4 && vec) {
+              if (CH == 2) {
+                raw[u] = __ldg(reinterpret_cast<const uint4 *>(src));
+              } else {
+                const uint2 t = __ldg(reinterpret_cast<const uint2 *>(src));
+                raw[u].x = t.x;
+                raw[u].y = t.y;
+              }
+            } else if (avail[u] > 0) {
+              slow[u] = src;
+            }
           }
-        } else if (static_cast<uint32_t>(f) < sc.n_in) {
-          src = a.in + static_cast<size_t>(s) * a.in_stride + static_cast<size_t>(f) * CH;
-          avail = min(4, static_cast<int>(sc.n_in) - f);
         }
-        if (avail == 4) {
-          if (CH == 2) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(src));
-            v0 = make_float4(s16lo(raw.x), s16lo(raw.y), s16lo(raw.z), s16lo(raw.w));
-            v1 = make_float4(s16hi(raw.x), s16hi(raw.y), s16hi(raw.z), s16hi(raw.w));
-          } else {
-            const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(src));
-            v0 = make_float4(s16lo(raw.x), s16hi(raw.x), s16lo(raw.y), s16hi(raw.y));
-          }
-        } else if (avail > 0) {
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int id = base + u * NT;
+        if (id >= items) continue;
+        const int sl = id / G4;
+        const int g4 = id - sl * G4;
+        float4 v0, v1;
+        if (slow[u] != nullptr) {  // tail of the input or unaligned rows: frame by frame
           float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int i = 0; i < avail; ++i) {
-            t0[i] = static_cast<float>(src[i * CH]);
-            if (CH == 2) t1[i] = static_cast<float>(src[i * CH + 1]);
+          for (int i = 0; i < avail[u]; ++i) {
+            t0[i] = static_cast<float>(slow[u][i * CH]);
+            if (CH == 2) t1[i] = static_cast<float>(slow[u][i * CH + 1]);
           }
           v0 = make_float4(t0[0], t0[1], t0[2], t0[3]);
           v1 = make_float4(t1[0], t1[1], t1[2], t1[3]);
+        } else if (CH == 2) {
+          v0 = make_float4(s16lo(raw[u].x), s16lo(raw[u].y), s16lo(raw[u].z), s16lo(raw[u].w));
+          v1 = make_float4(s16hi(raw[u].x), s16hi(raw[u].y), s16hi(raw[u].z), s16hi(raw[u].w));
+        } else {
+          v0 = make_float4(s16lo(raw[u].x), s16hi(raw[u].x), s16lo(raw[u].y), s16hi(raw[u].y));
+          v1 = v0;
         }
+        // shared row of (stream sl, channel c): lane = sl % 32, thread column = CH*(sl/32) + c
+        const int rho = (sl & 31) + 32 * CH * (sl >> 5);
+        *reinterpret_cast<float4 *>(Bs + static_cast<size_t>(rho) * Wp + 4 * g4) = v0;
+        if (CH == 2) *reinterpret_cast<float4 *>(Bs + static_cast<size_t>(rho + 32) * Wp + 4 * g4) = v1;
       }
-      // shared row of (stream sl, channel c): lane = sl % 32, thread column = CH*(sl/32) + c
-      const int rho = (sl & 31) + 32 * CH * (sl >> 5);
-      *reinterpret_cast<float4 *>(Bs + static_cast<size_t>(rho) * Wp + 4 * g4) = v0;
-      if (CH == 2) *reinterpret_cast<float4 *>(Bs + static_cast<size_t>(rho + 32) * Wp + 4 * g4) = v1;
     }
   }
 
   // ---- build this warp's pre-shifted tap tile ----
+  // As[r][k] = h[phase_r][k + a0 - q_r]; the 8 rows' loads of one k are issued together.
   float *Aw = As + static_cast<size_t>(w) * kRows * Kp;
   const uint32_t m0 = M0 + kRows * w;
   int q_mine;
   uint32_t ph_mine;
   q_mine = window_start(m0 + (lane & 7), &ph_mine);
   const int a0 = __shfl_sync(0xffffffffu, q_mine, 0) & ~3;
+  {
+    const float *hrow[kRows];
+    int shift[kRows];
 #pragma unroll
-  for (int r = 0; r < kRows; ++r) {
-    const int q_r = __shfl_sync(0xffffffffu, q_mine, r);
-    const uint32_t ph_r = __shfl_sync(0xffffffffu, ph_mine, r);
-    const float *hrow = a.filt.phase_taps + static_cast<size_t>(ph_r) * N;
-    const int shift = a0 - q_r;  // tap index = k + shift
+    for (int r = 0; r < kRows; ++r) {
+      const int q_r = __shfl_sync(0xffffffffu, q_mine, r);
+      const uint32_t ph_r = __shfl_sync(0xffffffffu, ph_mine, r);
+      hrow[r] = a.filt.phase_taps + static_cast<size_t>(ph_r) * N;
+      shift[r] = a0 - q_r;  // tap index = k + shift
+    }
     for (int k = lane; k < Kp; k += 32) {
-      const int j = k + shift;
-      Aw[r * Kp + k] = (j >= 0 && j < N) ? __ldg(hrow + j) : 0.f;
+      float v[kRows];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const int j = k + shift[r];
+        v[r] = (j >= 0 && j < N) ? __ldg(hrow[r] + j) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) Aw[r * Kp + k] = v[r];
     }
   }
   __syncthreads();
@@ -250,8 +337,7 @@ cudaError_t launch_one(const CallArgs &a, const TileGeom &g, uint32_t smem, cuda
     if (e != cudaSuccess) return e;
     configured_dev = dev;
   }
-  const uint32_t total = g.fir_blocks + hist_blocks(a, TR * 32);
-  kern<<<total, TR * 32, smem, stream>>>(a, g);
+  kern<<<g.fir_blocks, TR * 32, smem, stream>>>(a, g);
   return cudaGetLastError();
 }
 
@@ -288,8 +374,7 @@ bool tiled_qualifies(const CallArgs &a, int sm_count, TiledConfig *cfg) {
   if (a.channels != 1 && a.channels != 2) return false;
   if (a.filt.phase_taps == nullptr) return false;
   if (a.uniform.n_out == 0) return false;
-  // 16-byte loads of the input and history
-  if ((reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || a.in_stride % 8 != 0) return false;
+  // 16-byte loads of the history (our own buffer); unaligned input rows are handled in-kernel
   if ((reinterpret_cast<uintptr_t>(a.hist_src) & 15) != 0 || a.hist_stride % 8 != 0) return false;
   // window positions are handled as int: keep them small enough
   if (a.uniform.n_in > 0x3fffffffu || a.filt.taps > 4096) return false;
