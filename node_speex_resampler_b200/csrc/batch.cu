@@ -73,7 +73,8 @@ struct spxb_batch {
   FilterSpec spec;
   uint32_t n_streams = 0, channels = 0;
   // filter bank in HBM
-  float *d_table = nullptr, *d_taps = nullptr, *d_blend = nullptr;
+  float *d_table = nullptr, *d_taps = nullptr, *d_blend = nullptr, *d_band = nullptr;
+  uint32_t band_kp = 0, band_pad = 0, band_row = 0;
   // stream state in HBM
   int16_t *d_hist[2] = {nullptr, nullptr};
   int hist_cur = 0;
@@ -212,6 +213,10 @@ static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elem
   a.filt.table = b->d_table;
   a.filt.phase_taps = b->d_taps;
   a.filt.blend = b->d_blend;
+  a.filt.band = b->d_band;
+  a.filt.band_kp = b->band_kp;
+  a.filt.band_pad = b->band_pad;
+  a.filt.band_row = b->band_row;
   a.n_streams = b->n_streams;
   a.channels = b->channels;
   a.in = d_in;
@@ -233,7 +238,7 @@ static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elem
   int used = SPXB_KERNEL_STRICT;
   TiledConfig cfg;
   const bool want_tiled = b->kernel_pref != SPXB_KERNEL_STRICT;
-  if (want_tiled && b->d_taps && tiled_qualifies(a, b->sm_count, &cfg)) {
+  if (want_tiled && b->d_band && tiled_qualifies(a, b->sm_count, &cfg)) {
     ce = launch_tiled(a, cfg, b->s_compute, &launches);
     used = SPXB_KERNEL_TILED;
   } else if (b->kernel_pref == SPXB_KERNEL_TILED && max_n_out != 0) {
@@ -332,6 +337,7 @@ static void free_batch(spxb_batch *b) {
   if (b->d_table) cudaFree(b->d_table);
   if (b->d_taps) cudaFree(b->d_taps);
   if (b->d_blend) cudaFree(b->d_blend);
+  if (b->d_band) cudaFree(b->d_band);
   if (b->d_hist[0]) cudaFree(b->d_hist[0]);
   if (b->d_hist[1]) cudaFree(b->d_hist[1]);
   if (b->d_last_sample) cudaFree(b->d_last_sample);
@@ -378,6 +384,15 @@ static int create_batch(spxb_batch *b) {
     std::vector<float> taps = build_phase_taps(sp, table);
     SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->d_taps), taps.size() * sizeof(float)));
     SPXB_CUDA(cudaMemcpy(b->d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // pre-shifted tap tiles of the streaming kernel, while they stay modest too
+    BandTable band;
+    if (build_band_table(sp, taps, 64ull << 20, &band)) {
+      SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->d_band), band.data.size() * sizeof(float)));
+      SPXB_CUDA(cudaMemcpy(b->d_band, band.data.data(), band.data.size() * sizeof(float), cudaMemcpyHostToDevice));
+      b->band_kp = band.kp;
+      b->band_pad = band.pad;
+      b->band_row = band.row;
+    }
   }
   if (!sp.direct) {
     std::vector<float> blend(static_cast<size_t>(sp.den) * 4);
@@ -390,7 +405,7 @@ static int create_batch(spxb_batch *b) {
   }
 
   // stream state, zeroed: resample.c:721-725 and the calloc'd per-channel arrays :838-843
-  b->hist_frames = static_cast<uint32_t>(round_up(sp.taps - 1, 4));
+  b->hist_frames = static_cast<uint32_t>(round_up(sp.taps - 1, 8));
   b->hist_stride = static_cast<uint32_t>(round_up(static_cast<size_t>(b->hist_frames) * b->channels, 8));
   const size_t hist_bytes = static_cast<size_t>(b->n_streams) * b->hist_stride * sizeof(int16_t);
   for (int i = 0; i < 2; ++i) {

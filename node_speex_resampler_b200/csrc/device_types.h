@@ -38,6 +38,10 @@ struct FilterDev {
   const float *table;
   const float *phase_taps;
   const float *blend;  // [den][4], interpolate path only
+  // pre-shifted tap tiles for the streaming kernel (filter_bank.h: BandTable); nullptr when
+  // the table would be too large for this ratio
+  const float *band;
+  uint32_t band_kp, band_pad, band_row;
 };
 
 struct CallArgs {

@@ -217,3 +217,36 @@ std::vector<float> build_phase_taps(const FilterSpec &s, const std::vector<float
 }
 
 }  // namespace spxb
+
+namespace spxb {
+
+uint32_t max_window_advance(uint32_t n, uint32_t num, uint32_t den) {
+  return static_cast<uint32_t>((static_cast<uint64_t>(n) * num + den - 1) / den);
+}
+
+bool build_band_table(const FilterSpec &s, const std::vector<float> &taps, size_t max_bytes, BandTable *out) {
+  const uint32_t N = s.taps;
+  BandTable t;
+  t.kp = (3 + max_window_advance(7, s.num, s.den) + N + 3) / 4 * 4;
+  t.pad = (max_window_advance(8, s.num, s.den) + 3 + 3) / 4 * 4;
+  t.row = t.kp + 2 * t.pad;
+  const uint64_t floats = static_cast<uint64_t>(s.den) * 4 * 8 * t.row;
+  if (floats * sizeof(float) > max_bytes) return false;
+  t.data.assign(floats, 0.f);
+  for (uint32_t p0 = 0; p0 < s.den; ++p0) {
+    for (uint32_t al = 0; al < 4; ++al) {
+      for (uint32_t r = 0; r < 8; ++r) {
+        const uint64_t acc = static_cast<uint64_t>(p0) + static_cast<uint64_t>(r) * s.num;
+        const uint32_t phase = static_cast<uint32_t>(acc % s.den);
+        const uint32_t shift = al + static_cast<uint32_t>(acc / s.den);  // first tap's column
+        float *dst = t.data.data() + ((static_cast<uint64_t>(p0) * 4 + al) * 8 + r) * t.row + t.pad + shift;
+        const float *src = taps.data() + static_cast<size_t>(phase) * N;
+        for (uint32_t j = 0; j < N; ++j) dst[j] = src[j];
+      }
+    }
+  }
+  *out = std::move(t);
+  return true;
+}
+
+}  // namespace spxb

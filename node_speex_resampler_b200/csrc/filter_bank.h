@@ -43,3 +43,29 @@ void cubic_weights(float t, float w[4]);
 std::vector<float> build_phase_taps(const FilterSpec &spec, const std::vector<float> &ref_table);
 
 }  // namespace spxb
+
+namespace spxb {
+
+// Banded tap tiles for the streaming FIR kernel. A tile is 8 consecutive outputs whose first
+// output has phase p0 and whose first window frame q0 has (q0 & 3) == al. Column k of every
+// row multiplies window frame (q0 - al) + k, so row r (phase (p0 + r*num) % den, window
+// start q0 + floor((p0 + r*num)/den)) holds its N taps shifted right by al + that advance,
+// with zeros elsewhere. Rows are `row` floats long: `pad` zero columns, then columns
+// 0 .. kp-1, then `pad` more, so neighbouring tiles of one warp can run a common column range.
+// Layout: data[((p0*4 + al)*8 + r)*row + pad + k].
+struct BandTable {
+  std::vector<float> data;
+  uint32_t kp = 0;   // columns that can hold a tap: 3 + max advance over 7 outputs + N, /4 up
+  uint32_t pad = 0;  // zero margin on each side (multiple of 4)
+  uint32_t row = 0;  // kp + 2*pad
+};
+
+// largest advance of the window start over n outputs: ceil(n*num/den)
+uint32_t max_window_advance(uint32_t n, uint32_t num, uint32_t den);
+
+// false when the table would exceed `max_bytes` (huge denominators): such batches are
+// served by the strict kernel
+bool build_band_table(const FilterSpec &spec, const std::vector<float> &phase_taps, size_t max_bytes,
+                      BandTable *out);
+
+}  // namespace spxb

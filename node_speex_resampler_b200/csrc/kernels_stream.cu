@@ -1,0 +1,364 @@
+// kernels_stream.cu -- streaming banded-GEMM FIR for sm_100a (FP32 FMA pipe); the "tiled"
+// kernel family of include/speexb200.h.
+//
+// One launch does the whole hot path of speex_resampler_process_interleaved_int
+// (deps/speex/resample.c:1061-1082 over :968-1036 and the four resampler_basic_* kernels
+// :331-558) for a batch of streams at a common stream position: int16 de-interleave and
+// convert, the polyphase FIR, WORD2INT (arch.h:208-209), re-interleave, and the history slide
+// (:898-899). Both reference table shapes collapse to one form: every output phase has its
+// own N-tap FIR (the direct table as is; for the interpolating path the cubic blend of
+// :467-476 folded into the taps on the host), so  y(m) = sum_j h[phase(m)][j] * X~[q(m)+j].
+//
+// That is a banded GEMM  Y[outputs x series] = G[outputs x window] * X[window x series]:
+//   CTA   = 64 consecutive outputs x 128 series (series = stream x channel), 4 warps
+//   warp  = 16 outputs (two 8-output row tiles, one per half-warp) x 128 series
+//   lane  = 8 outputs x 8 series -> 64 fp32 accumulators
+// The window axis is streamed in chunks of 32 frames through double-buffered shared memory:
+//   Bs[2][128][36] f32  window chunk of every series, time-major (int16 from HBM is converted
+//                       once per chunk; history for frames < 0, this call's input for >= 0)
+//   As[2][4][16][32] f32 the warps' tap chunks, copied with 16-byte cp.async from a host-built
+//                       table of pre-shifted tap tiles (filter_bank.h: BandTable), so that
+//                       column k of a row tile multiplies window frame a0 + k for all 8 rows
+// Chunk c+1 is fetched (window: LDG.128 into registers, taps: cp.async) while chunk c is
+// contracted. Per 4 window frames a lane issues 8 LDS.128 of taps (one address per half-warp)
+// + 8 LDS.128 of window (two lanes per address) for 256 FFMA, i.e. half the shared-memory
+// wavefronts per FMA of a plain 8x4 tile. Each warp contracts only the columns of its band.
+#include <cstdlib>
+
+#include "kernels_common.cuh"
+#include "launch.h"
+
+namespace spxb {
+
+namespace {
+
+constexpr int kKC = 32;          // window frames per chunk
+constexpr int kKCP = kKC + 4;    // padded Bs row (36 floats: rows 16 B apart modulo 128 B)
+constexpr int kTS = 128;         // series per CTA
+constexpr int kWarps = 4;
+constexpr int kNT = kWarps * 32;
+constexpr int kTM = 16 * kWarps; // outputs per CTA
+constexpr int kBsFloats = kTS * kKCP;
+constexpr int kAsFloats = kWarps * 16 * kKC;
+constexpr uint32_t kSmemBytes = 2u * (kBsFloats + kAsFloats) * sizeof(float);
+
+struct StreamGeom {
+  uint32_t n_sg;  // series groups (grid.x = n_sg * n_rg)
+  uint32_t n_rg;  // row groups
+};
+
+__device__ __forceinline__ float s16lo(uint32_t w) { return static_cast<float>(static_cast<short>(w & 0xffffu)); }
+__device__ __forceinline__ float s16hi(uint32_t w) { return static_cast<float>(static_cast<int>(w) >> 16); }
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// 16 bytes of one stream's PCM starting at frame f (CH == 2: 4 frames, CH == 1: 8 frames):
+// history for f < 0, the call's input for f >= 0, zeros outside both.
+template <int CH>
+__device__ __forceinline__ uint4 fetch_raw16(const CallArgs &a, const StreamCall &sc, uint32_t s, int f,
+                                             bool in_vec) {
+  constexpr int FPI = 8 / CH;  // frames per item
+  uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+  if (s >= a.n_streams) return raw;
+  if (f < 0) {
+    const int hf = f + static_cast<int>(a.hist_frames);
+    if (hf >= 0)
+      raw = __ldg(reinterpret_cast<const uint4 *>(a.hist_src + static_cast<size_t>(s) * a.hist_stride +
+                                                  static_cast<size_t>(hf) * CH));
+    return raw;
+  }
+  if (static_cast<uint32_t>(f) >= sc.n_in) return raw;
+  const int16_t *src = a.in + static_cast<size_t>(s) * a.in_stride + static_cast<size_t>(f) * CH;
+  const int avail = min(FPI, static_cast<int>(sc.n_in) - f);
+  if (avail == FPI && in_vec) return __ldg(reinterpret_cast<const uint4 *>(src));
+  // tail of the input, or caller rows that are not 16-byte aligned: sample by sample
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  const int n = avail * CH;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < n) w[i >> 1] |= static_cast<uint32_t>(static_cast<uint16_t>(src[i])) << (16 * (i & 1));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kNT, 3) stream_fir_kernel(const CallArgs a, const StreamGeom g) {
+  extern __shared__ __align__(16) float smem[];
+  float *Bs = smem;                   // [2][kTS][kKCP]
+  float *As = smem + 2 * kBsFloats;   // [2][kWarps][16][kKC]
+
+  constexpr int kStreams = kTS / CH;  // streams per CTA
+  constexpr int FPI = 8 / CH;         // frames per 16-byte item
+  constexpr int kItems = kStreams * (kKC / FPI) / kNT;  // window items per thread per chunk (= 4)
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int half = lane >> 4, l16 = lane & 15;
+  const uint32_t sg = blockIdx.x % g.n_sg;
+  const uint32_t rg = blockIdx.x / g.n_sg;
+  const StreamCall sc = a.uniform;
+  const int N = static_cast<int>(a.filt.taps);
+  const uint32_t num = a.filt.num, den = a.filt.den;
+  const uint32_t M0 = rg * kTM;
+  const bool in_vec = (a.in_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
+
+  // first frame of output m's window in X~ coordinates (history is f < 0), and its phase
+  auto window_start = [&](uint32_t m, uint32_t *phase) -> int {
+    const unsigned long long t = static_cast<unsigned long long>(sc.frac0) +
+                                 static_cast<unsigned long long>(m) * num;
+    if (phase) *phase = static_cast<uint32_t>(t % den);
+    return sc.ls0 - (N - 1) + static_cast<int>(t / den);
+  };
+
+  // ---- this CTA's slice of the history slide (resample.c:898-899) ----
+  // stream sl of the group is copied by the row-group CTA with rg == sl % n_rg
+  {
+    const uint32_t hist_elems = a.hist_frames * CH;
+    for (uint32_t sl = rg; sl < static_cast<uint32_t>(kStreams); sl += g.n_rg) {
+      const uint32_t s = sg * kStreams + sl;
+      if (s >= a.n_streams) break;
+      const int16_t *hs = a.hist_src + static_cast<size_t>(s) * a.hist_stride;
+      const int16_t *is = a.in + static_cast<size_t>(s) * a.in_stride;
+      int16_t *hd = a.hist_dst + static_cast<size_t>(s) * a.hist_stride;
+      const size_t shift = static_cast<size_t>(sc.consumed) * CH;
+      for (uint32_t e = tid; e < hist_elems; e += kNT) {
+        const size_t src = shift + e;
+        hd[e] = (src < hist_elems) ? hs[src] : is[src - hist_elems];
+      }
+      if (tid == 0) {
+        a.last_sample[s] = sc.ls1;
+        a.samp_frac[s] = sc.frac1;
+      }
+    }
+  }
+
+  // ---- geometry of this CTA's window and of this half-warp's row tile ----
+  constexpr int FA = FPI;  // window origin alignment in frames (16-byte items)
+  const int W0 = window_start(M0, nullptr) & ~(FA - 1);
+  const int Wend = window_start(M0 + kTM - 1, nullptr) + N;
+  const int n_chunks = (Wend - W0 + kKC - 1) / kKC;
+
+  const uint32_t m0 = M0 + 16 * w + 8 * half;  // first output of my row tile
+  uint32_t p0;
+  const int q0 = window_start(m0, &p0);
+  const int al = q0 & 3;
+  const int boff = (q0 - al) - W0;  // window column of tile column 0 (multiple of 4, >= 0)
+  const int kp = static_cast<int>(a.filt.band_kp), pad = static_cast<int>(a.filt.band_pad);
+  const int brow = static_cast<int>(a.filt.band_row);
+  // tile column k of row r lives at tile_taps[r*brow + k], k in [-pad, kp+pad)
+  const float *tile_taps = a.filt.band + (static_cast<size_t>(p0) * 4 + al) * 8 * brow + pad;
+  // columns the warp contracts: union of its two tiles' bands
+  const int lo_w = __shfl_sync(0xffffffffu, boff, 0);
+  const int hi_w = __shfl_sync(0xffffffffu, boff, 16) + kp;
+  const bool warp_active = (M0 + 16 * w) < sc.n_out;
+
+  // window item -> (stream of the group, first frame within the chunk, shared rows)
+  int it_sl[kItems], it_f[kItems], it_row[kItems];
+#pragma unroll
+  for (int u = 0; u < kItems; ++u) {
+    const int id = tid + kNT * u;
+    constexpr int per_stream = kKC / FPI;  // items per stream per chunk
+    it_sl[u] = id / per_stream;
+    it_f[u] = (id % per_stream) * FPI;
+    // lane l16 = sl % 16 owns the series; CH == 2: thread columns 2j (left), 2j+1 (right)
+    it_row[u] = (CH == 2) ? (it_sl[u] & 15) + 32 * (it_sl[u] >> 4) : it_sl[u];
+  }
+
+  uint4 raw[kItems];
+  auto fetch_window = [&](int c) {
+#pragma unroll
+    for (int u = 0; u < kItems; ++u)
+      raw[u] = fetch_raw16<CH>(a, sc, sg * kStreams + it_sl[u], W0 + c * kKC + it_f[u], in_vec);
+  };
+  auto store_window = [&](int buf) {
+    float *B = Bs + buf * kBsFloats;
+#pragma unroll
+    for (int u = 0; u < kItems; ++u) {
+      float4 v0, v1;
+      if (CH == 2) {
+        v0 = make_float4(s16lo(raw[u].x), s16lo(raw[u].y), s16lo(raw[u].z), s16lo(raw[u].w));
+        v1 = make_float4(s16hi(raw[u].x), s16hi(raw[u].y), s16hi(raw[u].z), s16hi(raw[u].w));
+        *reinterpret_cast<float4 *>(B + it_row[u] * kKCP + it_f[u]) = v0;
+        *reinterpret_cast<float4 *>(B + (it_row[u] + 16) * kKCP + it_f[u]) = v1;
+      } else {
+        v0 = make_float4(s16lo(raw[u].x), s16hi(raw[u].x), s16lo(raw[u].y), s16hi(raw[u].y));
+        v1 = make_float4(s16lo(raw[u].z), s16hi(raw[u].z), s16lo(raw[u].w), s16hi(raw[u].w));
+        *reinterpret_cast<float4 *>(B + it_row[u] * kKCP + it_f[u]) = v0;
+        *reinterpret_cast<float4 *>(B + it_row[u] * kKCP + it_f[u] + 4) = v1;
+      }
+    }
+  };
+  // taps of chunk c for this warp: lane -> row (lane >> 1) of the warp's 16, 16 columns
+  auto fetch_taps = [&](int c, int buf) {
+    if (!warp_active) return;
+    const int c0 = c * kKC;
+    if (c0 + kKC <= lo_w || c0 >= hi_w) return;  // chunk outside the warp's band
+    const int r = (lane >> 1) & 7;               // row within my tile (lanes 0-15 tile 0, 16-31 tile 1)
+    const int cpart = (lane & 1) * 16;
+    float *dst = As + buf * kAsFloats + (w * 16 + (lane >> 1)) * kKC + cpart;
+    const float *src = tile_taps + r * brow + (c0 + cpart - boff);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = c0 + cpart + 4 * i - boff;  // tile column
+      if (k >= -pad && k + 4 <= kp + pad)
+        cp_async16(dst + 4 * i, src + 4 * i);
+      else
+        *reinterpret_cast<float4 *>(dst + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  float acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
+
+  // ---- prologue: chunk 0 ----
+  fetch_window(0);
+  fetch_taps(0, 0);
+  cp_async_commit();
+
+  for (int c = 0; c < n_chunks; ++c) {
+    const int buf = c & 1;
+    store_window(buf);
+    cp_async_wait_all();
+    __syncthreads();  // chunk c is in shared memory; every warp is done with chunk c-1
+    if (c + 1 < n_chunks) {
+      fetch_window(c + 1);
+      fetch_taps(c + 1, buf ^ 1);
+      cp_async_commit();
+    }
+    if (warp_active) {
+      const int c0 = c * kKC;
+      const int k_lo = max(c0, lo_w), k_hi = min(c0 + kKC, hi_w);  // multiples of 4
+      const float *A = As + buf * kAsFloats + (w * 16 + half * 8) * kKC - c0;
+      const float *B = Bs + buf * kBsFloats + l16 * kKCP - c0;
+#pragma unroll 1
+      for (int k = k_lo; k < k_hi; k += 4) {
+        float4 b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = *reinterpret_cast<const float4 *>(B + (16 * i) * kKCP + k);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float4 av = *reinterpret_cast<const float4 *>(A + r * kKC + k);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            acc[r][i] = fmaf(av.x, b[i].x, acc[r][i]);
+            acc[r][i] = fmaf(av.y, b[i].y, acc[r][i]);
+            acc[r][i] = fmaf(av.z, b[i].z, acc[r][i]);
+            acc[r][i] = fmaf(av.w, b[i].w, acc[r][i]);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- WORD2INT + interleaved store: 8 consecutive outputs per series ----
+  if (m0 >= sc.n_out) return;
+  const bool full_rows = m0 + 8 <= sc.n_out;
+  const bool vec_ok = (a.out_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+  if (CH == 2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // stream l16 + 16*j: thread columns 2j (left), 2j+1 (right)
+      const uint32_t s = sg * kStreams + l16 + 16 * j;
+      if (s >= a.n_streams) continue;
+      int16_t *dst = a.out + static_cast<size_t>(s) * a.out_stride + static_cast<size_t>(m0) * 2;
+      uint32_t pk[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const uint32_t lo = static_cast<uint32_t>(word2int_fast(acc[r][2 * j])) & 0xffffu;
+        const uint32_t hi = static_cast<uint32_t>(word2int_fast(acc[r][2 * j + 1])) << 16;
+        pk[r] = lo | hi;
+      }
+      if (full_rows && vec_ok) {
+        reinterpret_cast<uint4 *>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        reinterpret_cast<uint4 *>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (m0 + r < sc.n_out) reinterpret_cast<uint32_t *>(dst)[r] = pk[r];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // series l16 + 16*i
+      const uint32_t s = sg * kStreams + l16 + 16 * i;
+      if (s >= a.n_streams) continue;
+      int16_t *dst = a.out + static_cast<size_t>(s) * a.out_stride + m0;
+      uint32_t pk[4];
+#pragma unroll
+      for (int r = 0; r < 8; r += 2) {
+        const uint32_t lo = static_cast<uint32_t>(word2int_fast(acc[r][i])) & 0xffffu;
+        const uint32_t hi = static_cast<uint32_t>(word2int_fast(acc[r + 1][i])) << 16;
+        pk[r / 2] = lo | hi;
+      }
+      if (full_rows && vec_ok) {
+        reinterpret_cast<uint4 *>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (m0 + r < sc.n_out)
+            dst[r] = static_cast<int16_t>((r & 1) ? (pk[r / 2] >> 16) : (pk[r / 2] & 0xffffu));
+      }
+    }
+  }
+}
+
+template <int CH>
+cudaError_t launch_one(const CallArgs &a, const StreamGeom &g, cudaStream_t stream) {
+  auto kern = stream_fir_kernel<CH>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  kern<<<g.n_sg * g.n_rg, kNT, kSmemBytes, stream>>>(a, g);
+  return cudaGetLastError();
+}
+
+bool geometry(const CallArgs &a, StreamGeom *g) {
+  const uint32_t n_series = a.n_streams * a.channels;
+  g->n_sg = (n_series + kTS - 1) / kTS;
+  g->n_rg = (a.uniform.n_out + kTM - 1) / kTM;
+  return static_cast<uint64_t>(g->n_sg) * g->n_rg <= 0x3fffffffull;
+}
+
+}  // namespace
+
+cudaError_t tiled_prepare_device() { return cudaSuccess; }
+
+bool tiled_qualifies(const CallArgs &a, int sm_count, TiledConfig *cfg) {
+  (void)sm_count;
+  if (a.per_stream != nullptr) return false;  // streams at different positions -> strict kernel
+  if (a.channels != 1 && a.channels != 2) return false;
+  if (a.filt.band == nullptr) return false;   // band table too large for this ratio
+  if (a.uniform.n_out == 0) return false;
+  // 16-byte loads of the history (our own buffer); unaligned input rows are handled in-kernel
+  if ((reinterpret_cast<uintptr_t>(a.hist_src) & 15) != 0 || a.hist_stride % 8 != 0 || a.hist_frames % 8 != 0)
+    return false;
+  // window positions are handled as int
+  if (a.uniform.n_in > 0x3fffffffu || a.uniform.ls0 > 0x3fffffff) return false;
+  StreamGeom g;
+  if (!geometry(a, &g)) return false;
+  cfg->variant = 0;
+  cfg->smem_bytes = kSmemBytes;
+  cfg->grid = g.n_sg * g.n_rg;
+  return true;
+}
+
+cudaError_t launch_tiled(const CallArgs &a, const TiledConfig &cfg, cudaStream_t stream, uint32_t *launches) {
+  (void)cfg;
+  StreamGeom g;
+  if (!geometry(a, &g)) return cudaErrorInvalidConfiguration;
+  const cudaError_t e = (a.channels == 2) ? launch_one<2>(a, g, stream) : launch_one<1>(a, g, stream);
+  if (e == cudaSuccess && launches) *launches += 1;
+  return e;
+}
+
+}  // namespace spxb
