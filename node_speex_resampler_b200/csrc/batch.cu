@@ -451,8 +451,14 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
   }
   Decided d = decide(b, in_frames, out_frames, sl.h_calls);
 
-  const size_t dev_in_stride = round_up(static_cast<size_t>(d.max_n_in) * ch, 8);
-  const size_t dev_out_stride = round_up(static_cast<size_t>(d.max_n_out) * ch, 8);
+  // Device rows mirror densely packed pinned host rows (one flat DMA, no per-row pitch walk);
+  // anything else is re-pitched to 16-byte rows.
+  const bool dense_in = d.uniform && in_stride_frames == d.max_n_in && is_pinned_or_device(in);
+  const bool dense_out = d.uniform && out_stride_frames == d.max_n_out && is_pinned_or_device(out);
+  const size_t dev_in_stride = dense_in ? static_cast<size_t>(d.max_n_in) * ch
+                                        : round_up(static_cast<size_t>(d.max_n_in) * ch, 8);
+  const size_t dev_out_stride = dense_out ? static_cast<size_t>(d.max_n_out) * ch
+                                          : round_up(static_cast<size_t>(d.max_n_out) * ch, 8);
   if (int e = grow_device(&sl.d_in, &sl.d_in_cap, std::max<size_t>(dev_in_stride * S, 8))) return e;
   if (int e = grow_device(&sl.d_out, &sl.d_out_cap, std::max<size_t>(dev_out_stride * S, 8))) return e;
 
@@ -471,7 +477,9 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
   // ---- H2D ----
   const size_t in_row_bytes = static_cast<size_t>(d.max_n_in) * ch * sizeof(int16_t);
   const bool direct_in = d.uniform && is_pinned_or_device(in);
-  if (direct_in) {
+  if (dense_in) {
+    SPXB_CUDA(cudaMemcpyAsync(sl.d_in, in, in_row_bytes * S, cudaMemcpyDefault, b->s_in));
+  } else if (direct_in) {
     SPXB_CUDA(cudaMemcpy2DAsync(sl.d_in, dev_in_stride * sizeof(int16_t), in,
                                 in_stride_frames * ch * sizeof(int16_t), in_row_bytes, S,
                                 cudaMemcpyDefault, b->s_in));
@@ -503,7 +511,9 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
   const size_t out_row_bytes = static_cast<size_t>(d.max_n_out) * ch * sizeof(int16_t);
   if (d.max_n_out != 0) {
     const bool direct_out = d.uniform && is_pinned_or_device(out);
-    if (direct_out) {
+    if (dense_out) {
+      SPXB_CUDA(cudaMemcpyAsync(out, sl.d_out, out_row_bytes * S, cudaMemcpyDefault, b->s_out));
+    } else if (direct_out) {
       SPXB_CUDA(cudaMemcpy2DAsync(out, out_stride_frames * ch * sizeof(int16_t), sl.d_out,
                                   dev_out_stride * sizeof(int16_t), out_row_bytes, S,
                                   cudaMemcpyDefault, b->s_out));

@@ -32,15 +32,22 @@ namespace spxb {
 
 namespace {
 
-constexpr int kKC = 32;          // window frames per chunk
-constexpr int kKCP = kKC + 4;    // padded Bs row (36 floats: rows 16 B apart modulo 128 B)
-constexpr int kTS = 128;         // series per CTA
-constexpr int kWarps = 4;
-constexpr int kNT = kWarps * 32;
-constexpr int kTM = 16 * kWarps; // outputs per CTA
-constexpr int kBsFloats = kTS * kKCP;
-constexpr int kAsFloats = kWarps * 16 * kKC;
-constexpr uint32_t kSmemBytes = 2u * (kBsFloats + kAsFloats) * sizeof(float);
+// CW = series per lane (8: 8x8 register tile, 4: 8x4), WARPS per CTA, KC = window frames per
+// chunk (32 or 64). Bs rows are padded by 4 floats so consecutive rows sit 16 B apart modulo
+// 128 B (the 16 lanes of a half-warp then read 16 distinct rows in two wavefronts).
+template <int CW, int WARPS, int KC>
+struct Shape {
+  static constexpr int kKC = KC;
+  static constexpr int kKCP = KC + 4;
+  static constexpr int kTS = 16 * CW;          // series per CTA
+  static constexpr int kNT = WARPS * 32;
+  static constexpr int kTM = 16 * WARPS;       // outputs per CTA
+  static constexpr int kBsFloats = kTS * kKCP;
+  static constexpr int kAsFloats = WARPS * 16 * KC;
+  static constexpr uint32_t kSmemBytes = 2u * (kBsFloats + kAsFloats) * sizeof(float);
+  // resident CTAs per SM the register budget is tuned for (8x8: 168 registers)
+  static constexpr int kMinBlocks = (CW == 8 ? 3 : 4) * (4 / WARPS);
+};
 
 struct StreamGeom {
   uint32_t n_sg;  // series groups (grid.x = n_sg * n_rg)
@@ -59,9 +66,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // 16 bytes of one stream's PCM starting at frame f (CH == 2: 4 frames, CH == 1: 8 frames):
 // history for f < 0, the call's input for f >= 0, zeros outside both.
+// in_align: largest of 16 / 8 / 4 / 2 bytes that every input row start is aligned to.
 template <int CH>
 __device__ __forceinline__ uint4 fetch_raw16(const CallArgs &a, const StreamCall &sc, uint32_t s, int f,
-                                             bool in_vec) {
+                                             int in_align) {
   constexpr int FPI = 8 / CH;  // frames per item
   uint4 raw = make_uint4(0u, 0u, 0u, 0u);
   if (s >= a.n_streams) return raw;
@@ -75,8 +83,19 @@ __device__ __forceinline__ uint4 fetch_raw16(const CallArgs &a, const StreamCall
   if (static_cast<uint32_t>(f) >= sc.n_in) return raw;
   const int16_t *src = a.in + static_cast<size_t>(s) * a.in_stride + static_cast<size_t>(f) * CH;
   const int avail = min(FPI, static_cast<int>(sc.n_in) - f);
-  if (avail == FPI && in_vec) return __ldg(reinterpret_cast<const uint4 *>(src));
-  // tail of the input, or caller rows that are not 16-byte aligned: sample by sample
+  if (avail == FPI) {
+    if (in_align == 16) return __ldg(reinterpret_cast<const uint4 *>(src));
+    if (in_align == 8) {
+      const uint2 lo = __ldg(reinterpret_cast<const uint2 *>(src));
+      const uint2 hi = __ldg(reinterpret_cast<const uint2 *>(src) + 1);
+      return make_uint4(lo.x, lo.y, hi.x, hi.y);
+    }
+    if (in_align == 4) {
+      const uint32_t *p = reinterpret_cast<const uint32_t *>(src);
+      return make_uint4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+    }
+  }
+  // tail of the input, or rows that are only 2-byte aligned: sample by sample
   uint32_t w[4] = {0u, 0u, 0u, 0u};
   const int n = avail * CH;
 #pragma unroll
@@ -85,11 +104,16 @@ __device__ __forceinline__ uint4 fetch_raw16(const CallArgs &a, const StreamCall
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-template <int CH>
-__global__ void __launch_bounds__(kNT, 3) stream_fir_kernel(const CallArgs a, const StreamGeom g) {
+template <int CH, int CW, int WARPS, int KC>
+__global__ void __launch_bounds__(Shape<CW, WARPS, KC>::kNT, Shape<CW, WARPS, KC>::kMinBlocks)
+    stream_fir_kernel(const CallArgs a, const StreamGeom g) {
+  using SH = Shape<CW, WARPS, KC>;
+  constexpr int kKC = SH::kKC, kKCP = SH::kKCP;
+  constexpr int kTS = SH::kTS, kNT = SH::kNT, kTM = SH::kTM;
+  constexpr int kBsFloats = SH::kBsFloats, kAsFloats = SH::kAsFloats;
   extern __shared__ __align__(16) float smem[];
   float *Bs = smem;                   // [2][kTS][kKCP]
-  float *As = smem + 2 * kBsFloats;   // [2][kWarps][16][kKC]
+  float *As = smem + 2 * kBsFloats;   // [2][WARPS][16][kKC]
 
   constexpr int kStreams = kTS / CH;  // streams per CTA
   constexpr int FPI = 8 / CH;         // frames per 16-byte item
@@ -103,7 +127,10 @@ __global__ void __launch_bounds__(kNT, 3) stream_fir_kernel(const CallArgs a, co
   const int N = static_cast<int>(a.filt.taps);
   const uint32_t num = a.filt.num, den = a.filt.den;
   const uint32_t M0 = rg * kTM;
-  const bool in_vec = (a.in_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
+  // alignment every input row start shares (items start at multiples of 16 bytes within a row)
+  const uint32_t row_bits = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(a.in)) |
+                            (static_cast<uint32_t>(a.in_stride) * 2u);
+  const int in_align = (row_bits & 15u) == 0 ? 16 : (row_bits & 7u) == 0 ? 8 : (row_bits & 3u) == 0 ? 4 : 2;
 
   // first frame of output m's window in X~ coordinates (history is f < 0), and its phase
   auto window_start = [&](uint32_t m, uint32_t *phase) -> int {
@@ -114,23 +141,68 @@ __global__ void __launch_bounds__(kNT, 3) stream_fir_kernel(const CallArgs a, co
   };
 
   // ---- this CTA's slice of the history slide (resample.c:898-899) ----
-  // stream sl of the group is copied by the row-group CTA with rg == sl % n_rg
+  // stream sl of the group is copied by the row-group CTA with rg == sl % n_rg; new history
+  // element e = element consumed*CH + e of (old history || input). Copies are as wide as the
+  // alignment of that shift allows and all loads of a pass are issued before the stores.
   {
-    const uint32_t hist_elems = a.hist_frames * CH;
-    for (uint32_t sl = rg; sl < static_cast<uint32_t>(kStreams); sl += g.n_rg) {
-      const uint32_t s = sg * kStreams + sl;
-      if (s >= a.n_streams) break;
-      const int16_t *hs = a.hist_src + static_cast<size_t>(s) * a.hist_stride;
-      const int16_t *is = a.in + static_cast<size_t>(s) * a.in_stride;
-      int16_t *hd = a.hist_dst + static_cast<size_t>(s) * a.hist_stride;
-      const size_t shift = static_cast<size_t>(sc.consumed) * CH;
-      for (uint32_t e = tid; e < hist_elems; e += kNT) {
-        const size_t src = shift + e;
-        hd[e] = (src < hist_elems) ? hs[src] : is[src - hist_elems];
+    const uint32_t hist_elems = a.hist_frames * CH;  // multiple of 8
+    const size_t shift = static_cast<size_t>(sc.consumed) * CH;
+    // elements per copy: limited by the alignment of the shift and of the input rows
+    const int vshift = (shift % 8 == 0) ? 8 : (shift % 4 == 0) ? 4 : (shift % 2 == 0) ? 2 : 1;
+    const int vw = min(vshift, in_align / 2);
+    constexpr int U = 4;
+    for (uint32_t sl0 = rg; sl0 < static_cast<uint32_t>(kStreams); sl0 += g.n_rg * U) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t sl = sl0 + u * g.n_rg;
+        const uint32_t s = sg * kStreams + sl;
+        const uint32_t e = tid * vw;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (sl < static_cast<uint32_t>(kStreams) && s < a.n_streams && e < hist_elems) {
+          const size_t src = shift + e;
+          const int16_t *p = (src < hist_elems) ? a.hist_src + static_cast<size_t>(s) * a.hist_stride + src
+                                                : a.in + static_cast<size_t>(s) * a.in_stride + (src - hist_elems);
+          if (vw == 8) v[u] = *reinterpret_cast<const uint4 *>(p);
+          else if (vw == 4) { const uint2 t = *reinterpret_cast<const uint2 *>(p); v[u].x = t.x; v[u].y = t.y; }
+          else if (vw == 2) v[u].x = *reinterpret_cast<const uint32_t *>(p);
+          else v[u].x = static_cast<uint16_t>(*p);
+        }
       }
-      if (tid == 0) {
-        a.last_sample[s] = sc.ls1;
-        a.samp_frac[s] = sc.frac1;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t sl = sl0 + u * g.n_rg;
+        const uint32_t s = sg * kStreams + sl;
+        const uint32_t e = tid * vw;
+        if (sl < static_cast<uint32_t>(kStreams) && s < a.n_streams) {
+          if (e < hist_elems) {
+            int16_t *d = a.hist_dst + static_cast<size_t>(s) * a.hist_stride + e;
+            if (vw == 8) *reinterpret_cast<uint4 *>(d) = v[u];
+            else if (vw == 4) *reinterpret_cast<uint2 *>(d) = make_uint2(v[u].x, v[u].y);
+            else if (vw == 2) *reinterpret_cast<uint32_t *>(d) = v[u].x;
+            else *d = static_cast<int16_t>(v[u].x);
+          }
+          if (tid == 0) {
+            a.last_sample[s] = sc.ls1;
+            a.samp_frac[s] = sc.frac1;
+          }
+        }
+      }
+      // histories longer than one pass of the CTA (kNT * vw elements): remaining elements
+      for (int u = 0; u < U; ++u) {
+        const uint32_t sl = sl0 + u * g.n_rg;
+        const uint32_t s = sg * kStreams + sl;
+        if (sl >= static_cast<uint32_t>(kStreams) || s >= a.n_streams) continue;
+        for (uint32_t e = (kNT + tid) * vw; e < hist_elems; e += kNT * vw) {
+          const size_t src = shift + e;
+          const int16_t *p = (src < hist_elems) ? a.hist_src + static_cast<size_t>(s) * a.hist_stride + src
+                                                : a.in + static_cast<size_t>(s) * a.in_stride + (src - hist_elems);
+          int16_t *d = a.hist_dst + static_cast<size_t>(s) * a.hist_stride + e;
+          if (vw == 8) *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(p);
+          else if (vw == 4) *reinterpret_cast<uint2 *>(d) = *reinterpret_cast<const uint2 *>(p);
+          else if (vw == 2) *reinterpret_cast<uint32_t *>(d) = *reinterpret_cast<const uint32_t *>(p);
+          else *d = *p;
+        }
       }
     }
   }
@@ -165,13 +237,14 @@ __global__ void __launch_bounds__(kNT, 3) stream_fir_kernel(const CallArgs a, co
     it_f[u] = (id % per_stream) * FPI;
     // lane l16 = sl % 16 owns the series; CH == 2: thread columns 2j (left), 2j+1 (right)
     it_row[u] = (CH == 2) ? (it_sl[u] & 15) + 32 * (it_sl[u] >> 4) : it_sl[u];
+    static_assert(kItems >= 1 && kItems * kNT == kStreams * per_stream, "window items must tile the CTA");
   }
 
   uint4 raw[kItems];
   auto fetch_window = [&](int c) {
 #pragma unroll
     for (int u = 0; u < kItems; ++u)
-      raw[u] = fetch_raw16<CH>(a, sc, sg * kStreams + it_sl[u], W0 + c * kKC + it_f[u], in_vec);
+      raw[u] = fetch_raw16<CH>(a, sc, sg * kStreams + it_sl[u], W0 + c * kKC + it_f[u], in_align);
   };
   auto store_window = [&](int buf) {
     float *B = Bs + buf * kBsFloats;
@@ -197,11 +270,11 @@ __global__ void __launch_bounds__(kNT, 3) stream_fir_kernel(const CallArgs a, co
     const int c0 = c * kKC;
     if (c0 + kKC <= lo_w || c0 >= hi_w) return;  // chunk outside the warp's band
     const int r = (lane >> 1) & 7;               // row within my tile (lanes 0-15 tile 0, 16-31 tile 1)
-    const int cpart = (lane & 1) * 16;
+    const int cpart = (lane & 1) * (kKC / 2);
     float *dst = As + buf * kAsFloats + (w * 16 + (lane >> 1)) * kKC + cpart;
     const float *src = tile_taps + r * brow + (c0 + cpart - boff);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kKC / 8; ++i) {
       const int k = c0 + cpart + 4 * i - boff;  // tile column
       if (k >= -pad && k + 4 <= kp + pad)
         cp_async16(dst + 4 * i, src + 4 * i);
@@ -210,11 +283,11 @@ __global__ void __launch_bounds__(kNT, 3) stream_fir_kernel(const CallArgs a, co
     }
   };
 
-  float acc[8][8];
+  float acc[8][CW];
 #pragma unroll
   for (int r = 0; r < 8; ++r)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
+    for (int i = 0; i < CW; ++i) acc[r][i] = 0.f;
 
   // ---- prologue: chunk 0 ----
   fetch_window(0);
@@ -236,16 +309,16 @@ __global__ void __launch_bounds__(kNT, 3) stream_fir_kernel(const CallArgs a, co
       const int k_lo = max(c0, lo_w), k_hi = min(c0 + kKC, hi_w);  // multiples of 4
       const float *A = As + buf * kAsFloats + (w * 16 + half * 8) * kKC - c0;
       const float *B = Bs + buf * kBsFloats + l16 * kKCP - c0;
-#pragma unroll 1
+#pragma unroll(CW == 8 ? 1 : 2)
       for (int k = k_lo; k < k_hi; k += 4) {
-        float4 b[8];
+        float4 b[CW];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b[i] = *reinterpret_cast<const float4 *>(B + (16 * i) * kKCP + k);
+        for (int i = 0; i < CW; ++i) b[i] = *reinterpret_cast<const float4 *>(B + (16 * i) * kKCP + k);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const float4 av = *reinterpret_cast<const float4 *>(A + r * kKC + k);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < CW; ++i) {
             acc[r][i] = fmaf(av.x, b[i].x, acc[r][i]);
             acc[r][i] = fmaf(av.y, b[i].y, acc[r][i]);
             acc[r][i] = fmaf(av.z, b[i].z, acc[r][i]);
@@ -262,7 +335,7 @@ __global__ void __launch_bounds__(kNT, 3) stream_fir_kernel(const CallArgs a, co
   const bool vec_ok = (a.out_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
   if (CH == 2) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {  // stream l16 + 16*j: thread columns 2j (left), 2j+1 (right)
+    for (int j = 0; j < CW / 2; ++j) {  // stream l16 + 16*j: thread columns 2j (left), 2j+1 (right)
       const uint32_t s = sg * kStreams + l16 + 16 * j;
       if (s >= a.n_streams) continue;
       int16_t *dst = a.out + static_cast<size_t>(s) * a.out_stride + static_cast<size_t>(m0) * 2;
@@ -284,7 +357,7 @@ __global__ void __launch_bounds__(kNT, 3) stream_fir_kernel(const CallArgs a, co
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {  // series l16 + 16*i
+    for (int i = 0; i < CW; ++i) {  // series l16 + 16*i
       const uint32_t s = sg * kStreams + l16 + 16 * i;
       if (s >= a.n_streams) continue;
       int16_t *dst = a.out + static_cast<size_t>(s) * a.out_stride + m0;
@@ -307,26 +380,40 @@ __global__ void __launch_bounds__(kNT, 3) stream_fir_kernel(const CallArgs a, co
   }
 }
 
-template <int CH>
+template <int CH, int CW, int WARPS, int KC>
 cudaError_t launch_one(const CallArgs &a, const StreamGeom &g, cudaStream_t stream) {
-  auto kern = stream_fir_kernel<CH>;
+  using SH = Shape<CW, WARPS, KC>;
+  auto kern = stream_fir_kernel<CH, CW, WARPS, KC>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SH::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured_dev = dev;
   }
-  kern<<<g.n_sg * g.n_rg, kNT, kSmemBytes, stream>>>(a, g);
+  kern<<<g.n_sg * g.n_rg, SH::kNT, SH::kSmemBytes, stream>>>(a, g);
   return cudaGetLastError();
 }
 
-bool geometry(const CallArgs &a, StreamGeom *g) {
+bool geometry(const CallArgs &a, int cw, int warps, StreamGeom *g) {
   const uint32_t n_series = a.n_streams * a.channels;
-  g->n_sg = (n_series + kTS - 1) / kTS;
-  g->n_rg = (a.uniform.n_out + kTM - 1) / kTM;
+  const uint32_t ts = 16 * cw, tm = 16 * warps;
+  g->n_sg = (n_series + ts - 1) / ts;
+  g->n_rg = (a.uniform.n_out + tm - 1) / tm;
   return static_cast<uint64_t>(g->n_sg) * g->n_rg <= 0x3fffffffull;
+}
+
+// variant = cw*100 + warps*10 + kc/32   (SPXB_STREAM_SHAPE overrides, e.g. 841)
+int pick_variant(const CallArgs &a, int sm_count) {
+  static const int forced = [] {
+    const char *e = getenv("SPXB_STREAM_SHAPE");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced) return forced;
+  (void)a;
+  (void)sm_count;
+  return 441;  // 8x4 register tiles, 4 warps, 32-frame chunks: best of the r1 sweep on C3/C4/C5
 }
 
 }  // namespace
@@ -334,7 +421,6 @@ bool geometry(const CallArgs &a, StreamGeom *g) {
 cudaError_t tiled_prepare_device() { return cudaSuccess; }
 
 bool tiled_qualifies(const CallArgs &a, int sm_count, TiledConfig *cfg) {
-  (void)sm_count;
   if (a.per_stream != nullptr) return false;  // streams at different positions -> strict kernel
   if (a.channels != 1 && a.channels != 2) return false;
   if (a.filt.band == nullptr) return false;   // band table too large for this ratio
@@ -344,19 +430,29 @@ bool tiled_qualifies(const CallArgs &a, int sm_count, TiledConfig *cfg) {
     return false;
   // window positions are handled as int
   if (a.uniform.n_in > 0x3fffffffu || a.uniform.ls0 > 0x3fffffff) return false;
+  const int v = pick_variant(a, sm_count);
   StreamGeom g;
-  if (!geometry(a, &g)) return false;
-  cfg->variant = 0;
-  cfg->smem_bytes = kSmemBytes;
+  if (!geometry(a, v / 100, (v / 10) % 10, &g)) return false;
+  cfg->variant = v;
+  cfg->smem_bytes = 0;
   cfg->grid = g.n_sg * g.n_rg;
   return true;
 }
 
 cudaError_t launch_tiled(const CallArgs &a, const TiledConfig &cfg, cudaStream_t stream, uint32_t *launches) {
-  (void)cfg;
+  const int cw = cfg.variant / 100, warps = (cfg.variant / 10) % 10, kc = 32 * (cfg.variant % 10);
   StreamGeom g;
-  if (!geometry(a, &g)) return cudaErrorInvalidConfiguration;
-  const cudaError_t e = (a.channels == 2) ? launch_one<2>(a, g, stream) : launch_one<1>(a, g, stream);
+  if (!geometry(a, cw, warps, &g)) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaErrorInvalidConfiguration;
+#define SPXB_LAUNCH(CHV, CWV, WV, KCV) \
+  if (a.channels == CHV && cw == CWV && warps == WV && kc == KCV) e = launch_one<CHV, CWV, WV, KCV>(a, g, stream);
+#define SPXB_LAUNCH_CH(CHV)                                                                   \
+  SPXB_LAUNCH(CHV, 8, 4, 32) SPXB_LAUNCH(CHV, 8, 2, 32) SPXB_LAUNCH(CHV, 4, 4, 32) SPXB_LAUNCH(CHV, 4, 2, 32) \
+  SPXB_LAUNCH(CHV, 8, 4, 64) SPXB_LAUNCH(CHV, 8, 2, 64) SPXB_LAUNCH(CHV, 4, 4, 64) SPXB_LAUNCH(CHV, 4, 2, 64)
+  SPXB_LAUNCH_CH(2)
+  SPXB_LAUNCH_CH(1)
+#undef SPXB_LAUNCH_CH
+#undef SPXB_LAUNCH
   if (e == cudaSuccess && launches) *launches += 1;
   return e;
 }
