@@ -192,6 +192,10 @@ def ours(args):
     L = pkg.lib()
     wl = args.workload
     S, ch, i, o, q, n = WORKLOADS[wl]
+    # weak scaling: the job is world * S independent streams, rank r owns one contiguous block
+    from node_speex_resampler_b200.sharding import shard_range
+    lo, hi = shard_range(S * world, world, rank)
+    assert hi - lo == S
     info = _lib.FilterInfo()
     L.spxb_filter_describe(i, o, q, C.byref(info))
     N = info.filt_len
@@ -277,9 +281,19 @@ def ours(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # DRAM bytes per launch of this kernel from the committed ncu --set full capture (never measured
+    # under the profiler here); null when no capture exists for the workload
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl)
+        if tr and kernel_used == "tiled":
+            traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
+            traffic_src = tr["source"]
+    except Exception:
+        pass
     roof = {"bound": "fp32_fma", "achieved": flops_per_launch / t_launch / 1e12, "peak": fp32_peak / 1e12,
             "unit": "TFLOP/s", "frac": (flops_per_launch / t_launch) / fp32_peak if fp32_peak else None,
-            "traffic": None,
+            "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": "FFMA probe measured in this run (MEASURED_PEAKS.json has no fp32 entry); "
                            "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
             "flops_per_output_sample": 2 * N, "launch_us": t_launch * 1e6,
