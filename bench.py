@@ -2,7 +2,7 @@
 """bench.py -- throughput of the Speex resampler hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload C3|C4|C5] [--kernel auto|strict|tiled]
+                    [--workload C3|C4|C5] [--kernel auto|strict|tiled|tensor]
 
 One step = one 20 ms processChunk-equivalent for every stream of the batch (state carried
 step to step). Workload (BASELINE.json): C3 = 1024 stereo streams 44100->48000 q7 per GPU
@@ -14,8 +14,11 @@ Prints ONE JSON line (rank 0):
   value      output Msamples/s, inputs already in HBM (hops queued in a ring > L2)
   e2e        same metric through the C ABI with pinned HOST buffers: H2D + kernel + D2H
              every step, pipelined with spxb_batch_submit / spxb_batch_wait
-  roofline   FP32-FMA roofline of the FIR kernel (algorithmic 2*N flops per output sample,
-             SURVEY 8d) against an FFMA probe measured in this run; HBM fraction beside it
+  roofline   of the FIR kernel. Tensor kernel (tcgen05 int8): the algorithmic work (2*N flops
+             per output sample) takes less time at the measured tensor peak than
+             the algorithmic bytes take at the measured HBM peak, so the binding roofline is
+             HBM ("bound": "hbm"); the executed int8 MMA rate is reported beside it. FP32-FMA
+             kernel ("tiled"): FP32 FMA rate against an FFMA probe measured in this run.
   cpu_baseline  the reference's own C (oracle/_ref, kind "reference") or the oracle port on
              this box's host cores, bounded sample of the same workload
 
@@ -201,7 +204,8 @@ def ours(args):
     N = info.filt_len
     cap = int(math.ceil(n * o / i))
     batch = pkg.StreamBatch(S, ch, i, o, q, device=local)
-    batch.set_kernel({"auto": pkg.KERNEL_AUTO, "strict": pkg.KERNEL_STRICT, "tiled": pkg.KERNEL_TILED}[args.kernel])
+    batch.set_kernel({"auto": pkg.KERNEL_AUTO, "strict": pkg.KERNEL_STRICT, "tiled": pkg.KERNEL_TILED,
+                      "tensor": pkg.KERNEL_TENSOR}[args.kernel])
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)  # events below and the batch's kernels share this stream
     assert L.spxb_batch_set_stream(batch._h, C.c_void_p(stream.cuda_stream)) == 0
@@ -268,7 +272,7 @@ def ours(args):
         sec = float(t.item())
     out_samples_step = S * cap * ch  # per GPU
     value = out_samples_step * world * K / sec
-    kernel_used = {0: "auto", 1: "strict", 2: "tiled"}[batch.last_kernel()]
+    kernel_used = {0: "auto", 1: "strict", 2: "tiled", 3: "tensor"}[batch.last_kernel()]
 
     # ---- roofline of the FIR kernel ----
     fp32_peak = L.spxb_measure_fp32_peak(8192)
@@ -285,22 +289,41 @@ def ours(args):
     # under the profiler here); null when no capture exists for the workload
     traffic, traffic_src = None, None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl)
-        if tr and kernel_used == "tiled":
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{wl}:{kernel_used}")
+        if tr:
             traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
             traffic_src = tr["source"]
     except Exception:
         pass
-    roof = {"bound": "fp32_fma", "achieved": flops_per_launch / t_launch / 1e12, "peak": fp32_peak / 1e12,
-            "unit": "TFLOP/s", "frac": (flops_per_launch / t_launch) / fp32_peak if fp32_peak else None,
-            "traffic": traffic, "traffic_source": traffic_src,
-            "peak_source": "FFMA probe measured in this run (MEASURED_PEAKS.json has no fp32 entry); "
-                           "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
-            "flops_per_output_sample": 2 * N, "launch_us": t_launch * 1e6,
-            "hbm": {"achieved": bytes_per_launch / t_launch / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": bytes_per_launch / t_launch / 1e9 / hbm_peak,
-                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
-                    "bytes_per_output_sample": bytes_per_launch / out_samples_step}}
+    hbm = {"achieved": bytes_per_launch / t_launch / 1e9, "peak": hbm_peak, "unit": "GB/s",
+           "frac": bytes_per_launch / t_launch / 1e9 / hbm_peak,
+           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+           "bytes_per_output_sample": bytes_per_launch / out_samples_step}
+    fma = {"achieved": flops_per_launch / t_launch / 1e12, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
+           "frac": (flops_per_launch / t_launch) / fp32_peak if fp32_peak else None,
+           "peak_source": "FFMA probe measured in this run (MEASURED_PEAKS.json has no fp32 entry); "
+                          "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+           "flops_per_output_sample": 2 * N}
+    if kernel_used == "tensor":
+        # binding roofline: max(algorithmic bytes / HBM peak, algorithmic flops / tensor peak)
+        bf16_peak = float(peaks.get("bf16_tflops", 1590.0)) * 1e12
+        t_hbm = bytes_per_launch / (hbm_peak * 1e9)
+        t_tensor = flops_per_launch / bf16_peak
+        geom = batch.tensor_geometry() or {}
+        mma_ops = (geom.get("tiles", 0) * geom.get("groups", 0) * geom.get("ksteps", 0)
+                   * 2 * 128 * 3 * geom.get("nt", 0) * 32 * 2.0)
+        roof = dict(hbm, bound="hbm" if t_hbm >= t_tensor else "tensor", traffic=traffic, traffic_source=traffic_src,
+                    launch_us=t_launch * 1e6, algorithmic_bytes_per_launch=bytes_per_launch,
+                    why_bound=f"algorithmic bytes / measured HBM peak = {t_hbm * 1e6:.2f} us vs algorithmic "
+                              f"2N flops / measured bf16 tensor peak = {t_tensor * 1e6:.2f} us per launch",
+                    tensor={"executed_int8_ops_per_launch": mma_ops, "achieved": mma_ops / t_launch / 1e12,
+                            "unit": "Tops/s (int8 MMA, incl. band padding and the 6 digit products)",
+                            "peak_nominal": 4500.0, "frac_of_nominal": mma_ops / t_launch / 4.5e15,
+                            "geometry": geom},
+                    fp32_fma_equivalent=fma)
+    else:
+        roof = dict(fma, bound="fp32_fma", traffic=traffic, traffic_source=traffic_src, launch_us=t_launch * 1e6,
+                    hbm=hbm)
 
     # ---- end to end through the C ABI with pinned host buffers ----
     L.spxb_batch_use_own_stream(batch._h)
@@ -366,7 +389,9 @@ def ours(args):
     if rank == 0:
         line = {"metric": "output_msamples_per_sec", "value": value / 1e6, "unit": "Msamples/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": sec / K * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "s8 x s8 -> s32 (exact integer FIR)" if kernel_used == "tensor" else "f32",
+                "data": "synthetic",
                 "config": dict(describe(wl), timing=f"median of {reps} regions of exactly {K} steps, CUDA events; "
                                f"inputs: ring of {ring} distinct hops in HBM ({ring * in_slot * 2 >> 20} MiB > L2), "
                                "no L2 flush needed", kernel=kernel_used, filt_len=N),
@@ -388,7 +413,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="auto", choices=["auto", "strict", "tiled"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "strict", "tiled", "tensor"])
     ap.add_argument("--min-seconds", type=float, default=1.0, help="clock-sampling window for the timed regions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

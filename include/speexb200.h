@@ -88,11 +88,14 @@ typedef struct spxb_batch spxb_batch;
 
 /* which device kernel family runs the FIR */
 enum {
-  SPXB_KERNEL_AUTO = 0,   /* tiled when the batch qualifies, else strict */
+  SPXB_KERNEL_AUTO = 0,   /* tensor when the call qualifies, else tiled, else strict */
   SPXB_KERNEL_STRICT = 1, /* one thread per output, the reference's own operation order:
                              bit-exact against the scalar reference */
-  SPXB_KERNEL_TILED = 2   /* register-tiled per-phase FIR (precomputed per-phase taps,
+  SPXB_KERNEL_TILED = 2,  /* register-tiled per-phase FIR (precomputed per-phase taps,
                              fp32 accumulate): <= 1 LSB from the reference */
+  SPXB_KERNEL_TENSOR = 3  /* tcgen05 int8 tensor-core FIR: exact integer dot product with
+                             24-bit fixed-point per-phase taps, one rounding at the end:
+                             <= 1 LSB from the reference */
 };
 
 SPXB_API int spxb_device_count(void);
@@ -108,6 +111,10 @@ SPXB_API spxb_batch *spxb_batch_create(uint32_t n_streams, uint32_t channels,
 SPXB_API void spxb_batch_destroy(spxb_batch *b);
 SPXB_API int spxb_batch_set_kernel(spxb_batch *b, int kernel); /* SPXB_KERNEL_* */
 SPXB_API int spxb_batch_get_kernel(const spxb_batch *b);       /* family used by last call */
+/* launch geometry of the last tensor-kernel call: {outputs per tile, 32-frame MMA steps per
+ * tile, tiles per series group, series groups (128 series each), shared-memory stages,
+ * dynamic shared memory bytes}; RESAMPLER_ERR_BAD_STATE when no tensor call was planned yet */
+SPXB_API int spxb_batch_tensor_geometry(const spxb_batch *b, uint32_t *geom6);
 
 /* One processChunk-equivalent for every stream, HOST buffers (pageable or pinned).
  * Stream s reads in + s*in_stride_frames*channels (in_frames[s] frames) and writes
@@ -213,6 +220,21 @@ SPXB_API long spxb_filter_table(uint32_t in_rate, uint32_t out_rate, int quality
 /* per-phase taps h[phase][j] (den*N floats) the tiled kernel contracts with */
 SPXB_API long spxb_filter_phase_taps(uint32_t in_rate, uint32_t out_rate, int quality,
                                      float *dst, size_t cap);
+
+/* tensor kernel (SPXB_KERNEL_TENSOR): the per-phase taps as signed 24-bit fixed point,
+ * h[phase][j] = round(tap * 2^shift) with |h| <= 8355711 (three balanced base-256 digits) */
+SPXB_API long spxb_filter_fixed_taps(uint32_t in_rate, uint32_t out_rate, int quality,
+                                     int32_t *dst, size_t cap, int *shift);
+/* output tiles of one uniform call at stream position (last_sample, samp_frac_num): per tile
+ * {first output m0, first frame of the K axis kf0 (history is < 0), phase of m0, q0 - kf0};
+ * dst has room for cap_tiles x 4 ints; *ksteps = 32-frame MMA steps per tile. Returns tiles. */
+SPXB_API long spxb_tensor_plan(uint32_t in_rate, uint32_t out_rate, int quality,
+                               int32_t last_sample, uint32_t samp_frac_num, uint32_t n_out,
+                               uint32_t nt, int32_t *dst, size_t cap_tiles, uint32_t *ksteps);
+/* the int8 tap tile of (phase0, delta) exactly as the kernel consumes it:
+ * [chunk < 2*ksteps][row < 3*nt][16 B], rows = digit d2 | d1 | d0 of each of the nt outputs */
+SPXB_API long spxb_tensor_tap_tile(uint32_t in_rate, uint32_t out_rate, int quality, uint32_t nt,
+                                   uint32_t phase0, uint32_t delta, int8_t *dst, size_t cap);
 
 /* lengths and next state of one speex_resampler_process_int call (resample.c:968-1036
  * with :878-902), without touching samples: a pure function of the stream position. */

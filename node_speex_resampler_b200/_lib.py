@@ -19,15 +19,16 @@ DECLARED_SYMBOLS = (
     "speex_resampler_get_input_latency", "speex_resampler_get_output_latency",
     "speex_resampler_skip_zeros", "speex_resampler_reset_mem",
     "spxb_device_count", "spxb_last_error", "spxb_batch_create", "spxb_batch_destroy",
-    "spxb_batch_set_kernel", "spxb_batch_get_kernel", "spxb_batch_process", "spxb_batch_submit",
+    "spxb_batch_set_kernel", "spxb_batch_get_kernel", "spxb_batch_tensor_geometry", "spxb_batch_process", "spxb_batch_submit",
     "spxb_batch_wait", "spxb_batch_pipeline_depth", "spxb_batch_process_device",
     "spxb_batch_process_device_uniform", "spxb_batch_process_device_ring", "spxb_batch_set_stream", "spxb_batch_use_own_stream", "spxb_batch_synchronize",
     "spxb_batch_get_state", "spxb_batch_set_state", "spxb_batch_reset", "spxb_batch_skip_zeros",
     "spxb_batch_counters", "spxb_host_alloc", "spxb_host_free", "spxb_filter_describe",
-    "spxb_filter_table", "spxb_filter_phase_taps", "spxb_plan_call", "spxb_version", "spxb_resampler_batch",
+    "spxb_filter_table", "spxb_filter_phase_taps", "spxb_filter_fixed_taps", "spxb_tensor_plan",
+    "spxb_tensor_tap_tile", "spxb_plan_call", "spxb_version", "spxb_resampler_batch",
 )
 
-KERNEL_AUTO, KERNEL_STRICT, KERNEL_TILED = 0, 1, 2
+KERNEL_AUTO, KERNEL_STRICT, KERNEL_TILED, KERNEL_TENSOR = 0, 1, 2, 3
 
 
 class FilterInfo(C.Structure):
@@ -95,6 +96,13 @@ def _bind(L):
     L.spxb_filter_table.argtypes = [u32, u32, C.c_int, vp, sz]
     L.spxb_filter_phase_taps.restype = C.c_long
     L.spxb_filter_phase_taps.argtypes = [u32, u32, C.c_int, vp, sz]
+    L.spxb_batch_tensor_geometry.argtypes = [vp, vp]
+    L.spxb_filter_fixed_taps.restype = C.c_long
+    L.spxb_filter_fixed_taps.argtypes = [u32, u32, C.c_int, vp, sz, pint]
+    L.spxb_tensor_plan.restype = C.c_long
+    L.spxb_tensor_plan.argtypes = [u32, u32, C.c_int, i32, u32, u32, u32, vp, sz, pu32]
+    L.spxb_tensor_tap_tile.restype = C.c_long
+    L.spxb_tensor_tap_tile.argtypes = [u32, u32, C.c_int, u32, u32, u32, vp, sz]
     L.spxb_plan_call.argtypes = [u32, u32, i32, u32, u32, u32, C.POINTER(CallPlan)]
     L.spxb_resampler_batch.restype = vp
     L.spxb_resampler_batch.argtypes = [vp]

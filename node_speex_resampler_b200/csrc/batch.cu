@@ -19,6 +19,7 @@
 #include "device_types.h"
 #include "filter_bank.h"
 #include "launch.h"
+#include "umma_plan.h"
 
 namespace spxb {
 
@@ -91,6 +92,7 @@ struct spxb_batch {
   cudaEvent_t ev_state = nullptr;
   Slot slots[kPipelineDepth];
   uint64_t next_ticket = 1;
+  UmmaContext *umma = nullptr;  // tensor kernel state (nullptr: filter not covered)
   int kernel_pref = SPXB_KERNEL_AUTO;
   int last_kernel = SPXB_KERNEL_AUTO;
   spxb_counters counters{};
@@ -237,11 +239,21 @@ static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elem
   cudaError_t ce = cudaSuccess;
   int used = SPXB_KERNEL_STRICT;
   TiledConfig cfg;
-  const bool want_tiled = b->kernel_pref != SPXB_KERNEL_STRICT;
-  if (want_tiled && b->d_band && tiled_qualifies(a, b->sm_count, &cfg)) {
+  const int pref = b->kernel_pref;
+  const bool want_tensor = pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TENSOR;
+  const bool want_tiled = pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TILED;
+  if (want_tensor && max_n_out != 0 && umma_prepare(b->umma, a, b->s_compute, &ce)) {
+    ce = launch_umma(b->umma, a, b->s_compute, &launches);
+    used = SPXB_KERNEL_TENSOR;
+  } else if (ce != cudaSuccess) {
+    // planning failed on a CUDA error (not merely "not covered")
+  } else if (pref == SPXB_KERNEL_TENSOR && max_n_out != 0) {
+    set_error("SPXB_KERNEL_TENSOR requested but this call does not qualify for the tensor kernel");
+    return RESAMPLER_ERR_BAD_STATE;
+  } else if (want_tiled && b->d_band && tiled_qualifies(a, b->sm_count, &cfg)) {
     ce = launch_tiled(a, cfg, b->s_compute, &launches);
     used = SPXB_KERNEL_TILED;
-  } else if (b->kernel_pref == SPXB_KERNEL_TILED && max_n_out != 0) {
+  } else if (pref == SPXB_KERNEL_TILED && max_n_out != 0) {
     set_error("SPXB_KERNEL_TILED requested but this call does not qualify for the tiled kernel");
     return RESAMPLER_ERR_BAD_STATE;
   } else {
@@ -338,6 +350,7 @@ static void free_batch(spxb_batch *b) {
   if (b->d_taps) cudaFree(b->d_taps);
   if (b->d_blend) cudaFree(b->d_blend);
   if (b->d_band) cudaFree(b->d_band);
+  umma_destroy(b->umma);
   if (b->d_hist[0]) cudaFree(b->d_hist[0]);
   if (b->d_hist[1]) cudaFree(b->d_hist[1]);
   if (b->d_last_sample) cudaFree(b->d_last_sample);
@@ -394,6 +407,8 @@ static int create_batch(spxb_batch *b) {
       b->band_row = band.row;
     }
   }
+  // tensor kernel: fixed-point taps + tap-tile pool (nullptr when the filter is not covered)
+  b->umma = umma_create(sp, table, b->channels, b->sm_count);
   if (!sp.direct) {
     std::vector<float> blend(static_cast<size_t>(sp.den) * 4);
     for (uint32_t ph = 0; ph < sp.den; ++ph) {
@@ -405,7 +420,7 @@ static int create_batch(spxb_batch *b) {
   }
 
   // stream state, zeroed: resample.c:721-725 and the calloc'd per-channel arrays :838-843
-  b->hist_frames = static_cast<uint32_t>(round_up(sp.taps - 1, 8));
+  b->hist_frames = static_cast<uint32_t>(round_up(sp.taps - 1, 16));  // 16-frame K chunks (tensor kernel)
   b->hist_stride = static_cast<uint32_t>(round_up(static_cast<size_t>(b->hist_frames) * b->channels, 8));
   const size_t hist_bytes = static_cast<size_t>(b->n_streams) * b->hist_stride * sizeof(int16_t);
   for (int i = 0; i < 2; ++i) {
@@ -599,12 +614,18 @@ spxb_batch *spxb_batch_create(uint32_t n_streams, uint32_t channels, uint32_t in
 void spxb_batch_destroy(spxb_batch *b) { free_batch(b); }
 
 int spxb_batch_set_kernel(spxb_batch *b, int kernel) {
-  if (!b || kernel < SPXB_KERNEL_AUTO || kernel > SPXB_KERNEL_TILED) return RESAMPLER_ERR_INVALID_ARG;
+  if (!b || kernel < SPXB_KERNEL_AUTO || kernel > SPXB_KERNEL_TENSOR) return RESAMPLER_ERR_INVALID_ARG;
   b->kernel_pref = kernel;
   return 0;
 }
 
 int spxb_batch_get_kernel(const spxb_batch *b) { return b ? b->last_kernel : 0; }
+
+int spxb_batch_tensor_geometry(const spxb_batch *b, uint32_t *geom6) {
+  if (!b || !geom6) return RESAMPLER_ERR_INVALID_ARG;
+  umma_geometry(b->umma, geom6);
+  return geom6[0] ? 0 : RESAMPLER_ERR_BAD_STATE;
+}
 
 int spxb_batch_pipeline_depth(const spxb_batch *) { return kPipelineDepth - 1; }
 
@@ -851,6 +872,59 @@ long spxb_filter_phase_taps(uint32_t in_rate, uint32_t out_rate, int quality, fl
   std::vector<float> t = build_phase_taps(s, build_reference_table(s));
   std::memcpy(dst, t.data(), n * sizeof(float));
   return static_cast<long>(n);
+}
+
+long spxb_filter_fixed_taps(uint32_t in_rate, uint32_t out_rate, int quality, int32_t *dst, size_t cap,
+                            int *shift) {
+  FilterSpec s;
+  if (int e = derive_filter_spec(in_rate, out_rate, quality, &s)) return -e;
+  const size_t n = static_cast<size_t>(s.den) * s.taps;
+  if (!dst || !shift || cap < n) return -RESAMPLER_ERR_INVALID_ARG;
+  FixedTaps ft;
+  if (!build_fixed_taps(s, build_reference_table(s), &ft)) return -RESAMPLER_ERR_BAD_STATE;
+  std::memcpy(dst, ft.h.data(), n * sizeof(int32_t));
+  *shift = ft.shift;
+  return static_cast<long>(n);
+}
+
+long spxb_tensor_plan(uint32_t in_rate, uint32_t out_rate, int quality, int32_t last_sample,
+                      uint32_t samp_frac_num, uint32_t n_out, uint32_t nt, int32_t *dst, size_t cap_tiles,
+                      uint32_t *ksteps) {
+  FilterSpec s;
+  if (int e = derive_filter_spec(in_rate, out_rate, quality, &s)) return -e;
+  if (!dst || !ksteps || nt < 16 || nt > 128 || nt % 16 != 0 || last_sample < 0 || samp_frac_num >= s.den)
+    return -RESAMPLER_ERR_INVALID_ARG;
+  std::vector<UmmaTile> tiles;
+  std::vector<UmmaTileKey> keys;
+  const uint32_t hist_frames = static_cast<uint32_t>(round_up(s.taps - 1, 16));
+  plan_umma_tiles(s.num, s.den, s.taps, hist_frames, last_sample, samp_frac_num, n_out, nt, &tiles, &keys);
+  if (tiles.size() > cap_tiles) return -RESAMPLER_ERR_INVALID_ARG;
+  for (size_t i = 0; i < tiles.size(); ++i) {
+    dst[4 * i + 0] = static_cast<int32_t>(tiles[i].m0);
+    dst[4 * i + 1] = tiles[i].kf0;
+    dst[4 * i + 2] = static_cast<int32_t>(keys[i].phase0);
+    dst[4 * i + 3] = static_cast<int32_t>(keys[i].delta);
+  }
+  *ksteps = umma_ksteps(s.taps, s.num, s.den, nt);
+  return static_cast<long>(tiles.size());
+}
+
+long spxb_tensor_tap_tile(uint32_t in_rate, uint32_t out_rate, int quality, uint32_t nt, uint32_t phase0,
+                          uint32_t delta, int8_t *dst, size_t cap) {
+  FilterSpec s;
+  if (int e = derive_filter_spec(in_rate, out_rate, quality, &s)) return -e;
+  if (!dst || nt < 16 || nt > 128 || nt % 16 != 0 || phase0 >= s.den || delta >= 16)
+    return -RESAMPLER_ERR_INVALID_ARG;
+  const uint32_t ks = umma_ksteps(s.taps, s.num, s.den, nt);
+  const size_t bytes = static_cast<size_t>(2) * ks * 3 * nt * 16;
+  if (cap < bytes) return -RESAMPLER_ERR_INVALID_ARG;
+  FixedTaps ft;
+  if (!build_fixed_taps(s, build_reference_table(s), &ft)) return -RESAMPLER_ERR_BAD_STATE;
+  UmmaTileKey key;
+  key.phase0 = phase0;
+  key.delta = delta;
+  fill_tap_tile_host(ft, s.num, s.den, s.taps, nt, ks, key, dst);
+  return static_cast<long>(bytes);
 }
 
 int spxb_plan_call(uint32_t in_rate, uint32_t out_rate, int32_t last_sample, uint32_t samp_frac_num,

@@ -24,6 +24,46 @@ __device__ __forceinline__ int fetch_sample(const CallArgs &a, uint32_t s, int f
   return a.in[static_cast<size_t>(s) * a.in_stride + static_cast<size_t>(f) * a.channels + c];
 }
 
+// 16 bytes of one stream's PCM starting at frame f (CH == 2: 4 frames, CH == 1: 8 frames):
+// history for f < 0, the call's input for f >= 0, zeros outside both.
+// in_align: largest of 16 / 8 / 4 / 2 bytes that every input row start is aligned to.
+template <int CH>
+__device__ __forceinline__ uint4 fetch_raw16(const CallArgs &a, const StreamCall &sc, uint32_t s, int f,
+                                             int in_align) {
+  constexpr int FPI = 8 / CH;  // frames per item
+  uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+  if (s >= a.n_streams) return raw;
+  if (f < 0) {
+    const int hf = f + static_cast<int>(a.hist_frames);
+    if (hf >= 0)
+      raw = __ldg(reinterpret_cast<const uint4 *>(a.hist_src + static_cast<size_t>(s) * a.hist_stride +
+                                                  static_cast<size_t>(hf) * CH));
+    return raw;
+  }
+  if (static_cast<uint32_t>(f) >= sc.n_in) return raw;
+  const int16_t *src = a.in + static_cast<size_t>(s) * a.in_stride + static_cast<size_t>(f) * CH;
+  const int avail = min(FPI, static_cast<int>(sc.n_in) - f);
+  if (avail == FPI) {
+    if (in_align == 16) return __ldg(reinterpret_cast<const uint4 *>(src));
+    if (in_align == 8) {
+      const uint2 lo = __ldg(reinterpret_cast<const uint2 *>(src));
+      const uint2 hi = __ldg(reinterpret_cast<const uint2 *>(src) + 1);
+      return make_uint4(lo.x, lo.y, hi.x, hi.y);
+    }
+    if (in_align == 4) {
+      const uint32_t *p = reinterpret_cast<const uint32_t *>(src);
+      return make_uint4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+    }
+  }
+  // tail of the input, or rows that are only 2-byte aligned: sample by sample
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  const int n = avail * CH;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < n) w[i >> 1] |= static_cast<uint32_t>(static_cast<uint16_t>(src[i])) << (16 * (i & 1));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // float -> int16 exactly as the reference's WORD2INT (deps/speex/arch.h:208-209):
 // saturate at -32767.5 / +32766.5, otherwise floor(0.5 + x) evaluated in f64.
 __device__ __forceinline__ int16_t word2int_exact(float v) {

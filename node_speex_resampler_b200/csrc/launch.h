@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <vector>
 
 #include "device_types.h"
 
@@ -27,6 +28,21 @@ cudaError_t launch_tiled(const CallArgs &a, const TiledConfig &cfg, cudaStream_t
                          uint32_t *launches);
 // one-time per-device attribute setup (opt-in shared memory sizes)
 cudaError_t tiled_prepare_device();
+
+// tensor kernel (kernels_umma.cu): exact integer banded GEMM on the int8 tensor cores.
+// A context holds the batch's fixed-point taps and tap-tile pool. umma_prepare plans the call
+// (tiles, tap tiles it still has to build -- queued on `stream`) and says whether the call is
+// covered (uniform stream positions, mono/stereo, ...); launch_umma then runs the FIR.
+struct UmmaContext;
+struct FilterSpec;
+UmmaContext *umma_create(const FilterSpec &spec, const std::vector<float> &ref_table, uint32_t channels,
+                         int sm_count);
+void umma_destroy(UmmaContext *c);
+int umma_shift(const UmmaContext *c);
+// last planned call: {outputs per tile, K steps per tile, tiles, series groups, smem stages, smem bytes}
+void umma_geometry(const UmmaContext *c, uint32_t out[6]);
+bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaError_t *err);
+cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, uint32_t *launches);
 
 // register-resident FFMA microbenchmark: returns achieved FP32 FLOP/s (2 flops per FMA)
 // on the current device; the measured denominator of the fp32 roofline (bench.py)

@@ -1,0 +1,154 @@
+// umma_ptx.cuh -- inline-PTX wrappers for the sm_100a tensor-core path (tcgen05 / TMEM /
+// mbarrier / bulk async copy). Only what kernels_umma.cu and umma_probe.cu need.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace spxb {
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make barrier inits visible to the async proxy (TMA / tcgen05.commit arrivals)
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
+                   smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// generic-proxy writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier.
+// dst, src 16-byte aligned; bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------- TMEM
+// whole warp; cols a power of two in [32, 512]; the base address lands in *smem_slot
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// 16 consecutive fp32 columns of this thread's TMEM lane (warp w reads lanes 32*(w%4)..+31)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------- UMMA
+// Shared-memory operand descriptor, K-major, no swizzle (canonical layout, in 16-byte units:
+// ((8,n),2):((1,SBO),LBO)): a core matrix is 8 rows x 16 bytes stored as 128 contiguous
+// bytes; `lbo` = byte distance between the two 16-byte K halves of one MMA, `sbo` = byte
+// distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fffu);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3fffu) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  return d;         // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
+}
+
+// Instruction descriptor for kind::f16: A, B = fp16 (K-major), D = fp32, M x N tile.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
+  return (1u << 4)            // D format: F32
+         | (0u << 7)          // A format: F16
+         | (0u << 10)         // B format: F16
+         | (0u << 15)         // A K-major
+         | (0u << 16)         // B K-major
+         | ((n >> 3) << 17)   // N / 8
+         | ((m >> 4) << 24);  // M / 16
+}
+// kind::i8: A, B = 8-bit integers (a_signed / b_signed select s8 vs u8), D = s32.
+__host__ __device__ constexpr uint32_t umma_idesc_i8(uint32_t m, uint32_t n, bool a_signed, bool b_signed) {
+  return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((n >> 3) << 17) |
+         ((m >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; one thread issues on behalf of the CTA
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all MMAs issued so far by this thread -> one arrival on `bar` when they complete
+// (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+}  // namespace ptx
+}  // namespace spxb

@@ -21,7 +21,7 @@ from typing import Callable, Iterable, List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import KERNEL_AUTO, KERNEL_STRICT, KERNEL_TILED  # noqa: F401
+from ._lib import KERNEL_AUTO, KERNEL_STRICT, KERNEL_TENSOR, KERNEL_TILED  # noqa: F401
 
 
 class _Resolved:
@@ -214,6 +214,14 @@ class StreamBatch:
 
     def last_kernel(self) -> int:
         return _lib.lib().spxb_batch_get_kernel(self._h)
+
+    def tensor_geometry(self):
+        """{nt, ksteps, tiles, groups, stages, smem_bytes} of the last tensor-kernel call, or None"""
+        import numpy as np
+        g = np.zeros(6, np.uint32)
+        if _lib.lib().spxb_batch_tensor_geometry(self._h, g.ctypes.data) != 0:
+            return None
+        return dict(zip(("nt", "ksteps", "tiles", "groups", "stages", "smem_bytes"), (int(v) for v in g)))
 
     def filter_info(self) -> _lib.FilterInfo:
         info = _lib.FilterInfo()

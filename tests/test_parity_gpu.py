@@ -1,8 +1,9 @@
 """Parity of the CUDA path against the oracle, through the C ABI / the reference-shaped
 wrapper. Needs a B200:  python -m pytest tests -m gpu
 
-Bars (BASELINE.json north_star): strict kernel bit-exact; tiled kernel within +-1 LSB per
-int16 sample and >= 90 dB SNR against the reference output. The golden vectors were
+Bars (BASELINE.json north_star): strict kernel bit-exact; tiled (fp32 FMA) and tensor
+(tcgen05 int8) kernels within +-1 LSB per int16 sample and >= 90 dB SNR against the reference
+output. The golden vectors were
 produced by the reference's own C (oracle/gen_golden.py); the oracle restatement is the
 live checker for everything else.
 """
@@ -13,7 +14,7 @@ import numpy as np
 import pytest
 
 from cases import GOLDEN_CHUNKS, GOLDEN_STREAMS, MATRIX, case_id
-from node_speex_resampler_b200 import (KERNEL_AUTO, KERNEL_STRICT, KERNEL_TILED, SpeexResampler,
+from node_speex_resampler_b200 import (KERNEL_AUTO, KERNEL_STRICT, KERNEL_TENSOR, KERNEL_TILED, SpeexResampler,
                                        SpeexResamplerTransform, StreamBatch, _lib, lib, synth_pcm)
 from oracle import oracle as O
 
@@ -63,18 +64,19 @@ def test_golden_strict_is_bit_exact(c):
         r.destroy()
 
 
+@pytest.mark.parametrize("kernel", [KERNEL_TILED, KERNEL_TENSOR], ids=["tiled", "tensor"])
 @pytest.mark.parametrize("c", [c for c in MATRIX if c[0] <= 2], ids=case_id)
-def test_golden_tiled_within_one_lsb(c):
+def test_golden_fast_kernels_within_one_lsb(c, kernel):
     ch = c[0]
     key = case_id(c)
-    r = new_resampler(c, KERNEL_TILED)
+    r = new_resampler(c, kernel)
     pos, outs = 0, []
     for k, n in enumerate(GOLDEN_CHUNKS):
         try:
             raw = r.processChunk(VEC[key + "/in"][0][pos * ch:(pos + n) * ch])
         except RuntimeError as e:
             assert "Bad resampler state" in str(e) and "does not qualify" in _lib.last_error()
-            pytest.skip("tiled kernel does not cover this filter length yet (strict serves it)")
+            pytest.skip("this kernel does not cover this filter (strict serves it)")
         y = np.frombuffer(raw, dtype=np.int16)
         assert y.size // ch == VEC[key + "/lens"][0][k]
         outs.append(y)
@@ -96,7 +98,8 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("kernel", [KERNEL_STRICT, KERNEL_AUTO], ids=["strict", "auto"])
+@pytest.mark.parametrize("kernel", [KERNEL_STRICT, KERNEL_TILED, KERNEL_TENSOR, KERNEL_AUTO],
+                         ids=["strict", "tiled", "tensor", "auto"])
 @pytest.mark.parametrize("shape", SHAPES, ids=[s[0] for s in SHAPES])
 def test_batch_state_carry(shape, kernel):
     name, S, ch, i, o, q, n, calls = shape
@@ -104,17 +107,19 @@ def test_batch_state_carry(shape, kernel):
     b.set_kernel(kernel)
     refs = [O.OracleResampler(ch, i, o, q) for _ in range(S)]
     cap = int(np.ceil(n * o / i)) + 2
-    used_tiled = False
+    kernels_used = set()
     for k in range(calls):
         pcm = synth_pcm(S, ch, n, i, seed=0xC0DE, start_frame=k * n)
         out, used, made = b.process(pcm, n, cap)
-        used_tiled |= b.last_kernel() == KERNEL_TILED
+        kernels_used.add(b.last_kernel())
         for s in range(S):
             y, u, m = refs[s].process(pcm[s], cap)
             assert (u, m) == (int(used[s]), int(made[s])), (name, k, s)
             check_close(y, out[s, : m * ch], exact=kernel == KERNEL_STRICT, what=(name, k, s))
-    if kernel == KERNEL_AUTO and name in ("C3", "up2_direct", "sweep_q9"):
-        assert used_tiled, "auto should pick the tiled kernel for this shape"
+    if kernel == KERNEL_AUTO:
+        assert kernels_used == {KERNEL_TENSOR}, "auto should pick the tensor kernel for uniform mono/stereo batches"
+    else:
+        assert kernels_used == {kernel}
     # device-resident state equals the oracle's
     for s in (0, S - 1):
         ls, fr, mg, hist = b.get_state(s)
@@ -145,7 +150,7 @@ def test_full_size_c3_properties():
         for s in pick:
             y, _, m = refs[s].process(pcm[s], 960)
             check_close(y, out[s, : m * ch], exact=False, what=("C3full", k, s))
-    assert b.last_kernel() == KERNEL_TILED
+    assert b.last_kernel() == KERNEL_TENSOR
     b.close()
     twin.close()
 
@@ -304,7 +309,7 @@ def test_device_pointer_entry_matches_host_entry():
                                                    C.byref(used), C.byref(made)) == 0
         ts.synchronize()  # the kernel ran on `ts`, not on the batch's own stream
         assert (used.value, made.value) == (n, cap)
-        assert b.last_kernel() == a.last_kernel() == KERNEL_TILED  # odd row stride still tiled
+        assert b.last_kernel() == a.last_kernel() == KERNEL_TENSOR  # odd row stride still on the tensor cores
         assert np.array_equal(d_out.cpu().numpy(), want)
     a.close()
     b.close()
