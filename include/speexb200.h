@@ -115,6 +115,9 @@ SPXB_API int spxb_batch_get_kernel(const spxb_batch *b);       /* family used by
  * tile, tiles per series group, series groups (128 series each), shared-memory stages,
  * dynamic shared memory bytes}; RESAMPLER_ERR_BAD_STATE when no tensor call was planned yet */
 SPXB_API int spxb_batch_tensor_geometry(const spxb_batch *b, uint32_t *geom6);
+/* debug: with SPXB_UMMA_TRACE=1 in the environment the tensor kernel records a clock64
+ * timeline (32 words per CTA) of its last launch; copies it out, returns CTAs copied */
+SPXB_API long spxb_batch_tensor_trace(spxb_batch *b, uint64_t *dst, size_t cap_words);
 
 /* One processChunk-equivalent for every stream, HOST buffers (pageable or pinned).
  * Stream s reads in + s*in_stride_frames*channels (in_frames[s] frames) and writes

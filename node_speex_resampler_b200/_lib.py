@@ -19,7 +19,7 @@ DECLARED_SYMBOLS = (
     "speex_resampler_get_input_latency", "speex_resampler_get_output_latency",
     "speex_resampler_skip_zeros", "speex_resampler_reset_mem",
     "spxb_device_count", "spxb_last_error", "spxb_batch_create", "spxb_batch_destroy",
-    "spxb_batch_set_kernel", "spxb_batch_get_kernel", "spxb_batch_tensor_geometry", "spxb_batch_process", "spxb_batch_submit",
+    "spxb_batch_set_kernel", "spxb_batch_get_kernel", "spxb_batch_tensor_geometry", "spxb_batch_tensor_trace", "spxb_batch_process", "spxb_batch_submit",
     "spxb_batch_wait", "spxb_batch_pipeline_depth", "spxb_batch_process_device",
     "spxb_batch_process_device_uniform", "spxb_batch_process_device_ring", "spxb_batch_set_stream", "spxb_batch_use_own_stream", "spxb_batch_synchronize",
     "spxb_batch_get_state", "spxb_batch_set_state", "spxb_batch_reset", "spxb_batch_skip_zeros",
@@ -97,6 +97,8 @@ def _bind(L):
     L.spxb_filter_phase_taps.restype = C.c_long
     L.spxb_filter_phase_taps.argtypes = [u32, u32, C.c_int, vp, sz]
     L.spxb_batch_tensor_geometry.argtypes = [vp, vp]
+    L.spxb_batch_tensor_trace.restype = C.c_long
+    L.spxb_batch_tensor_trace.argtypes = [vp, vp, sz]
     L.spxb_filter_fixed_taps.restype = C.c_long
     L.spxb_filter_fixed_taps.argtypes = [u32, u32, C.c_int, vp, sz, pint]
     L.spxb_tensor_plan.restype = C.c_long

@@ -627,6 +627,13 @@ int spxb_batch_tensor_geometry(const spxb_batch *b, uint32_t *geom6) {
   return geom6[0] ? 0 : RESAMPLER_ERR_BAD_STATE;
 }
 
+long spxb_batch_tensor_trace(spxb_batch *b, uint64_t *dst, size_t cap_words) {
+  if (!b || !dst) return -RESAMPLER_ERR_INVALID_ARG;
+  if (spxb_batch_synchronize(b)) return -RESAMPLER_ERR_BAD_STATE;
+  DeviceGuard g(b->device);
+  return umma_read_trace(b->umma, reinterpret_cast<unsigned long long *>(dst), cap_words);
+}
+
 int spxb_batch_pipeline_depth(const spxb_batch *) { return kPipelineDepth - 1; }
 
 int spxb_batch_submit(spxb_batch *b, const int16_t *in, size_t in_stride_frames, uint32_t *in_frames,

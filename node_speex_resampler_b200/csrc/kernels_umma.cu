@@ -41,11 +41,13 @@ using namespace ptx;
 
 constexpr int kConvWarps = 8;
 constexpr int kConvThreads = kConvWarps * 32;
-constexpr int kTmaWarp = 8, kMmaWarp = 9;
-constexpr int kThreads = 320;
+constexpr int kTmaWarp = 8, kMmaWarp = 9;  // warp 10 slides the history
+constexpr int kThreads = 352;
 constexpr int kStageChunks = 4;                                  // 64 frames, 2 K steps
-constexpr uint32_t kChunkBytesX = kUmmaRows * 16;                // 2048
-constexpr uint32_t kXPlaneBytes = kStageChunks * kChunkBytesX;   // 8192
+// K chunk of one byte plane: 128 rows x 16 B, plus 32 B so that the four chunks of a stage start
+// 8 banks apart (the converters' stores hit 32 distinct banks; LBO is a free multiple of 16 B)
+constexpr uint32_t kChunkBytesX = kUmmaRows * 16 + 32;           // 2080
+constexpr uint32_t kXPlaneBytes = kStageChunks * kChunkBytesX;   // 8320
 constexpr uint32_t kXStageBytes = 2 * kXPlaneBytes;              // hi + lo planes
 constexpr int kMaxStages = 6;
 constexpr uint32_t kMaxSmem = 227u * 1024u - 2048u;              // dynamic part; barriers are static
@@ -61,16 +63,65 @@ struct UmmaArgs {
   uint32_t stages;
   uint32_t tmem_cols;
   int shift;
+  unsigned long long *trace;  // optional per-CTA timeline (kTraceSlots words per CTA), else nullptr
 };
 
-// one MMA per <= 256 rows of B: D[:, col0 + (r - row0)] (+)= A * B[r]^T
-__device__ __forceinline__ void issue_rows(uint32_t tmem, uint64_t adesc, bool a_signed, uint32_t b_addr,
-                                           uint32_t b_lbo, uint32_t row0, uint32_t nrows, uint32_t col0,
-                                           uint32_t acc) {
-  for (uint32_t r = 0; r < nrows; r += 256) {
-    const uint32_t n = min(256u, nrows - r);
-    const uint64_t bdesc = umma_smem_desc(b_addr + (row0 + r) * 16, b_lbo, 128);
-    umma_i8(tmem + col0 + r, adesc, bdesc, umma_idesc_i8(128, n, a_signed, true), acc);
+constexpr int kTraceSlots = 32;
+__device__ __forceinline__ void trace_mark(const UmmaArgs &u, int slot) {
+  if (u.trace) u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + slot] = static_cast<unsigned long long>(clock64());
+}
+
+// 16 bytes of one stream's input starting at frame f >= 0, sample by sample with zero fill past
+// the end of the call's input (kept out of line: only the last chunk of a row takes this path)
+__device__ __noinline__ uint4 fetch_item_slow(const int16_t *row, int f, uint32_t n_in, int ch) {
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  const long long avail = (static_cast<long long>(n_in) - f) * ch;  // samples left from frame f
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < avail)
+      w[i >> 1] |= static_cast<uint32_t>(static_cast<uint16_t>(row[static_cast<size_t>(f) * ch + i])) << (16 * (i & 1));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// exactly one lane of a converged warp (elect.sync): the lane that issues tcgen05 / bulk copies
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// the 16 accumulator columns of one output group -> rounded, saturated int16 values
+// y = (p0*2^24 + p1*2^16 + p2*2^8 + p3) * 2^-shift, result floor(y + 1/2) (arch.h:208-209)
+__device__ __forceinline__ void combine16(const uint32_t (&p0)[16], const uint32_t (&p1)[16],
+                                          const uint32_t (&p2)[16], const uint32_t (&p3)[16], int shift,
+                                          int (&r16)[16]) {
+  if (shift >= 16 && shift <= 30) {
+    // nested floor division by 256 is exact: floor((a*256 + b) / 256) = a + floor(b / 256). The
+    // running value after two steps is floor((v + half) / 2^16); it fits int32 (|y| < 2^18 for any
+    // windowed-sinc filter, so |v| * 2^-16 < 2^(shift+2)), hence wrapping arithmetic is exact.
+    const int half = 1 << (shift - 1), s2 = shift - 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      int w = static_cast<int>(p3[i]) + half;
+      w = (w >> 8) + static_cast<int>(p2[i]);
+      w = (w >> 8) + static_cast<int>(p1[i]) + static_cast<int>(p0[i] << 8);
+      r16[i] = max(-32768, min(32767, w >> s2));
+    }
+  } else {
+    const long long half = 1ll << (shift - 1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      long long v = static_cast<long long>(static_cast<int>(p3[i]));
+      v += static_cast<long long>(static_cast<int>(p2[i])) << 8;
+      v += static_cast<long long>(static_cast<int>(p1[i])) << 16;
+      v += static_cast<long long>(static_cast<int>(p0[i])) << 24;
+      const long long r = (v + half) >> shift;
+      r16[i] = static_cast<int>(max(-32768ll, min(32767ll, r)));
+    }
   }
 }
 
@@ -83,9 +134,19 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   constexpr int kStreams = kUmmaRows / CH;  // streams per series group
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t g = blockIdx.x % u.n_groups, t = blockIdx.x / u.n_groups;
-  const UmmaTile tile = u.tiles[t];
   const StreamCall sc = a.uniform;
   const uint32_t nt = u.nt;
+  // tile geometry in closed form (umma_plan.cpp: plan_umma_tiles), no dependent global load
+  const uint32_t m0 = t * nt;
+  int kf0;
+  {
+    const unsigned long long tt = static_cast<unsigned long long>(sc.frac0) +
+                                  static_cast<unsigned long long>(m0) * a.filt.num;
+    const long long q0 = static_cast<long long>(sc.ls0) - (static_cast<long long>(a.filt.taps) - 1) +
+                         static_cast<long long>(tt / a.filt.den);
+    const long long from_hist = q0 + a.hist_frames;
+    kf0 = static_cast<int>(from_hist - (from_hist % kUmmaChunkFrames) - a.hist_frames);
+  }
   const uint32_t tap_chunk = 3 * nt * 16;
   const uint32_t tap_stage = kStageChunks * tap_chunk;
   const uint32_t stage_bytes = kXStageBytes + tap_stage;
@@ -97,7 +158,20 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
                             (static_cast<uint32_t>(a.in_stride) * 2u);
   const int in_align = (row_bits & 15u) == 0 ? 16 : (row_bits & 7u) == 0 ? 8 : (row_bits & 3u) == 0 ? 4 : 2;
 
+  // Programmatic dependent launch: let the next call's grid start its prologue (barrier init,
+  // TMEM allocation) while this grid drains; it blocks in griddepcontrol.wait below until this
+  // grid has completed, before it touches anything this grid reads or writes.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) {
+    trace_mark(u, 0);
+    if (u.trace) {
+      unsigned long long gt;
+      uint32_t smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + 14] = gt;
+      u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + 16] = smid;
+    }
     for (uint32_t s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], kConvThreads + 1);
       mbar_init(&empty_bar[s], 1);
@@ -109,89 +183,132 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     tmem_alloc(&tmem_slot, u.tmem_cols);
     tmem_relinquish();
   }
+
+  // ---- converter state: PCM items in flight, two stages deep ----
+  // A stage is 64 frames of 128 series = kStreams stream segments of 64*CH*2 bytes. Lanes of a
+  // warp walk ALONG a segment in 16-byte items (PPS items per stream, SPI streams per warp
+  // instruction), so one LDG.128 covers four full 128-byte lines; each thread owns kItems items
+  // per stage, item i of warp w belonging to stream (4w + i) * SPI + lane / PPS.
+  constexpr int FPI = 8 / CH;          // frames per 16-byte item
+  constexpr int PPS = 64 / FPI;        // items per stream per stage (16 stereo, 8 mono)
+  constexpr int SPI = 32 / PPS;        // streams per warp instruction (2 stereo, 4 mono)
+  constexpr int kItems = 4;
+  const int conv_p = lane % PPS;       // item position inside the stage segment
+  const int16_t *hist_row0[kItems];    // frame 0 of the stream in history coordinates (f < 0 indexes back)
+  const int16_t *in_row[kItems];
+  bool conv_live[kItems];
+  uint32_t conv_off[kItems];           // byte offset of the item's hi/left word(s) inside an X stage
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) {
+    const uint32_t sl = static_cast<uint32_t>((4 * (warp & 7) + i) * SPI + lane / PPS);
+    const uint32_t sg = g * kStreams + sl;
+    conv_live[i] = sg < a.n_streams;
+    const size_t r = conv_live[i] ? sg : 0;
+    hist_row0[i] = a.hist_src + r * a.hist_stride + static_cast<size_t>(a.hist_frames) * CH;
+    in_row[i] = a.in + r * a.in_stride;
+    // chunk j = 16 frames; inside the chunk row sl holds 16 bytes = 16 frames of one plane
+    const uint32_t j = static_cast<uint32_t>(conv_p * FPI) / kUmmaChunkFrames;
+    const uint32_t byte_in_row = static_cast<uint32_t>(conv_p * FPI) % kUmmaChunkFrames;
+    conv_off[i] = j * kChunkBytesX + sl * 16 + byte_in_row;
+  }
+  uint4 raw0[kItems], raw1[kItems];
+  auto fetch = [&](uint32_t it, uint4 (&raw)[kItems]) {
+    const int f = kf0 + static_cast<int>(it * (kStageChunks * kUmmaChunkFrames)) + conv_p * FPI;
+    const bool in_hist = f < 0;
+    const bool full = in_hist || f + FPI <= static_cast<int>(sc.n_in);
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+      const int16_t *p = (in_hist ? hist_row0[i] : in_row[i]) + static_cast<ptrdiff_t>(f) * CH;
+      if (!conv_live[i] || (!in_hist && f >= static_cast<int>(sc.n_in))) {
+        raw[i] = make_uint4(0u, 0u, 0u, 0u);
+      } else if (full && (in_hist || in_align == 16)) {
+        raw[i] = __ldg(reinterpret_cast<const uint4 *>(p));
+      } else if (full && in_align == 8) {
+        const uint2 lo = __ldg(reinterpret_cast<const uint2 *>(p));
+        const uint2 hi = __ldg(reinterpret_cast<const uint2 *>(p) + 1);
+        raw[i] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+      } else if (full && in_align == 4) {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(p);
+        raw[i] = make_uint4(__ldg(w), __ldg(w + 1), __ldg(w + 2), __ldg(w + 3));
+      } else {
+        // the item holding the end of the input, or rows only 2-byte aligned: sample by sample
+        raw[i] = fetch_item_slow(in_row[i], f, sc.n_in, CH);
+      }
+    }
+  };
+  // Everything above touched only kernel parameters and this CTA's own resources. The previous
+  // call's grid (which reads the history buffer this call overwrites, and writes the one this call
+  // reads) must have completed before any global access below.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // the first two stages' loads go out before the setup barrier
+  if (warp < kConvWarps) {
+    fetch(0, raw0);
+    if (n_iters > 1) fetch(1, raw1);
+  }
+
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
+  if (tid == 0) trace_mark(u, 1);
 
   if (warp < kConvWarps) {
     // ================= converters: PCM -> byte planes in UMMA layout =================
-    constexpr int kTasks = 2 / CH;    // (stream, chunk) tasks per thread per stage
-    constexpr int kItems = 2 * CH;    // 16-byte items per task (16 frames)
-    constexpr int FPI = 8 / CH;       // frames per item
-    uint4 raw[kTasks][kItems];
-    auto fetch = [&](uint32_t it) {
+    auto convert_store = [&](uint8_t *xs, const uint4 (&raw)[kItems]) {
 #pragma unroll
-      for (int q = 0; q < kTasks; ++q) {
-        const int id = tid + kConvThreads * q;
-        const int sl = id % kStreams, j = id / kStreams;
-        const int f0 = tile.kf0 + static_cast<int>((it * kStageChunks + j) * kUmmaChunkFrames);
-#pragma unroll
-        for (int i = 0; i < kItems; ++i)
-          raw[q][i] = fetch_raw16<CH>(a, sc, g * kStreams + sl, f0 + i * FPI, in_align);
-      }
-    };
-    auto convert_store = [&](uint8_t *xs) {
-#pragma unroll
-      for (int q = 0; q < kTasks; ++q) {
-        const int id = tid + kConvThreads * q;
-        const int sl = id % kStreams, j = id / kStreams;
-        uint8_t *base = xs + j * kChunkBytesX;
+      for (int i = 0; i < kItems; ++i) {
+        uint8_t *base = xs + conv_off[i];
+        const uint4 w = raw[i];
         if (CH == 1) {
-          // word = (x[2i+1] << 16) | x[2i]: bytes lo0 hi0 lo1 hi1
-          uint4 lo, hi;
-          lo.x = __byte_perm(raw[q][0].x, raw[q][0].y, 0x6420);
-          lo.y = __byte_perm(raw[q][0].z, raw[q][0].w, 0x6420);
-          lo.z = __byte_perm(raw[q][1].x, raw[q][1].y, 0x6420);
-          lo.w = __byte_perm(raw[q][1].z, raw[q][1].w, 0x6420);
-          hi.x = __byte_perm(raw[q][0].x, raw[q][0].y, 0x7531);
-          hi.y = __byte_perm(raw[q][0].z, raw[q][0].w, 0x7531);
-          hi.z = __byte_perm(raw[q][1].x, raw[q][1].y, 0x7531);
-          hi.w = __byte_perm(raw[q][1].z, raw[q][1].w, 0x7531);
-          *reinterpret_cast<uint4 *>(base + sl * 16) = hi;
-          *reinterpret_cast<uint4 *>(base + kXPlaneBytes + sl * 16) = lo;
+          // 8 frames; word = (x[2k+1] << 16) | x[2k]: bytes lo0 hi0 lo1 hi1 -> 8 bytes per plane
+          const uint2 hi = make_uint2(__byte_perm(w.x, w.y, 0x7531), __byte_perm(w.z, w.w, 0x7531));
+          const uint2 lo = make_uint2(__byte_perm(w.x, w.y, 0x6420), __byte_perm(w.z, w.w, 0x6420));
+          *reinterpret_cast<uint2 *>(base) = hi;
+          *reinterpret_cast<uint2 *>(base + kXPlaneBytes) = lo;
         } else {
-          // word f = (R_f << 16) | L_f. Four frames (one item) -> one word of each plane/channel.
-          uint32_t llo[4], lhi[4], rlo[4], rhi[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 w = raw[q][i];
-            const uint32_t ul = __byte_perm(w.x, w.y, 0x5140), vl = __byte_perm(w.z, w.w, 0x5140);
-            const uint32_t ur = __byte_perm(w.x, w.y, 0x7362), vr = __byte_perm(w.z, w.w, 0x7362);
-            llo[i] = __byte_perm(ul, vl, 0x5410);
-            lhi[i] = __byte_perm(ul, vl, 0x7632);
-            rlo[i] = __byte_perm(ur, vr, 0x5410);
-            rhi[i] = __byte_perm(ur, vr, 0x7632);
-          }
+          // 4 frames; word f = (R_f << 16) | L_f -> one word per plane and channel.
           // rows: left channel of stream sl -> row sl, right channel -> row 64 + sl
-          *reinterpret_cast<uint4 *>(base + sl * 16) = make_uint4(lhi[0], lhi[1], lhi[2], lhi[3]);
-          *reinterpret_cast<uint4 *>(base + (64 + sl) * 16) = make_uint4(rhi[0], rhi[1], rhi[2], rhi[3]);
-          *reinterpret_cast<uint4 *>(base + kXPlaneBytes + sl * 16) = make_uint4(llo[0], llo[1], llo[2], llo[3]);
-          *reinterpret_cast<uint4 *>(base + kXPlaneBytes + (64 + sl) * 16) =
-              make_uint4(rlo[0], rlo[1], rlo[2], rlo[3]);
+          const uint32_t ul = __byte_perm(w.x, w.y, 0x5140), vl = __byte_perm(w.z, w.w, 0x5140);
+          const uint32_t ur = __byte_perm(w.x, w.y, 0x7362), vr = __byte_perm(w.z, w.w, 0x7362);
+          *reinterpret_cast<uint32_t *>(base) = __byte_perm(ul, vl, 0x7632);
+          *reinterpret_cast<uint32_t *>(base + 64 * 16) = __byte_perm(ur, vr, 0x7632);
+          *reinterpret_cast<uint32_t *>(base + kXPlaneBytes) = __byte_perm(ul, vl, 0x5410);
+          *reinterpret_cast<uint32_t *>(base + kXPlaneBytes + 64 * 16) = __byte_perm(ur, vr, 0x5410);
         }
       }
     };
-
-    fetch(0);
-    for (uint32_t it = 0; it < n_iters; ++it) {
+    auto stage_step = [&](uint32_t it, uint4 (&raw)[kItems]) {
       const uint32_t slot = it % S, par = (it / S) & 1u;
+      const bool tr = tid == 0 && it == 6;
+      if (tr) trace_mark(u, 17);
       mbar_wait(&empty_bar[slot], par ^ 1u);
-      convert_store(smem + slot * stage_bytes);
-      if (it + 1 < n_iters) fetch(it + 1);
+      if (tr) trace_mark(u, 18);
+      convert_store(smem + slot * stage_bytes, raw);
+      if (tr) trace_mark(u, 19);
+      if (it + 2 < n_iters) fetch(it + 2, raw);
+      if (tr) trace_mark(u, 10);
       fence_proxy_async_smem();
       mbar_arrive(&full_bar[slot]);
+      if (tr) trace_mark(u, 31);
+    };
+
+    if (tid == 0) trace_mark(u, 2);
+    for (uint32_t it = 0; it < n_iters; it += 2) {
+      stage_step(it, raw0);
+      if (tid == 0 && it == 0) trace_mark(u, 3);
+      if (it + 1 < n_iters) stage_step(it + 1, raw1);
     }
+    if (tid == 0) trace_mark(u, 4);
 
     // ================= epilogue =================
     mbar_wait(&acc_bar, 0);
     tc_fence_after_sync();
-    const uint32_t n_valid = min(nt, sc.n_out - tile.m0);
+    if (tid == 0) trace_mark(u, 5);
+    const uint32_t n_valid = min(nt, sc.n_out - m0);
     const uint32_t row = (warp & 3) * 32 + lane;  // TMEM lane
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const uint32_t pitch_w = (CH == 2 ? nt : nt / 2) + 1;  // words per staged row (odd)
     uint16_t *stage16 = reinterpret_cast<uint16_t *>(smem);
-    const long long half_ulp = 1ll << (u.shift - 1);
     for (uint32_t cg = warp >> 2; cg * 16 < n_valid; cg += 2) {
       uint32_t p0[16], p1[16], p2[16], p3[16];
       tmem_ld16(lane_addr + cg * 16, p0);
@@ -200,16 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
       tmem_ld16(lane_addr + 3 * nt + cg * 16, p3);
       tmem_ld_wait();
       int r16[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        long long v = static_cast<long long>(static_cast<int>(p3[i]));
-        v += static_cast<long long>(static_cast<int>(p2[i])) << 8;
-        v += static_cast<long long>(static_cast<int>(p1[i])) << 16;
-        v += static_cast<long long>(static_cast<int>(p0[i])) << 24;
-        // floor(y + 1/2) with y = v * 2^-shift, then saturate (arch.h:208-209)
-        const long long r = (v + half_ulp) >> u.shift;
-        r16[i] = static_cast<int>(max(-32768ll, min(32767ll, r)));
-      }
+      combine16(p0, p1, p2, p3, u.shift, r16);
       if (CH == 2) {
         const uint32_t sl = row & 63, c = row >> 6;
         uint16_t *dst = stage16 + (sl * pitch_w) * 2 + (cg * 16) * 2 + c;
@@ -222,25 +330,40 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
           dst[i] = (static_cast<uint32_t>(r16[2 * i]) & 0xffffu) | (static_cast<uint32_t>(r16[2 * i + 1]) << 16);
       }
     }
+    if (tid == 0) trace_mark(u, 6);
     asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
-    // staged rows -> global, coalesced along the stream's interleaved output
+    // staged rows -> global, coalesced along the stream's interleaved output; a row is at most
+    // 128 words, i.e. four words per lane, all four loads in flight before the stores
     const uint32_t *stage32 = reinterpret_cast<const uint32_t *>(smem);
+    const uint32_t n_elems = n_valid * CH;
+    const uint32_t n_words = n_elems / 2;
+#pragma unroll 2
     for (uint32_t r = warp; r < static_cast<uint32_t>(kStreams); r += kConvWarps) {
       const uint32_t s = g * kStreams + r;
       if (s >= a.n_streams) break;
-      int16_t *dst = a.out + static_cast<size_t>(s) * a.out_stride + static_cast<size_t>(tile.m0) * CH;
-      const uint32_t n_elems = n_valid * CH;
+      int16_t *dst = a.out + static_cast<size_t>(s) * a.out_stride + static_cast<size_t>(m0) * CH;
       if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
-        for (uint32_t i = lane; i < n_elems / 2; i += 32) reinterpret_cast<uint32_t *>(dst)[i] = stage32[r * pitch_w + i];
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t i = lane + 32 * j;
+          if (i < n_words) w[j] = stage32[r * pitch_w + i];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t i = lane + 32 * j;
+          if (i < n_words) reinterpret_cast<uint32_t *>(dst)[i] = w[j];
+        }
         if ((n_elems & 1u) && lane == 0) dst[n_elems - 1] = static_cast<int16_t>(stage16[r * pitch_w * 2 + n_elems - 1]);
       } else {
         for (uint32_t i = lane; i < n_elems; i += 32) dst[i] = static_cast<int16_t>(stage16[r * pitch_w * 2 + i]);
       }
     }
+    if (tid == 0) trace_mark(u, 7);
   } else if (warp == kTmaWarp) {
     // ================= tap tiles: one bulk copy per stage =================
     if (lane == 0) {
-      const int8_t *src = u.pool + static_cast<size_t>(tile.slot) * u.tile_bytes;
+      const int8_t *src = u.pool + static_cast<size_t>(u.tiles[t].slot) * u.tile_bytes;
       for (uint32_t it = 0; it < n_iters; ++it) {
         const uint32_t slot = it % S, par = (it / S) & 1u;
         mbar_wait(&empty_bar[slot], par ^ 1u);
@@ -249,71 +372,132 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
         mbar_arrive_expect_tx(&full_bar[slot], bytes);
         bulk_g2s(smem + slot * stage_bytes + kXStageBytes, src + static_cast<size_t>(it) * tap_stage, bytes,
                  &full_bar[slot]);
+        if (it == 0) trace_mark(u, 12);
       }
+      trace_mark(u, 13);
     }
     __syncwarp();
-  } else {
+  } else if (warp == kMmaWarp) {
     // ================= MMA issue =================
-    if (lane == 0) {
-      for (uint32_t it = 0; it < n_iters; ++it) {
-        const uint32_t slot = it % S, par = (it / S) & 1u;
-        mbar_wait(&full_bar[slot], par);
-        tc_fence_after_sync();
-        const uint32_t xs = smem_u32(smem + slot * stage_bytes);
-        const uint32_t ts = xs + kXStageBytes;
-        const uint32_t ks_here = min(static_cast<uint32_t>(kStageChunks), n_chunks - it * kStageChunks) / 2;
+    // The whole warp walks the stages (uniform control flow, descriptors in uniform registers);
+    // one elected lane issues. N = 3nt splits into pieces of at most 256 columns.
+    const uint32_t n3 = 3 * nt;
+    const uint32_t np0 = min(n3, 256u), np1 = n3 - np0;            // [0, 3nt)
+    const uint32_t nq0 = min(2 * nt, 256u), nq1 = 2 * nt - nq0;    // [0, 2nt) (first K step, lo plane)
+    const uint32_t id_hi0 = umma_idesc_i8(128, np0, true, true), id_hi1 = umma_idesc_i8(128, np1, true, true);
+    const uint32_t id_lo0 = umma_idesc_i8(128, np0, false, true), id_lo1 = umma_idesc_i8(128, np1, false, true);
+    const uint32_t id_lq0 = umma_idesc_i8(128, nq0, false, true), id_lq1 = umma_idesc_i8(128, nq1, false, true);
+    const uint32_t id_lf = umma_idesc_i8(128, nt, false, true);
+    const uint64_t a_base = umma_smem_desc(smem_u32(smem), kChunkBytesX, 128);
+    const uint64_t b_base = umma_smem_desc(smem_u32(smem) + kXStageBytes, tap_chunk, 128);
+    const uint32_t stage_step16 = stage_bytes >> 4;
+    const uint32_t a_ks16 = (2 * kChunkBytesX) >> 4, a_lo16 = kXPlaneBytes >> 4, b_ks16 = (2 * tap_chunk) >> 4;
+    for (uint32_t it = 0; it < n_iters; ++it) {
+      const uint32_t slot = it % S, par = (it / S) & 1u;
+      mbar_wait(&full_bar[slot], par);
+      tc_fence_after_sync();
+      if (lane == 0 && it < 12) trace_mark(u, 20 + it);
+      const uint32_t ks_here = min(static_cast<uint32_t>(kStageChunks), n_chunks - it * kStageChunks) / 2;
+      const uint64_t a_st = a_base + slot * stage_step16, b_st = b_base + slot * stage_step16;
+      if (elect_one()) {
         for (uint32_t ks = 0; ks < ks_here; ++ks) {
-          const uint64_t a_hi = umma_smem_desc(xs + ks * 2 * kChunkBytesX, kChunkBytesX, 128);
-          const uint64_t a_lo = umma_smem_desc(xs + kXPlaneBytes + ks * 2 * kChunkBytesX, kChunkBytesX, 128);
-          const uint32_t b = ts + ks * 2 * tap_chunk;
-          const bool first = (it == 0 && ks == 0);
-          issue_rows(tmem, a_hi, true, b, tap_chunk, 0, 3 * nt, 0, first ? 0u : 1u);
-          if (first) {
+          const uint64_t a_hi = a_st + ks * a_ks16, a_lo = a_hi + a_lo16, b = b_st + ks * b_ks16;
+          if (it == 0 && ks == 0) {
+            umma_i8(tmem, a_hi, b, id_hi0, 0u);
+            if (np1) umma_i8(tmem + 256, a_hi, b + 256, id_hi1, 0u);
             // columns [nt,3nt) already hold hi*B: accumulate; columns [3nt,4nt) are fresh
-            issue_rows(tmem, a_lo, false, b, tap_chunk, 0, 2 * nt, nt, 1u);
-            issue_rows(tmem, a_lo, false, b, tap_chunk, 2 * nt, nt, 3 * nt, 0u);
+            umma_i8(tmem + nt, a_lo, b, id_lq0, 1u);
+            if (nq1) umma_i8(tmem + nt + 256, a_lo, b + 256, id_lq1, 1u);
+            umma_i8(tmem + 3 * nt, a_lo, b + 2 * nt, id_lf, 0u);
           } else {
-            issue_rows(tmem, a_lo, false, b, tap_chunk, 0, 3 * nt, nt, 1u);
+            umma_i8(tmem, a_hi, b, id_hi0, 1u);
+            if (np1) umma_i8(tmem + 256, a_hi, b + 256, id_hi1, 1u);
+            umma_i8(tmem + nt, a_lo, b, id_lo0, 1u);
+            if (np1) umma_i8(tmem + nt + 256, a_lo, b + 256, id_lo1, 1u);
           }
         }
         umma_commit(&empty_bar[slot]);
+        if (it + 1 == n_iters) umma_commit(&acc_bar);
       }
-      umma_commit(&acc_bar);
+      __syncwarp();
     }
-    __syncwarp();
-  }
-
-  // ---- this CTA's slice of the history slide (resample.c:898-899) and the new position ----
-  // stream sl of the group is handled by the tile CTA with t == sl % n_tiles; new history
-  // element e = element consumed*CH + e of (old history || input)
-  {
+    if (lane == 0) trace_mark(u, 11);
+  } else {
+    // ================= history slide (resample.c:898-899) and the new position =================
+    // Runs beside the FIR: it reads the old history and this call's input, writes the other half
+    // of the ping-pong. Stream sl of the group is handled by the tile CTA with t == sl % n_tiles;
+    // new history element e = element consumed*CH + e of (old history || input).
     const uint32_t hist_elems = a.hist_frames * CH;
     const size_t shift = static_cast<size_t>(sc.consumed) * CH;
     const int vshift = (shift % 8 == 0) ? 8 : (shift % 4 == 0) ? 4 : (shift % 2 == 0) ? 2 : 1;
     const int vw = min(vshift, in_align / 2);
-    for (uint32_t sl = t; sl < static_cast<uint32_t>(kStreams); sl += u.n_tiles) {
-      const uint32_t s = g * kStreams + sl;
-      if (s >= a.n_streams) break;
-      for (uint32_t e = tid * vw; e < hist_elems; e += kThreads * vw) {
-        const size_t src = shift + e;
-        const int16_t *p = (src < hist_elems) ? a.hist_src + static_cast<size_t>(s) * a.hist_stride + src
-                                              : a.in + static_cast<size_t>(s) * a.in_stride + (src - hist_elems);
-        int16_t *d = a.hist_dst + static_cast<size_t>(s) * a.hist_stride + e;
-        if (vw == 8) *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(p);
-        else if (vw == 4) *reinterpret_cast<uint2 *>(d) = *reinterpret_cast<const uint2 *>(p);
-        else if (vw == 2) *reinterpret_cast<uint32_t *>(d) = *reinterpret_cast<const uint32_t *>(p);
-        else *d = *p;
+    // streams of this CTA: sl = t + k * n_tiles while the stream exists
+    const uint32_t first = g * kStreams + t;
+    const uint32_t in_group = t < static_cast<uint32_t>(kStreams) ? (kStreams - t + u.n_tiles - 1) / u.n_tiles : 0u;
+    const uint32_t in_batch = first < a.n_streams ? (a.n_streams - first + u.n_tiles - 1) / u.n_tiles : 0u;
+    const uint32_t n_mine = min(in_group, in_batch);
+    if (vw == 8) {
+      // 16-byte vectors; four streams x four vectors per lane in flight before the stores
+      for (uint32_t k0 = 0; k0 < n_mine; k0 += 4) {
+        for (uint32_t e0 = lane * 8; e0 < hist_elems; e0 += 32 * 8 * 4) {
+          uint4 val[4][4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const size_t s = first + static_cast<size_t>(k0 + kk) * u.n_tiles;
+            const int16_t *hsrc = a.hist_src + s * a.hist_stride;
+            const int16_t *isrc = a.in + s * a.in_stride;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t e = e0 + j * 256;
+              const size_t src = shift + e;
+              if (k0 + kk < n_mine && e < hist_elems)
+                val[kk][j] = __ldg(reinterpret_cast<const uint4 *>(src < hist_elems ? hsrc + src : isrc + (src - hist_elems)));
+            }
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const size_t s = first + static_cast<size_t>(k0 + kk) * u.n_tiles;
+            int16_t *hdst = a.hist_dst + s * a.hist_stride;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t e = e0 + j * 256;
+              if (k0 + kk < n_mine && e < hist_elems) *reinterpret_cast<uint4 *>(hdst + e) = val[kk][j];
+            }
+          }
+        }
       }
-      if (tid == 0) {
-        a.last_sample[s] = sc.ls1;
-        a.samp_frac[s] = sc.frac1;
+    } else {
+      for (uint32_t k = 0; k < n_mine; ++k) {
+        const size_t s = first + static_cast<size_t>(k) * u.n_tiles;
+        const int16_t *hsrc = a.hist_src + s * a.hist_stride;
+        const int16_t *isrc = a.in + s * a.in_stride;
+        int16_t *hdst = a.hist_dst + s * a.hist_stride;
+        for (uint32_t e = lane * vw; e < hist_elems; e += 32 * vw) {
+          const size_t src = shift + e;
+          const int16_t *p = src < hist_elems ? hsrc + src : isrc + (src - hist_elems);
+          if (vw == 4) *reinterpret_cast<uint2 *>(hdst + e) = *reinterpret_cast<const uint2 *>(p);
+          else if (vw == 2) *reinterpret_cast<uint32_t *>(hdst + e) = *reinterpret_cast<const uint32_t *>(p);
+          else hdst[e] = *p;
+        }
       }
     }
+    for (uint32_t k = lane; k < n_mine; k += 32) {
+      const size_t s = first + static_cast<size_t>(k) * u.n_tiles;
+      a.last_sample[s] = sc.ls1;
+      a.samp_frac[s] = sc.frac1;
+    }
+    if (lane == 0) trace_mark(u, 8);
   }
 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem, u.tmem_cols);
+  if (tid == 0 && u.trace) {
+    trace_mark(u, 9);
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + 15] = gt;
+  }
 }
 
 // One thread per (chunk, row): 16 digits -> one 16-byte store. jobs[i] = {slot, phase0, delta}.
@@ -374,6 +558,8 @@ struct UmmaContext {
   uint32_t n_tiles = 0;
   uint32_t *d_jobs = nullptr;
   size_t jobs_cap = 0;
+  unsigned long long *d_trace = nullptr;  // SPXB_UMMA_TRACE=1: timeline of the last launch
+  size_t trace_ctas = 0;
   // memo of the planned geometry
   bool memo = false;
   int32_t m_ls0 = 0;
@@ -392,9 +578,11 @@ uint32_t forced_nt() {
   return v;
 }
 
-// Tile width: fewest estimated cycles for the whole grid. A tile costs its MMA floor
-// (3*nt cycles per 32-frame K step: two MMAs of N = 3nt at N/2 cycles each) plus a fixed
-// prologue/epilogue; the grid runs in waves of one CTA per SM.
+// Tile width: fewest estimated cycles for the whole grid, from the measured timeline of a tile
+// (profiles/umma_trace_r1.log): ~5500 cycles of prologue + epilogue, then per 64-frame stage the
+// slower of the MMA floor (two K steps x two planes x 3nt/2 cycles) and the stage's operand bytes
+// (PCM planes + tap tile) at the ~30 B/clk an SM gets from L2 when every SM streams; the grid
+// runs in waves of one CTA per SM.
 uint32_t pick_nt(const UmmaContext &c, uint32_t n_groups, uint32_t n_out) {
   if (forced_nt() >= 16 && forced_nt() <= 128 && forced_nt() % 16 == 0) return forced_nt();
   uint32_t best = 16;
@@ -404,7 +592,8 @@ uint32_t pick_nt(const UmmaContext &c, uint32_t n_groups, uint32_t n_out) {
     const double ctas = static_cast<double>(tiles) * n_groups;
     const double waves = std::ceil(ctas / c.sm_count);
     const uint32_t ks = umma_ksteps(c.spec.taps, c.spec.num, c.spec.den, nt);
-    const double tile_cycles = 3000.0 + 3.0 * nt * ks + 10.0 * nt;
+    const double stage_cycles = std::max(6.0 * nt, (2.0 * kXPlaneBytes + 4.0 * 48.0 * nt) / 30.0);
+    const double tile_cycles = 5500.0 + stage_cycles * ((ks + 1) / 2) + 10.0 * nt;
     const double cost = waves * tile_cycles;
     if (cost < best_cost) {
       best_cost = cost;
@@ -461,6 +650,7 @@ void umma_destroy(UmmaContext *c) {
   if (c->d_pool) cudaFree(c->d_pool);
   if (c->d_tiles) cudaFree(c->d_tiles);
   if (c->d_jobs) cudaFree(c->d_jobs);
+  if (c->d_trace) cudaFree(c->d_trace);
   delete c;
 }
 
@@ -609,15 +799,49 @@ cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, 
   u.stages = c->stages;
   u.tmem_cols = c->tmem_cols;
   u.shift = c->ft.shift;
+  u.trace = nullptr;
   const uint64_t grid = static_cast<uint64_t>(u.n_groups) * u.n_tiles;
   if (grid == 0 || grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-  if (a.channels == 2)
-    umma_fir_kernel<2><<<static_cast<unsigned>(grid), kThreads, c->smem_bytes, stream>>>(a, u);
-  else
-    umma_fir_kernel<1><<<static_cast<unsigned>(grid), kThreads, c->smem_bytes, stream>>>(a, u);
-  const cudaError_t e = cudaGetLastError();
+  static const bool want_trace = getenv("SPXB_UMMA_TRACE") != nullptr;
+  if (want_trace) {
+    if (c->trace_ctas < grid) {
+      if (c->d_trace) cudaFree(c->d_trace);
+      c->d_trace = nullptr;
+      if (cudaMalloc(reinterpret_cast<void **>(&c->d_trace), grid * kTraceSlots * sizeof(unsigned long long)) ==
+          cudaSuccess)
+        c->trace_ctas = grid;
+    }
+    u.trace = c->d_trace;
+  }
+  static const bool use_pdl = [] {
+    const char *e = getenv("SPXB_UMMA_PDL");
+    return !e || atoi(e) != 0;
+  }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = c->smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  cudaError_t e = a.channels == 2 ? cudaLaunchKernelEx(&cfg, umma_fir_kernel<2>, a, u)
+                                  : cudaLaunchKernelEx(&cfg, umma_fir_kernel<1>, a, u);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e == cudaSuccess && launches) *launches += 1;
   return e;
+}
+
+// debug timeline of the last traced launch: kTraceSlots words per CTA; returns CTAs copied
+long umma_read_trace(const UmmaContext *c, unsigned long long *dst, size_t cap_words) {
+  if (!c || !c->d_trace || !c->memo) return 0;
+  const size_t ctas = std::min<size_t>(static_cast<size_t>(c->n_tiles) * c->m_groups, cap_words / kTraceSlots);
+  if (cudaMemcpy(dst, c->d_trace, ctas * kTraceSlots * sizeof(unsigned long long), cudaMemcpyDeviceToHost) !=
+      cudaSuccess)
+    return -1;
+  return static_cast<long>(ctas);
 }
 
 }  // namespace spxb

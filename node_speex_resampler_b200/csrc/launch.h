@@ -43,6 +43,8 @@ int umma_shift(const UmmaContext *c);
 void umma_geometry(const UmmaContext *c, uint32_t out[6]);
 bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaError_t *err);
 cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, uint32_t *launches);
+// SPXB_UMMA_TRACE=1: clock64 timeline of the last launch, 32 words per CTA (debug only)
+long umma_read_trace(const UmmaContext *c, unsigned long long *dst, size_t cap_words);
 
 // register-resident FFMA microbenchmark: returns achieved FP32 FLOP/s (2 flops per FMA)
 // on the current device; the measured denominator of the fp32 roofline (bench.py)
