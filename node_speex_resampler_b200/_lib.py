@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libspeexb200.so")
+LIB_PATH = os.environ.get("SPXB_LIB_PATH") or os.path.join(PKG_DIR, "libspeexb200.so")  # override: A/B builds
 
 # symbols include/speexb200.h declares; tests assert the .so exports every one of them
 DECLARED_SYMBOLS = (

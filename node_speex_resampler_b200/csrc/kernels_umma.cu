@@ -55,7 +55,9 @@ constexpr uint32_t kMaxSmem = 227u * 1024u - 2048u;              // dynamic part
 struct UmmaArgs {
   const UmmaTile *tiles;
   uint32_t n_tiles;
-  uint32_t n_groups;
+  uint32_t n_groups;          // series groups in the grid (padded to a multiple of `cluster`)
+  uint32_t cluster;           // CTAs per cluster (1, 2 or 4): same tile, consecutive series groups;
+                              // each loads 1/cluster of every tap stage and multicasts it
   const int8_t *pool;
   uint32_t tile_bytes;
   uint32_t nt;
@@ -64,8 +66,17 @@ struct UmmaArgs {
   uint32_t tmem_cols;
   int shift;
   unsigned long long *trace;  // optional per-CTA timeline (kTraceSlots words per CTA), else nullptr
+  uint32_t debug;             // SPXB_UMMA_DEBUG bits (timing experiments only, results are garbage):
+                              // 1 = no PCM loads, 2 = no MMAs, 4 = no PCM conversion/stores
 };
 
+// Timing-experiment knobs cost ~10 % on the long-filter shapes even when off (they perturb the
+// converters' load scheduling), so they exist only in builds made with -DSPXB_DEBUG_KNOBS.
+#ifdef SPXB_DEBUG_KNOBS
+#define SPXB_DEBUG_BITS(u) ((u).debug)
+#else
+#define SPXB_DEBUG_BITS(u) 0u
+#endif
 constexpr int kTraceSlots = 32;
 __device__ __forceinline__ void trace_mark(const UmmaArgs &u, int slot) {
   if (u.trace) u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + slot] = static_cast<unsigned long long>(clock64());
@@ -133,6 +144,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
 
   constexpr int kStreams = kUmmaRows / CH;  // streams per series group
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // series group fastest: CTAs running at the same time share a tap tile (measured: tile-fastest
+  // order is slower, the tap stream is bounded by bytes into the SM, not by hot L2 lines)
   const uint32_t g = blockIdx.x % u.n_groups, t = blockIdx.x / u.n_groups;
   const StreamCall sc = a.uniform;
   const uint32_t nt = u.nt;
@@ -153,6 +166,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   const uint32_t n_chunks = 2 * u.ksteps;
   const uint32_t n_iters = (n_chunks + kStageChunks - 1) / kStageChunks;
   const uint32_t S = u.stages;
+  const uint32_t cta_rank = u.cluster > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cluster_mask = static_cast<uint16_t>((1u << u.cluster) - 1u);
   // alignment every input row start shares (16-byte items start at multiples of 16 B in a row)
   const uint32_t row_bits = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(a.in)) |
                             (static_cast<uint32_t>(a.in_stride) * 2u);
@@ -172,12 +187,39 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
       u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + 14] = gt;
       u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + 16] = smid;
     }
+  }
+  // The tap-tile producer owns the barriers: it initialises them and has the first tap stages
+  // in flight before the grid dependency resolves. (The tile table and the tap pool are only ever
+  // rewritten by stream-ordered copies, and a call that re-planned launches without the
+  // programmatic edge, so they are safe to read here.)
+  uint32_t taps_issued = 0;
+  if (warp == kTmaWarp && lane == 0) {
     for (uint32_t s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], kConvThreads + 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], u.cluster);  // every CTA of the cluster is done with the slot
     }
     mbar_init(&acc_bar, 1);
     fence_mbar_init();
+  }
+  // peers multicast into this CTA's stages and arrive on its barriers: all initialised first
+  if (u.cluster > 1) cluster_sync_all();
+  auto load_taps = [&](uint32_t it, uint32_t slot, const int8_t *src) {
+    const uint32_t chunks_here = min(static_cast<uint32_t>(kStageChunks), n_chunks - it * kStageChunks);
+    const uint32_t bytes = chunks_here * tap_chunk;
+    uint8_t *dst = smem + slot * stage_bytes + kXStageBytes;
+    const int8_t *from = src + static_cast<size_t>(it) * tap_stage;
+    mbar_arrive_expect_tx(&full_bar[slot], bytes);
+    if (u.cluster == 1) {
+      bulk_g2s(dst, from, bytes, &full_bar[slot]);
+    } else {
+      const uint32_t part = bytes / u.cluster, off = part * cta_rank;  // multiples of 16 bytes
+      bulk_g2s_multicast(dst + off, from + off, part, &full_bar[slot], cluster_mask);
+    }
+  };
+  if (warp == kTmaWarp && lane == 0) {
+    const int8_t *src = u.pool + static_cast<size_t>(u.tiles[t].slot) * u.tile_bytes;
+    for (; taps_issued < min(S, n_iters); ++taps_issued) load_taps(taps_issued, taps_issued, src);
+    trace_mark(u, 12);
   }
   if (warp == kMmaWarp) {
     tmem_alloc(&tmem_slot, u.tmem_cols);
@@ -219,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
       const int16_t *p = (in_hist ? hist_row0[i] : in_row[i]) + static_cast<ptrdiff_t>(f) * CH;
-      if (!conv_live[i] || (!in_hist && f >= static_cast<int>(sc.n_in))) {
+      if (!conv_live[i] || (!in_hist && f >= static_cast<int>(sc.n_in)) || (SPXB_DEBUG_BITS(u) & 1u)) {
         raw[i] = make_uint4(0u, 0u, 0u, 0u);
       } else if (full && (in_hist || in_align == 16)) {
         raw[i] = __ldg(reinterpret_cast<const uint4 *>(p));
@@ -283,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
       if (tr) trace_mark(u, 17);
       mbar_wait(&empty_bar[slot], par ^ 1u);
       if (tr) trace_mark(u, 18);
-      convert_store(smem + slot * stage_bytes, raw);
+      if (!(SPXB_DEBUG_BITS(u) & 4u)) convert_store(smem + slot * stage_bytes, raw);
       if (tr) trace_mark(u, 19);
       if (it + 2 < n_iters) fetch(it + 2, raw);
       if (tr) trace_mark(u, 10);
@@ -299,6 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
       if (it + 1 < n_iters) stage_step(it + 1, raw1);
     }
     if (tid == 0) trace_mark(u, 4);
+    if (tid == kConvThreads - 32) trace_mark(u, 30);
 
     // ================= epilogue =================
     mbar_wait(&acc_bar, 0);
@@ -364,15 +407,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     // ================= tap tiles: one bulk copy per stage =================
     if (lane == 0) {
       const int8_t *src = u.pool + static_cast<size_t>(u.tiles[t].slot) * u.tile_bytes;
-      for (uint32_t it = 0; it < n_iters; ++it) {
+      for (uint32_t it = taps_issued; it < n_iters; ++it) {
         const uint32_t slot = it % S, par = (it / S) & 1u;
         mbar_wait(&empty_bar[slot], par ^ 1u);
-        const uint32_t chunks_here = min(static_cast<uint32_t>(kStageChunks), n_chunks - it * kStageChunks);
-        const uint32_t bytes = chunks_here * tap_chunk;
-        mbar_arrive_expect_tx(&full_bar[slot], bytes);
-        bulk_g2s(smem + slot * stage_bytes + kXStageBytes, src + static_cast<size_t>(it) * tap_stage, bytes,
-                 &full_bar[slot]);
-        if (it == 0) trace_mark(u, 12);
+        load_taps(it, slot, src);
       }
       trace_mark(u, 13);
     }
@@ -392,6 +430,16 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     const uint64_t b_base = umma_smem_desc(smem_u32(smem) + kXStageBytes, tap_chunk, 128);
     const uint32_t stage_step16 = stage_bytes >> 4;
     const uint32_t a_ks16 = (2 * kChunkBytesX) >> 4, a_lo16 = kXPlaneBytes >> 4, b_ks16 = (2 * tap_chunk) >> 4;
+    // One K step = hi plane x B into [0,3nt), lo plane x the same B into [nt,4nt).
+    auto kstep = [&](uint64_t a_hi, uint64_t b) {
+      const uint64_t a_lo = a_hi + a_lo16;
+      umma_i8(tmem, a_hi, b, id_hi0, 1u);
+      if (np1) umma_i8(tmem + 256, a_hi, b + 256, id_hi1, 1u);
+      umma_i8(tmem + nt, a_lo, b, id_lo0, 1u);
+      if (np1) umma_i8(tmem + nt + 256, a_lo, b + 256, id_lo1, 1u);
+    };
+#ifdef SPXB_OLD_MMA_LOOP
+    (void)kstep;
     for (uint32_t it = 0; it < n_iters; ++it) {
       const uint32_t slot = it % S, par = (it / S) & 1u;
       mbar_wait(&full_bar[slot], par);
@@ -405,7 +453,6 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
           if (it == 0 && ks == 0) {
             umma_i8(tmem, a_hi, b, id_hi0, 0u);
             if (np1) umma_i8(tmem + 256, a_hi, b + 256, id_hi1, 0u);
-            // columns [nt,3nt) already hold hi*B: accumulate; columns [3nt,4nt) are fresh
             umma_i8(tmem + nt, a_lo, b, id_lq0, 1u);
             if (nq1) umma_i8(tmem + nt + 256, a_lo, b + 256, id_lq1, 1u);
             umma_i8(tmem + 3 * nt, a_lo, b + 2 * nt, id_lf, 0u);
@@ -421,6 +468,44 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
       }
       __syncwarp();
     }
+#else
+    uint32_t slot = 0, par = 0;
+    uint64_t a_st = a_base, b_st = b_base;
+    const bool odd_tail = (n_chunks % kStageChunks) != 0;  // last stage holds one K step
+    for (uint32_t it = 0; it < n_iters; ++it) {
+      mbar_wait(&full_bar[slot], par);
+      tc_fence_after_sync();
+      if (u.trace && lane == 0 && it < 12) trace_mark(u, 20 + it);
+      const bool last = it + 1 == n_iters;
+      if (elect_one()) {
+        if (!(SPXB_DEBUG_BITS(u) & 2u)) {
+          if (it == 0) {
+            umma_i8(tmem, a_st, b_st, id_hi0, 0u);
+            if (np1) umma_i8(tmem + 256, a_st, b_st + 256, id_hi1, 0u);
+            // columns [nt,3nt) already hold hi*B: accumulate; columns [3nt,4nt) are fresh
+            umma_i8(tmem + nt, a_st + a_lo16, b_st, id_lq0, 1u);
+            if (nq1) umma_i8(tmem + nt + 256, a_st + a_lo16, b_st + 256, id_lq1, 1u);
+            umma_i8(tmem + 3 * nt, a_st + a_lo16, b_st + 2 * nt, id_lf, 0u);
+          } else {
+            kstep(a_st, b_st);
+          }
+          if (!(last && odd_tail)) kstep(a_st + a_ks16, b_st + b_ks16);
+        }
+        if (u.cluster == 1) umma_commit(&empty_bar[slot]);
+        else umma_commit_multicast(&empty_bar[slot], cluster_mask);
+        if (last) umma_commit(&acc_bar);
+      }
+      __syncwarp();
+      a_st += stage_step16;
+      b_st += stage_step16;
+      if (++slot == S) {
+        slot = 0;
+        par ^= 1u;
+        a_st = a_base;
+        b_st = b_base;
+      }
+    }
+#endif
     if (lane == 0) trace_mark(u, 11);
   } else {
     // ================= history slide (resample.c:898-899) and the new position =================
@@ -492,6 +577,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   tc_fence_before_sync();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem, u.tmem_cols);
+  // no CTA may leave while a peer can still multicast into it or arrive on its barriers
+  if (u.cluster > 1) cluster_sync_all();
   if (tid == 0 && u.trace) {
     trace_mark(u, 9);
     unsigned long long gt;
@@ -550,6 +637,7 @@ struct UmmaContext {
   int32_t *d_h = nullptr;
   // geometry (changes only when the tile width changes)
   uint32_t nt = 0, ksteps = 0, tile_bytes = 0, stages = 0, tmem_cols = 0, smem_bytes = 0;
+  uint32_t cluster = 1, grid_groups = 0;  // CTAs per cluster; series groups padded to a multiple of it
   int8_t *d_pool = nullptr;
   size_t pool_cap = 0;  // tiles
   std::unordered_map<uint64_t, uint32_t> slot_of;
@@ -562,6 +650,7 @@ struct UmmaContext {
   size_t trace_ctas = 0;
   // memo of the planned geometry
   bool memo = false;
+  bool fresh_plan = false;  // the last umma_prepare re-planned (tile table / pool just rewritten)
   int32_t m_ls0 = 0;
   uint32_t m_frac0 = 0, m_n_out = 0, m_hist_frames = 0, m_groups = 0;
 };
@@ -677,8 +766,11 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
   const uint32_t n_groups = (a.n_streams * a.channels + kUmmaRows - 1) / kUmmaRows;
   const StreamCall &sc = a.uniform;
   if (c->memo && c->m_ls0 == sc.ls0 && c->m_frac0 == sc.frac0 && c->m_n_out == sc.n_out &&
-      c->m_hist_frames == a.hist_frames && c->m_groups == n_groups)
+      c->m_hist_frames == a.hist_frames && c->m_groups == n_groups) {
+    c->fresh_plan = false;
     return true;  // steady state: same tiles as the previous call
+  }
+  c->fresh_plan = true;
 
   const uint32_t nt = pick_nt(*c, n_groups, sc.n_out);
   if (nt != c->nt) {
@@ -784,6 +876,21 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
   c->m_n_out = sc.n_out;
   c->m_hist_frames = a.hist_frames;
   c->m_groups = n_groups;
+  // Cluster: CTAs of one tile share the tap stream; multicast cuts each SM's requests for it.
+  // Only worth it with several groups; padding CTAs (no live streams) cost a whole tile each.
+  static const int forced_cluster = [] {
+    const char *e = getenv("SPXB_UMMA_CLUSTER");
+    return e ? atoi(e) : 0;
+  }();
+  uint32_t cl = 1;
+  if (forced_cluster == 1 || forced_cluster == 2 || forced_cluster == 4) {
+    cl = static_cast<uint32_t>(forced_cluster);
+  } else {
+    if (n_groups % 4 == 0) cl = 4;
+    else if (n_groups % 2 == 0) cl = 2;
+  }
+  c->cluster = cl;
+  c->grid_groups = (n_groups + cl - 1) / cl * cl;
   return true;
 }
 
@@ -791,7 +898,8 @@ cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, 
   UmmaArgs u;
   u.tiles = c->d_tiles;
   u.n_tiles = c->n_tiles;
-  u.n_groups = c->m_groups;
+  u.n_groups = c->grid_groups;
+  u.cluster = c->cluster;
   u.pool = c->d_pool;
   u.tile_bytes = c->tile_bytes;
   u.nt = c->nt;
@@ -800,6 +908,11 @@ cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, 
   u.tmem_cols = c->tmem_cols;
   u.shift = c->ft.shift;
   u.trace = nullptr;
+  static const uint32_t debug_bits = [] {
+    const char *e = getenv("SPXB_UMMA_DEBUG");
+    return e ? static_cast<uint32_t>(atoi(e)) : 0u;
+  }();
+  u.debug = debug_bits;
   const uint64_t grid = static_cast<uint64_t>(u.n_groups) * u.n_tiles;
   if (grid == 0 || grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   static const bool want_trace = getenv("SPXB_UMMA_TRACE") != nullptr;
@@ -822,11 +935,22 @@ cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, 
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = c->smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  unsigned n_attr = 0;
+  if (c->cluster > 1) {
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = c->cluster;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
+  if (use_pdl && !c->fresh_plan) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
+  cfg.numAttrs = n_attr;
   cudaError_t e = a.channels == 2 ? cudaLaunchKernelEx(&cfg, umma_fir_kernel<2>, a, u)
                                   : cudaLaunchKernelEx(&cfg, umma_fir_kernel<1>, a, u);
   if (e == cudaSuccess) e = cudaGetLastError();
@@ -837,7 +961,7 @@ cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, 
 // debug timeline of the last traced launch: kTraceSlots words per CTA; returns CTAs copied
 long umma_read_trace(const UmmaContext *c, unsigned long long *dst, size_t cap_words) {
   if (!c || !c->d_trace || !c->memo) return 0;
-  const size_t ctas = std::min<size_t>(static_cast<size_t>(c->n_tiles) * c->m_groups, cap_words / kTraceSlots);
+  const size_t ctas = std::min<size_t>(static_cast<size_t>(c->n_tiles) * c->grid_groups, cap_words / kTraceSlots);
   if (cudaMemcpy(dst, c->d_trace, ctas * kTraceSlots * sizeof(unsigned long long), cudaMemcpyDeviceToHost) !=
       cudaSuccess)
     return -1;

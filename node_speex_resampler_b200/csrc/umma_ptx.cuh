@@ -61,6 +61,29 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
                : "memory");
 }
 
+// same copy, delivered to the same shared-memory offset (and signalling the same barrier offset)
+// of every CTA of the cluster whose rank bit is set in `cta_mask`
+__device__ __forceinline__ void bulk_g2s_multicast(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- thread-block clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs of the cluster
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- TMEM
 // whole warp; cols a power of two in [32, 512]; the base address lands in *smem_slot
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t cols) {
@@ -148,6 +171,15 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+
+// same, arriving on the barrier at this offset in every CTA of the cluster selected by `cta_mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t *bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
 }
 
 }  // namespace ptx

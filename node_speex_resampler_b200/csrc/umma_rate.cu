@@ -102,6 +102,99 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(const RateArgs p) {
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// The FIR kernel's own issue pattern: per K step four MMAs (hi plane x [0,3nt), lo plane x the
+// same B into columns [nt,4nt)), N = 3nt split in two pieces, operands walking through a ring of
+// stages exactly as kernels_umma.cu lays them out. No loads, no converters: the tensor pipe alone.
+struct FirArgs {
+  uint32_t nt, a_lbo, b_lbo, piece0;  // piece0: columns of the first piece (rest in the second)
+  uint32_t stages, ksteps;
+  unsigned long long *cycles;
+};
+
+__global__ void __launch_bounds__(128, 1) fir_rate_kernel(const FirArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (uint32_t i = tid; i < 200 * 1024 / 16; i += blockDim.x)
+    reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0x01020304u * (i & 3), 0x01010101u, i * 2654435761u, 0x7f80ff01u);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 1) {
+    const uint32_t nt = p.nt, n3 = 3 * nt, np0 = p.piece0, np1 = n3 - np0;
+    const uint32_t a_chunk = p.a_lbo, x_plane = 4 * a_chunk, x_stage = 2 * x_plane;
+    const uint32_t tap_chunk = p.b_lbo, stage_bytes = x_stage + 4 * tap_chunk;
+    const uint32_t id_hi0 = umma_idesc_i8(128, np0, true, true), id_hi1 = umma_idesc_i8(128, np1 ? np1 : 16, true, true);
+    const uint32_t id_lo0 = umma_idesc_i8(128, np0, false, true), id_lo1 = umma_idesc_i8(128, np1 ? np1 : 16, false, true);
+    const uint64_t a_base = make_desc(smem_u32(smem), a_chunk, 128, 0);
+    const uint64_t b_base = make_desc(smem_u32(smem) + x_stage, tap_chunk, 128, 0);
+    const uint32_t st16 = stage_bytes >> 4, a_ks16 = (2 * a_chunk) >> 4, a_lo16 = x_plane >> 4, b_ks16 = (2 * tap_chunk) >> 4;
+    long long t0 = 0;
+    for (uint32_t k = 0; k < p.ksteps + 4; ++k) {
+      if (k == 4) {
+        // warm-up done
+        if ((tid & 31) == 0) {
+          umma_commit(&bar);
+          mbar_wait(&bar, 0);
+        }
+        __syncwarp();
+        t0 = clock64();
+      }
+      const uint32_t slot = (k / 2) % p.stages, ks = k & 1;
+      const uint64_t a_hi = a_base + slot * st16 + ks * a_ks16, a_lo = a_hi + a_lo16, b = b_base + slot * st16 + ks * b_ks16;
+      uint32_t pred;
+      asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(pred));
+      if (pred) {
+        umma_i8(tmem, a_hi, b, id_hi0, 1u);
+        if (np1) umma_i8(tmem + np0, a_hi, b + np0, id_hi1, 1u);
+        umma_i8(tmem + nt, a_lo, b, id_lo0, 1u);
+        if (np1) umma_i8(tmem + nt + np0, a_lo, b + np0, id_lo1, 1u);
+      }
+      __syncwarp();
+    }
+    if ((tid & 31) == 0) {
+      umma_commit(&bar);
+      mbar_wait(&bar, 1);
+      p.cycles[blockIdx.x] = static_cast<unsigned long long>(clock64() - t0);
+    }
+    __syncwarp();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static void run_fir(const char *name, FirArgs p, int grid) {
+  unsigned long long *d;
+  cudaMalloc(&d, grid * sizeof(unsigned long long));
+  p.cycles = d;
+  cudaFuncSetAttribute(fir_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  fir_rate_kernel<<<grid, 128, 204 * 1024>>>(p);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("%-60s CUDA error %s\n", name, cudaGetErrorString(e));
+    exit(2);
+  }
+  std::vector<unsigned long long> h(grid);
+  cudaMemcpy(h.data(), d, grid * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  double mx = 0;
+  for (auto v : h) mx = v > mx ? v : mx;
+  printf("%-60s grid %3d: %7.1f cyc per K step (MMA floor 2 x 3nt/2 = %u)\n", name, grid, mx / p.ksteps, 3 * p.nt);
+  fflush(stdout);
+}
+
 static double run(const char *name, RateArgs p, int grid) {
   unsigned long long *d;
   cudaMalloc(&d, grid * sizeof(unsigned long long));
@@ -128,8 +221,24 @@ static double run(const char *name, RateArgs p, int grid) {
   return per;
 }
 
-int main() {
+int main(int argc, char **argv) {
   const int R = 512;
+  if (argc > 1) {
+    // FIR issue pattern (kernels_umma.cu): tile widths, chunk strides, piece splits
+    for (int grid : {1, 148}) {
+      run_fir("fir nt=112 a_lbo=2080 pieces 256+80", FirArgs{112, 2080, 3 * 112 * 16, 256, 4, 512, nullptr}, grid);
+      run_fir("fir nt=112 a_lbo=2048 pieces 256+80", FirArgs{112, 2048, 3 * 112 * 16, 256, 4, 512, nullptr}, grid);
+      run_fir("fir nt=112 a_lbo=2080 pieces 176+160", FirArgs{112, 2080, 3 * 112 * 16, 176, 4, 512, nullptr}, grid);
+      run_fir("fir nt=112 a_lbo=2080 b_lbo+32 pieces 176+160", FirArgs{112, 2080, 3 * 112 * 16 + 32, 176, 4, 512, nullptr}, grid);
+      run_fir("fir nt=80  a_lbo=2080 one piece 240", FirArgs{80, 2080, 3 * 80 * 16, 240, 6, 512, nullptr}, grid);
+      run_fir("fir nt=80  a_lbo=2048 one piece 240", FirArgs{80, 2048, 3 * 80 * 16, 240, 6, 512, nullptr}, grid);
+      run_fir("fir nt=64  a_lbo=2080 one piece 192", FirArgs{64, 2080, 3 * 64 * 16, 192, 6, 512, nullptr}, grid);
+      run_fir("fir nt=128 a_lbo=2080 pieces 256+128", FirArgs{128, 2080, 3 * 128 * 16, 256, 3, 512, nullptr}, grid);
+      run_fir("fir nt=128 a_lbo=2080 pieces 192+192", FirArgs{128, 2080, 3 * 128 * 16, 192, 3, 512, nullptr}, grid);
+      run_fir("fir nt=128 a_lbo=2048 pieces 192+192", FirArgs{128, 2048, 3 * 128 * 16, 192, 3, 512, nullptr}, grid);
+    }
+    return 0;
+  }
   for (int grid : {1, 148}) {
     for (int i8 : {1, 0}) {
       for (int n : {64, 128, 256}) {

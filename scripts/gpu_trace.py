@@ -17,12 +17,13 @@ SHAPES = {"C3": (1024, 2, 44100, 48000, 7, 882), "C4": (4096, 1, 48000, 16000, 1
 NAMES = {0: "start", 1: "setup done", 2: "fetch0 issued", 3: "stage0 stored", 4: "convert loop end",
          5: "acc ready (conv)", 6: "epilogue math done", 7: "outputs stored", 8: "history done", 9: "exit",
          17: "conv it6: enter", 18: "conv it6: slot empty", 19: "conv it6: stored", 10: "conv it6: fetch issued",
-         31: "conv it6: arrived", 11: "mma: all issued", 12: "tma: first bulk", 13: "tma: last bulk"}
+         31: "conv it6: arrived", 30: "convert loop end (warp 7)", 11: "mma: all issued", 12: "tma: first bulk", 13: "tma: last bulk"}
 for it in range(12):
     NAMES[20 + it] = f"mma: stage {it} full"
 L = pkg.lib()
 for wl in (sys.argv[1:] or ["C3", "C5"]):
     S, ch, i, o, q, n = SHAPES[wl]
+    S = int(os.environ.get("STREAMS", S))
     cap = -(-n * o // i)
     b = pkg.StreamBatch(S, ch, i, o, q)
     b.set_kernel(pkg.KERNEL_TENSOR)
@@ -31,7 +32,7 @@ for wl in (sys.argv[1:] or ["C3", "C5"]):
     for k in range(4):
         b.process(pcm, n, cap)
     geom = b.tensor_geometry()
-    ctas = geom["tiles"] * geom["groups"]
+    ctas = geom["tiles"] * (geom["groups"] + 3)
     buf = np.zeros(ctas * 32, np.uint64)
     got = L.spxb_batch_tensor_trace(b._h, buf.ctypes.data, buf.size)
     t = buf.reshape(-1, 32)[:got].astype(np.int64)
