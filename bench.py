@@ -371,6 +371,34 @@ def ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_sec = float(t.item())
     e2e_value = out_samples_step * world * Ke / e2e_sec
+    # the ceiling of that number: this step's H2D and D2H bytes copied concurrently from/to pinned
+    # memory with nothing else running (PCIe Gen5 x16 on this box), no kernel in between
+    pcie = None
+    try:
+        h_i = torch.empty(in_bytes, dtype=torch.uint8).pin_memory()
+        h_o = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+        d_i = torch.empty(in_bytes, dtype=torch.uint8, device="cuda")
+        d_o = torch.empty(out_bytes, dtype=torch.uint8, device="cuda")
+        s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+        nrep = max(10, int(0.2 / max(e2e_sec / Ke, 1e-6)))
+        for timed in (False, True):
+            torch.cuda.synchronize()
+            tp0 = time.perf_counter()
+            for _ in range(nrep):
+                with torch.cuda.stream(s_a):
+                    d_i.copy_(h_i, non_blocking=True)
+                with torch.cuda.stream(s_b):
+                    h_o.copy_(d_o, non_blocking=True)
+            torch.cuda.synchronize()
+            tp1 = time.perf_counter()
+        per_step = (tp1 - tp0) / nrep
+        pcie = {"copy_only_us_per_step": per_step * 1e6, "h2d_GBs": in_bytes / per_step / 1e9,
+                "d2h_GBs": out_bytes / per_step / 1e9,
+                "ceiling_msamples_per_sec": out_samples_step * world / per_step / 1e6,
+                "e2e_frac_of_ceiling": (e2e_value / (out_samples_step * world / per_step))}
+        del h_i, h_o, d_i, d_o
+    except Exception as ex:  # noqa: BLE001
+        pcie = {"error": str(ex)}
     for p in hin + hout:
         L.spxb_host_free(p)
 
@@ -398,7 +426,8 @@ def ours(args):
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": in_bytes,
                         "d2h_bytes_per_step": out_bytes, "steps": Ke, "pipeline_depth": depth,
-                        "how": "spxb_batch_submit/wait (C ABI), pinned host buffers, H2D+kernel+D2H per step"},
+                        "how": "spxb_batch_submit/wait (C ABI), pinned host buffers, H2D+kernel+D2H per step",
+                        "pcie": pcie},
                 "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     batch.close()

@@ -36,7 +36,7 @@ void set_error(const std::string &msg) { g_last_error = msg; }
     }                                                                                 \
   } while (0)
 
-constexpr int kPipelineDepth = 3;
+constexpr int kPipelineDepth = 4;  // slots; kPipelineDepth - 1 calls in flight
 
 inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 

@@ -82,15 +82,13 @@ __device__ __forceinline__ void trace_mark(const UmmaArgs &u, int slot) {
   if (u.trace) u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + slot] = static_cast<unsigned long long>(clock64());
 }
 
-// 16 bytes of one stream's input starting at frame f >= 0, sample by sample with zero fill past
-// the end of the call's input (kept out of line: only the last chunk of a row takes this path)
-__device__ __noinline__ uint4 fetch_item_slow(const int16_t *row, int f, uint32_t n_in, int ch) {
+// 16 bytes of one stream's input, sample by sample: the first `n` int16 samples at p, zeros after
+// (kept out of line: only the item holding the end of a row, or 2-byte aligned rows, come here)
+__device__ __noinline__ uint4 fetch_item_slow(const int16_t *p, int n) {
   uint32_t w[4] = {0u, 0u, 0u, 0u};
-  const long long avail = (static_cast<long long>(n_in) - f) * ch;  // samples left from frame f
 #pragma unroll
   for (int i = 0; i < 8; ++i)
-    if (i < avail)
-      w[i >> 1] |= static_cast<uint32_t>(static_cast<uint16_t>(row[static_cast<size_t>(f) * ch + i])) << (16 * (i & 1));
+    if (i < n) w[i >> 1] |= static_cast<uint32_t>(static_cast<uint16_t>(p[i])) << (16 * (i & 1));
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
@@ -236,47 +234,70 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   constexpr int SPI = 32 / PPS;        // streams per warp instruction (2 stereo, 4 mono)
   constexpr int kItems = 4;
   const int conv_p = lane % PPS;       // item position inside the stage segment
-  const int16_t *hist_row0[kItems];    // frame 0 of the stream in history coordinates (f < 0 indexes back)
-  const int16_t *in_row[kItems];
-  bool conv_live[kItems];
+  // Rows past the end of the batch read row 0 (their results are never stored).
   uint32_t conv_off[kItems];           // byte offset of the item's hi/left word(s) inside an X stage
+  const char *cur[kItems];             // where this thread's item of the NEXT fetched stage lives
+  int f_next = kf0 + conv_p * FPI;     // its first frame: history for f < 0, this call's input after
+  auto input_ptr = [&](int i, int f) {
+    const uint32_t sg = g * kStreams + static_cast<uint32_t>((4 * (warp & 7) + i) * SPI + lane / PPS);
+    const size_t r = sg < a.n_streams ? sg : 0;
+    return reinterpret_cast<const char *>(a.in + r * a.in_stride + static_cast<ptrdiff_t>(f) * CH);
+  };
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
     const uint32_t sl = static_cast<uint32_t>((4 * (warp & 7) + i) * SPI + lane / PPS);
     const uint32_t sg = g * kStreams + sl;
-    conv_live[i] = sg < a.n_streams;
-    const size_t r = conv_live[i] ? sg : 0;
-    hist_row0[i] = a.hist_src + r * a.hist_stride + static_cast<size_t>(a.hist_frames) * CH;
-    in_row[i] = a.in + r * a.in_stride;
+    const size_t r = sg < a.n_streams ? sg : 0;
+    cur[i] = f_next < 0 ? reinterpret_cast<const char *>(a.hist_src + r * a.hist_stride +
+                                                         (static_cast<ptrdiff_t>(a.hist_frames) + f_next) * CH)
+                        : input_ptr(i, f_next);
     // chunk j = 16 frames; inside the chunk row sl holds 16 bytes = 16 frames of one plane
     const uint32_t j = static_cast<uint32_t>(conv_p * FPI) / kUmmaChunkFrames;
     const uint32_t byte_in_row = static_cast<uint32_t>(conv_p * FPI) % kUmmaChunkFrames;
     conv_off[i] = j * kChunkBytesX + sl * 16 + byte_in_row;
   }
+  constexpr int kStageFrames = kStageChunks * kUmmaChunkFrames;  // 64
   uint4 raw0[kItems], raw1[kItems];
-  auto fetch = [&](uint32_t it, uint4 (&raw)[kItems]) {
-    const int f = kf0 + static_cast<int>(it * (kStageChunks * kUmmaChunkFrames)) + conv_p * FPI;
-    const bool in_hist = f < 0;
-    const bool full = in_hist || f + FPI <= static_cast<int>(sc.n_in);
+  // fetch the next stage (stages are fetched strictly in order): pointers just advance by one
+  // stage of bytes, except once, where a thread's frames cross from the history into the input
+  auto fetch = [&](uint4 (&raw)[kItems]) {
+    const int f = f_next;
+    f_next += kStageFrames;
+    if (f >= 0 && f < kStageFrames) {
 #pragma unroll
-    for (int i = 0; i < kItems; ++i) {
-      const int16_t *p = (in_hist ? hist_row0[i] : in_row[i]) + static_cast<ptrdiff_t>(f) * CH;
-      if (!conv_live[i] || (!in_hist && f >= static_cast<int>(sc.n_in)) || (SPXB_DEBUG_BITS(u) & 1u)) {
-        raw[i] = make_uint4(0u, 0u, 0u, 0u);
-      } else if (full && (in_hist || in_align == 16)) {
-        raw[i] = __ldg(reinterpret_cast<const uint4 *>(p));
-      } else if (full && in_align == 8) {
-        const uint2 lo = __ldg(reinterpret_cast<const uint2 *>(p));
-        const uint2 hi = __ldg(reinterpret_cast<const uint2 *>(p) + 1);
-        raw[i] = make_uint4(lo.x, lo.y, hi.x, hi.y);
-      } else if (full && in_align == 4) {
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(p);
-        raw[i] = make_uint4(__ldg(w), __ldg(w + 1), __ldg(w + 2), __ldg(w + 3));
-      } else {
-        // the item holding the end of the input, or rows only 2-byte aligned: sample by sample
-        raw[i] = fetch_item_slow(in_row[i], f, sc.n_in, CH);
-      }
+      for (int i = 0; i < kItems; ++i) cur[i] = input_ptr(i, f);
     }
+    const int rem = static_cast<int>(sc.n_in) - f;  // input frames left from f (when f >= 0)
+    if (SPXB_DEBUG_BITS(u) & 1u) {
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) raw[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else if (f < 0 || (rem >= FPI && in_align == 16)) {
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) raw[i] = __ldg(reinterpret_cast<const uint4 *>(cur[i]));
+    } else if (rem >= FPI && in_align == 8) {
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) {
+        const uint2 lo = __ldg(reinterpret_cast<const uint2 *>(cur[i]));
+        const uint2 hi = __ldg(reinterpret_cast<const uint2 *>(cur[i]) + 1);
+        raw[i] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+      }
+    } else if (rem >= FPI && in_align == 4) {
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(cur[i]);
+        raw[i] = make_uint4(__ldg(w), __ldg(w + 1), __ldg(w + 2), __ldg(w + 3));
+      }
+    } else if (rem <= 0) {
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) raw[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      // the item holding the end of the input, or rows only 2-byte aligned: sample by sample
+#pragma unroll
+      for (int i = 0; i < kItems; ++i)
+        raw[i] = fetch_item_slow(reinterpret_cast<const int16_t *>(cur[i]), min(rem, FPI) * CH);
+    }
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) cur[i] += kStageFrames * CH * 2;
   };
   // Everything above touched only kernel parameters and this CTA's own resources. The previous
   // call's grid (which reads the history buffer this call overwrites, and writes the one this call
@@ -284,8 +305,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   asm volatile("griddepcontrol.wait;" ::: "memory");
   // the first two stages' loads go out before the setup barrier
   if (warp < kConvWarps) {
-    fetch(0, raw0);
-    if (n_iters > 1) fetch(1, raw1);
+    fetch(raw0);
+    if (n_iters > 1) fetch(raw1);
   }
 
   tc_fence_before_sync();
@@ -327,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
       if (tr) trace_mark(u, 18);
       if (!(SPXB_DEBUG_BITS(u) & 4u)) convert_store(smem + slot * stage_bytes, raw);
       if (tr) trace_mark(u, 19);
-      if (it + 2 < n_iters) fetch(it + 2, raw);
+      if (it + 2 < n_iters) fetch(raw);
       if (tr) trace_mark(u, 10);
       fence_proxy_async_smem();
       mbar_arrive(&full_bar[slot]);
@@ -886,8 +907,10 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
   if (forced_cluster == 1 || forced_cluster == 2 || forced_cluster == 4) {
     cl = static_cast<uint32_t>(forced_cluster);
   } else {
-    if (n_groups % 4 == 0) cl = 4;
-    else if (n_groups % 2 == 0) cl = 2;
+    // measured (profiles/umma_cluster_sweep_r1.log): multicast pairs / quads are 7-20 % SLOWER than
+    // independent CTAs -- the tap stream is not the binding resource, shared-memory bandwidth is,
+    // and the lock-step of a cluster costs more than the saved L2 requests. Kept as an option.
+    cl = 1;
   }
   c->cluster = cl;
   c->grid_groups = (n_groups + cl - 1) / cl * cl;

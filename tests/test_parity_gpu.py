@@ -155,6 +155,45 @@ def test_full_size_c3_properties():
     twin.close()
 
 
+@pytest.mark.parametrize("name,S,ch,i,o,q,n,calls", [
+    ("C4", 4096, 1, 48000, 16000, 10, 960, 6),    # BASELINE configs[3]: long direct filter (N = 768)
+    ("C5", 8192, 2, 96000, 44100, 10, 1920, 3),   # BASELINE configs[4], one GPU's share of 65536 streams
+], ids=["C4", "C5"])
+def test_full_size_long_filter_properties(name, S, ch, i, o, q, n, calls):
+    """BASELINE configs[3] / [4] at full per-GPU size on the tensor kernel: every call consumes
+    and produces whole frames, streams are independent (duplicate input -> duplicate output,
+    a permuted batch gives permuted outputs), a sample of streams matches the oracle within
+    1 LSB / 90 dB, and the carried state equals the oracle's."""
+    cap = -(-n * o // i)
+    b = StreamBatch(S, ch, i, o, q)
+    twin = StreamBatch(S, ch, i, o, q)
+    pick = [0, 1, S // 2 + 3, S - 1]
+    refs = {s: O.OracleResampler(ch, i, o, q) for s in pick}
+    perm = np.random.default_rng(11).permutation(S)
+    base = synth_pcm(256, ch, n * calls, i, seed=0xC0FFEE)
+    sel = np.resize(np.arange(256), S)
+    for k in range(calls):
+        pcm = np.ascontiguousarray(base[np.roll(sel, 3 * k), k * n * ch:(k + 1) * n * ch])
+        pcm[7] = pcm[5]
+        out, used, made = b.process(pcm, n, cap)
+        assert b.last_kernel() == KERNEL_TENSOR
+        assert np.all(used == n) and np.all(made == made[0]) and made[0] in (cap, cap - 1)
+        assert np.array_equal(out[7], out[5])
+        out2, _, _ = twin.process(pcm[perm], n, cap)
+        assert np.array_equal(out2, out[perm])
+        for s in pick:
+            y, u_, m = refs[s].process(pcm[s], cap)
+            assert (u_, m) == (int(used[s]), int(made[s]))
+            check_close(y, out[s, : m * ch], exact=False, what=(name, k, s))
+    for s in pick:
+        ls, fr, mg, hist = b.get_state(s)
+        rls, rfr, rhist = refs[s].state(0)
+        assert (ls, fr, mg) == (rls, rfr, 0)
+        assert np.array_equal(hist.reshape(-1, ch)[:, 0].astype(np.float32), rhist)
+    b.close()
+    twin.close()
+
+
 # ---------------------------------------------------------------------------
 # the reference wrapper's observable behaviour (src/index.ts:50-116, :121-162)
 # ---------------------------------------------------------------------------
