@@ -134,6 +134,43 @@ __device__ __forceinline__ void combine16(const uint32_t (&p0)[16], const uint32
   }
 }
 
+// History slide of the streams first, first + step, ... (n_mine of them) by one warp: vectors of
+// type V (the widest the shift and the row alignment allow), four streams x four vectors per lane
+// loaded before any store so that 16 loads per lane are in flight.
+template <typename V>
+__device__ __forceinline__ void slide_rows(const CallArgs &a, uint32_t step, uint32_t first, uint32_t n_mine,
+                                           uint32_t hist_elems, size_t shift, int lane) {
+  constexpr uint32_t VW = sizeof(V) / 2;  // int16 elements per vector
+  for (uint32_t k0 = 0; k0 < n_mine; k0 += 4) {
+    for (uint32_t e0 = lane * VW; e0 < hist_elems; e0 += 32 * VW * 4) {
+      V val[4][4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const size_t s = first + static_cast<size_t>(k0 + kk) * step;
+        const int16_t *hsrc = a.hist_src + s * a.hist_stride;
+        const int16_t *isrc = a.in + s * a.in_stride;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t e = e0 + j * 32 * VW;
+          const size_t src = shift + e;
+          if (k0 + kk < n_mine && e < hist_elems)
+            val[kk][j] = __ldg(reinterpret_cast<const V *>(src < hist_elems ? hsrc + src : isrc + (src - hist_elems)));
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const size_t s = first + static_cast<size_t>(k0 + kk) * step;
+        int16_t *hdst = a.hist_dst + s * a.hist_stride;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t e = e0 + j * 32 * VW;
+          if (k0 + kk < n_mine && e < hist_elems) *reinterpret_cast<V *>(hdst + e) = val[kk][j];
+        }
+      }
+    }
+  }
+}
+
 template <int CH>
 __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a, const UmmaArgs u) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -210,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     if (u.cluster == 1) {
       bulk_g2s(dst, from, bytes, &full_bar[slot]);
     } else {
-      const uint32_t part = bytes / u.cluster, off = part * cta_rank;  // multiples of 16 bytes
+      const uint32_t part = bytes >> (u.cluster >> 1), off = part * cta_rank;  // cluster is 2 or 4
       bulk_g2s_multicast(dst + off, from + off, part, &full_bar[slot], cluster_mask);
     }
   };
@@ -224,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     tmem_relinquish();
   }
 
-  // ---- converter state: PCM items in flight, two stages deep ----
+  // ---- converter state: PCM items in flight, three stages deep ----
   // A stage is 64 frames of 128 series = kStreams stream segments of 64*CH*2 bytes. Lanes of a
   // warp walk ALONG a segment in 16-byte items (PPS items per stream, SPI streams per warp
   // instruction), so one LDG.128 covers four full 128-byte lines; each thread owns kItems items
@@ -257,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     conv_off[i] = j * kChunkBytesX + sl * 16 + byte_in_row;
   }
   constexpr int kStageFrames = kStageChunks * kUmmaChunkFrames;  // 64
-  uint4 raw0[kItems], raw1[kItems];
+  uint4 raw0[kItems], raw1[kItems], raw2[kItems];  // three stages of loads in flight
   // fetch the next stage (stages are fetched strictly in order): pointers just advance by one
   // stage of bytes, except once, where a thread's frames cross from the history into the input
   auto fetch = [&](uint4 (&raw)[kItems]) {
@@ -303,10 +340,11 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   // call's grid (which reads the history buffer this call overwrites, and writes the one this call
   // reads) must have completed before any global access below.
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  // the first two stages' loads go out before the setup barrier
+  // the first three stages' loads go out before the setup barrier
   if (warp < kConvWarps) {
     fetch(raw0);
     if (n_iters > 1) fetch(raw1);
+    if (n_iters > 2) fetch(raw2);
   }
 
   tc_fence_before_sync();
@@ -340,26 +378,35 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
         }
       }
     };
+    uint32_t cslot = 0, cpar = 1;  // ring slot of the stage being filled, parity its `empty` wait expects
+    uint8_t *cstage = smem;
     auto stage_step = [&](uint32_t it, uint4 (&raw)[kItems]) {
-      const uint32_t slot = it % S, par = (it / S) & 1u;
-      const bool tr = tid == 0 && it == 6;
+      const uint32_t slot = cslot, par = cpar ^ 1u;
+      const bool tr = u.trace && tid == 0 && it == 6;
       if (tr) trace_mark(u, 17);
       mbar_wait(&empty_bar[slot], par ^ 1u);
       if (tr) trace_mark(u, 18);
-      if (!(SPXB_DEBUG_BITS(u) & 4u)) convert_store(smem + slot * stage_bytes, raw);
+      if (!(SPXB_DEBUG_BITS(u) & 4u)) convert_store(cstage, raw);
       if (tr) trace_mark(u, 19);
-      if (it + 2 < n_iters) fetch(raw);
+      if (it + 3 < n_iters) fetch(raw);
       if (tr) trace_mark(u, 10);
       fence_proxy_async_smem();
       mbar_arrive(&full_bar[slot]);
       if (tr) trace_mark(u, 31);
+      cstage += stage_bytes;
+      if (++cslot == S) {
+        cslot = 0;
+        cpar ^= 1u;
+        cstage = smem;
+      }
     };
 
     if (tid == 0) trace_mark(u, 2);
-    for (uint32_t it = 0; it < n_iters; it += 2) {
+    for (uint32_t it = 0; it < n_iters; it += 3) {
       stage_step(it, raw0);
       if (tid == 0 && it == 0) trace_mark(u, 3);
       if (it + 1 < n_iters) stage_step(it + 1, raw1);
+      if (it + 2 < n_iters) stage_step(it + 2, raw2);
     }
     if (tid == 0) trace_mark(u, 4);
     if (tid == kConvThreads - 32) trace_mark(u, 30);
@@ -428,10 +475,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     // ================= tap tiles: one bulk copy per stage =================
     if (lane == 0) {
       const int8_t *src = u.pool + static_cast<size_t>(u.tiles[t].slot) * u.tile_bytes;
+      uint32_t slot = taps_issued % S, par = (taps_issued / S) & 1u;
       for (uint32_t it = taps_issued; it < n_iters; ++it) {
-        const uint32_t slot = it % S, par = (it / S) & 1u;
         mbar_wait(&empty_bar[slot], par ^ 1u);
         load_taps(it, slot, src);
+        if (++slot == S) {
+          slot = 0;
+          par ^= 1u;
+        }
       }
       trace_mark(u, 13);
     }
@@ -459,37 +510,6 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
       umma_i8(tmem + nt, a_lo, b, id_lo0, 1u);
       if (np1) umma_i8(tmem + nt + 256, a_lo, b + 256, id_lo1, 1u);
     };
-#ifdef SPXB_OLD_MMA_LOOP
-    (void)kstep;
-    for (uint32_t it = 0; it < n_iters; ++it) {
-      const uint32_t slot = it % S, par = (it / S) & 1u;
-      mbar_wait(&full_bar[slot], par);
-      tc_fence_after_sync();
-      if (lane == 0 && it < 12) trace_mark(u, 20 + it);
-      const uint32_t ks_here = min(static_cast<uint32_t>(kStageChunks), n_chunks - it * kStageChunks) / 2;
-      const uint64_t a_st = a_base + slot * stage_step16, b_st = b_base + slot * stage_step16;
-      if (elect_one()) {
-        for (uint32_t ks = 0; ks < ks_here; ++ks) {
-          const uint64_t a_hi = a_st + ks * a_ks16, a_lo = a_hi + a_lo16, b = b_st + ks * b_ks16;
-          if (it == 0 && ks == 0) {
-            umma_i8(tmem, a_hi, b, id_hi0, 0u);
-            if (np1) umma_i8(tmem + 256, a_hi, b + 256, id_hi1, 0u);
-            umma_i8(tmem + nt, a_lo, b, id_lq0, 1u);
-            if (nq1) umma_i8(tmem + nt + 256, a_lo, b + 256, id_lq1, 1u);
-            umma_i8(tmem + 3 * nt, a_lo, b + 2 * nt, id_lf, 0u);
-          } else {
-            umma_i8(tmem, a_hi, b, id_hi0, 1u);
-            if (np1) umma_i8(tmem + 256, a_hi, b + 256, id_hi1, 1u);
-            umma_i8(tmem + nt, a_lo, b, id_lo0, 1u);
-            if (np1) umma_i8(tmem + nt + 256, a_lo, b + 256, id_lo1, 1u);
-          }
-        }
-        umma_commit(&empty_bar[slot]);
-        if (it + 1 == n_iters) umma_commit(&acc_bar);
-      }
-      __syncwarp();
-    }
-#else
     uint32_t slot = 0, par = 0;
     uint64_t a_st = a_base, b_st = b_base;
     const bool odd_tail = (n_chunks % kStageChunks) != 0;  // last stage holds one K step
@@ -526,7 +546,6 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
         b_st = b_base;
       }
     }
-#endif
     if (lane == 0) trace_mark(u, 11);
   } else {
     // ================= history slide (resample.c:898-899) and the new position =================
@@ -542,51 +561,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     const uint32_t in_group = t < static_cast<uint32_t>(kStreams) ? (kStreams - t + u.n_tiles - 1) / u.n_tiles : 0u;
     const uint32_t in_batch = first < a.n_streams ? (a.n_streams - first + u.n_tiles - 1) / u.n_tiles : 0u;
     const uint32_t n_mine = min(in_group, in_batch);
-    if (vw == 8) {
-      // 16-byte vectors; four streams x four vectors per lane in flight before the stores
-      for (uint32_t k0 = 0; k0 < n_mine; k0 += 4) {
-        for (uint32_t e0 = lane * 8; e0 < hist_elems; e0 += 32 * 8 * 4) {
-          uint4 val[4][4];
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const size_t s = first + static_cast<size_t>(k0 + kk) * u.n_tiles;
-            const int16_t *hsrc = a.hist_src + s * a.hist_stride;
-            const int16_t *isrc = a.in + s * a.in_stride;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t e = e0 + j * 256;
-              const size_t src = shift + e;
-              if (k0 + kk < n_mine && e < hist_elems)
-                val[kk][j] = __ldg(reinterpret_cast<const uint4 *>(src < hist_elems ? hsrc + src : isrc + (src - hist_elems)));
-            }
-          }
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const size_t s = first + static_cast<size_t>(k0 + kk) * u.n_tiles;
-            int16_t *hdst = a.hist_dst + s * a.hist_stride;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t e = e0 + j * 256;
-              if (k0 + kk < n_mine && e < hist_elems) *reinterpret_cast<uint4 *>(hdst + e) = val[kk][j];
-            }
-          }
-        }
-      }
-    } else {
-      for (uint32_t k = 0; k < n_mine; ++k) {
-        const size_t s = first + static_cast<size_t>(k) * u.n_tiles;
-        const int16_t *hsrc = a.hist_src + s * a.hist_stride;
-        const int16_t *isrc = a.in + s * a.in_stride;
-        int16_t *hdst = a.hist_dst + s * a.hist_stride;
-        for (uint32_t e = lane * vw; e < hist_elems; e += 32 * vw) {
-          const size_t src = shift + e;
-          const int16_t *p = src < hist_elems ? hsrc + src : isrc + (src - hist_elems);
-          if (vw == 4) *reinterpret_cast<uint2 *>(hdst + e) = *reinterpret_cast<const uint2 *>(p);
-          else if (vw == 2) *reinterpret_cast<uint32_t *>(hdst + e) = *reinterpret_cast<const uint32_t *>(p);
-          else hdst[e] = *p;
-        }
-      }
-    }
+    if (vw == 8) slide_rows<uint4>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane);
+    else if (vw == 4) slide_rows<uint2>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane);
+    else if (vw == 2) slide_rows<uint32_t>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane);
+    else slide_rows<uint16_t>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane);
     for (uint32_t k = lane; k < n_mine; k += 32) {
       const size_t s = first + static_cast<size_t>(k) * u.n_tiles;
       a.last_sample[s] = sc.ls1;
