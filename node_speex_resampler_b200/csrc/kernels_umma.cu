@@ -44,11 +44,16 @@ constexpr int kConvThreads = kConvWarps * 32;
 constexpr int kTmaWarp = 8, kMmaWarp = 9;  // warp 10 slides the history
 constexpr int kThreads = 352;
 constexpr int kStageChunks = 4;                                  // 64 frames, 2 K steps
-// K chunk of one byte plane: 128 rows x 16 B, plus 32 B so that the four chunks of a stage start
-// 8 banks apart (the converters' stores hit 32 distinct banks; LBO is a free multiple of 16 B)
-constexpr uint32_t kChunkBytesX = kUmmaRows * 16 + 32;           // 2080
-constexpr uint32_t kXPlaneBytes = kStageChunks * kChunkBytesX;   // 8320
-constexpr uint32_t kXStageBytes = 2 * kXPlaneBytes;              // hi + lo planes
+// One byte plane of a stage = four K chunks of 128 rows x 16 B. Chunk c sits at
+// (c >> 1) * x_kstep + (c & 1) * x_lbo: the pair of chunks of one MMA is LBO apart (a free multiple
+// of 16 B), and the paddings are chosen so that one converter store instruction hits 32 distinct
+// banks -- mono: a warp stores 4 rows x 8 positions (8 B each), chunks must start 8 banks apart;
+// stereo: a warp stores 2 streams x 16 positions into rows 2s (left) or 2s+1 (right), chunk
+// starts must be {0, 16, 4, 20} banks (checked exhaustively in tests/test_tensor_plan.py).
+__host__ __device__ constexpr uint32_t x_lbo(int ch) { return kUmmaRows * 16 + (ch == 2 ? 64 : 32); }
+__host__ __device__ constexpr uint32_t x_kstep(int ch) { return 2 * x_lbo(ch) + (ch == 2 ? 16 : 0); }
+__host__ __device__ constexpr uint32_t x_plane(int ch) { return 2 * x_kstep(ch); }
+__host__ __device__ constexpr uint32_t x_stage(int ch) { return 2 * x_plane(ch); }  // hi + lo planes
 constexpr int kMaxStages = 6;
 constexpr uint32_t kMaxSmem = 227u * 1024u - 2048u;              // dynamic part; barriers are static
 
@@ -103,7 +108,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// the 16 accumulator columns of one output group -> rounded, saturated int16 values
+// two int32 -> saturated int16 pair: (hi << 16) | lo  (the saturation of WORD2INT, arch.h:208-209)
+__device__ __forceinline__ uint32_t pack_sat_s16x2(int hi, int lo) {
+  uint32_t d;
+  asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+  return d;
+}
+
+// the 16 accumulator columns of one output group -> rounded (not yet saturated) integers
 // y = (p0*2^24 + p1*2^16 + p2*2^8 + p3) * 2^-shift, result floor(y + 1/2) (arch.h:208-209)
 __device__ __forceinline__ void combine16(const uint32_t (&p0)[16], const uint32_t (&p1)[16],
                                           const uint32_t (&p2)[16], const uint32_t (&p3)[16], int shift,
@@ -118,7 +130,7 @@ __device__ __forceinline__ void combine16(const uint32_t (&p0)[16], const uint32
       int w = static_cast<int>(p3[i]) + half;
       w = (w >> 8) + static_cast<int>(p2[i]);
       w = (w >> 8) + static_cast<int>(p1[i]) + static_cast<int>(p0[i] << 8);
-      r16[i] = max(-32768, min(32767, w >> s2));
+      r16[i] = w >> s2;
     }
   } else {
     const long long half = 1ll << (shift - 1);
@@ -129,7 +141,7 @@ __device__ __forceinline__ void combine16(const uint32_t (&p0)[16], const uint32
       v += static_cast<long long>(static_cast<int>(p1[i])) << 16;
       v += static_cast<long long>(static_cast<int>(p0[i])) << 24;
       const long long r = (v + half) >> shift;
-      r16[i] = static_cast<int>(max(-32768ll, min(32767ll, r)));
+      r16[i] = static_cast<int>(max(-40000ll, min(40000ll, r)));
     }
   }
 }
@@ -197,6 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   }
   const uint32_t tap_chunk = 3 * nt * 16;
   const uint32_t tap_stage = kStageChunks * tap_chunk;
+  constexpr uint32_t kXPlaneBytes = x_plane(CH), kXStageBytes = x_stage(CH);
   const uint32_t stage_bytes = kXStageBytes + tap_stage;
   const uint32_t n_chunks = 2 * u.ksteps;
   const uint32_t n_iters = (n_chunks + kStageChunks - 1) / kStageChunks;
@@ -291,7 +304,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     // chunk j = 16 frames; inside the chunk row sl holds 16 bytes = 16 frames of one plane
     const uint32_t j = static_cast<uint32_t>(conv_p * FPI) / kUmmaChunkFrames;
     const uint32_t byte_in_row = static_cast<uint32_t>(conv_p * FPI) % kUmmaChunkFrames;
-    conv_off[i] = j * kChunkBytesX + sl * 16 + byte_in_row;
+    // stereo: left channel of stream sl -> row 2 sl, right channel -> row 2 sl + 1
+    conv_off[i] = (j >> 1) * x_kstep(CH) + (j & 1) * x_lbo(CH) + sl * (16 * CH) + byte_in_row;
   }
   constexpr int kStageFrames = kStageChunks * kUmmaChunkFrames;  // 64
   uint4 raw0[kItems], raw1[kItems], raw2[kItems];  // three stages of loads in flight
@@ -367,14 +381,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
           *reinterpret_cast<uint2 *>(base) = hi;
           *reinterpret_cast<uint2 *>(base + kXPlaneBytes) = lo;
         } else {
-          // 4 frames; word f = (R_f << 16) | L_f -> one word per plane and channel.
-          // rows: left channel of stream sl -> row sl, right channel -> row 64 + sl
+          // 4 frames; word f = (R_f << 16) | L_f -> one word per plane and channel (rows 2 sl, 2 sl + 1)
           const uint32_t ul = __byte_perm(w.x, w.y, 0x5140), vl = __byte_perm(w.z, w.w, 0x5140);
           const uint32_t ur = __byte_perm(w.x, w.y, 0x7362), vr = __byte_perm(w.z, w.w, 0x7362);
           *reinterpret_cast<uint32_t *>(base) = __byte_perm(ul, vl, 0x7632);
-          *reinterpret_cast<uint32_t *>(base + 64 * 16) = __byte_perm(ur, vr, 0x7632);
+          *reinterpret_cast<uint32_t *>(base + 16) = __byte_perm(ur, vr, 0x7632);
           *reinterpret_cast<uint32_t *>(base + kXPlaneBytes) = __byte_perm(ul, vl, 0x5410);
-          *reinterpret_cast<uint32_t *>(base + kXPlaneBytes + 64 * 16) = __byte_perm(ur, vr, 0x5410);
+          *reinterpret_cast<uint32_t *>(base + kXPlaneBytes + 16) = __byte_perm(ur, vr, 0x5410);
         }
       }
     };
@@ -415,11 +428,20 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     mbar_wait(&acc_bar, 0);
     tc_fence_after_sync();
     if (tid == 0) trace_mark(u, 5);
+    // Straight from TMEM to the interleaved int16 output: a lane owns one series (TMEM lane) and 16
+    // consecutive outputs per column group; mono packs them into 32 contiguous bytes, stereo first
+    // swaps halves with the neighbouring lane (the other channel of the same stream) so that each
+    // lane of the pair holds 8 whole frames = 32 contiguous bytes.
     const uint32_t n_valid = min(nt, sc.n_out - m0);
     const uint32_t row = (warp & 3) * 32 + lane;  // TMEM lane
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const uint32_t pitch_w = (CH == 2 ? nt : nt / 2) + 1;  // words per staged row (odd)
-    uint16_t *stage16 = reinterpret_cast<uint16_t *>(smem);
+    const uint32_t sl_out = CH == 2 ? row >> 1 : row, ch_out = CH == 2 ? (row & 1u) : 0u;
+    const uint32_t s_out = g * kStreams + sl_out;
+    const bool live_out = s_out < a.n_streams;
+    int16_t *out_row = a.out + static_cast<size_t>(live_out ? s_out : 0) * a.out_stride + static_cast<size_t>(m0) * CH;
+    const uint32_t out_bits = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(a.out)) |
+                              (static_cast<uint32_t>(a.out_stride) * 2u);
+    const int out_align = (out_bits & 15u) == 0 ? 16 : (out_bits & 3u) == 0 ? 4 : 2;
     for (uint32_t cg = warp >> 2; cg * 16 < n_valid; cg += 2) {
       uint32_t p0[16], p1[16], p2[16], p3[16];
       tmem_ld16(lane_addr + cg * 16, p0);
@@ -428,48 +450,48 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
       tmem_ld16(lane_addr + 3 * nt + cg * 16, p3);
       tmem_ld_wait();
       int r16[16];
-      combine16(p0, p1, p2, p3, u.shift, r16);
+      combine16(p0, p1, p2, p3, u.shift, r16);  // rounded, not yet saturated
+      uint32_t w[8];       // this lane's 16 int16 values = 32 contiguous output bytes
+      uint32_t first_elem;  // their position in the stream's row, in int16 elements from m0
       if (CH == 2) {
-        const uint32_t sl = row & 63, c = row >> 6;
-        uint16_t *dst = stage16 + (sl * pitch_w) * 2 + (cg * 16) * 2 + c;
+        // lane pair (left, right): left keeps frames [0,8), right keeps frames [8,16)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dst[2 * i] = static_cast<uint16_t>(r16[i]);
+        for (int j = 0; j < 8; ++j) {
+          const int send = ch_out == 0 ? r16[8 + j] : r16[j];
+          const int recv = __shfl_xor_sync(0xffffffffu, send, 1);
+          w[j] = ch_out == 0 ? pack_sat_s16x2(recv, r16[j]) : pack_sat_s16x2(r16[8 + j], recv);
+        }
+        first_elem = (cg * 16 + ch_out * 8) * 2;
       } else {
-        uint32_t *dst = reinterpret_cast<uint32_t *>(smem) + row * pitch_w + cg * 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          dst[i] = (static_cast<uint32_t>(r16[2 * i]) & 0xffffu) | (static_cast<uint32_t>(r16[2 * i + 1]) << 16);
+        for (int j = 0; j < 8; ++j) w[j] = pack_sat_s16x2(r16[2 * j + 1], r16[2 * j]);
+        first_elem = cg * 16;
+      }
+      if (!live_out) continue;
+      const uint32_t total = n_valid * CH;
+      const uint32_t n_here = first_elem >= total ? 0u : min(16u, total - first_elem);  // int16 elements
+      int16_t *dst = out_row + first_elem;
+      if (n_here == 16 && out_align == 16) {
+        reinterpret_cast<uint4 *>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        reinterpret_cast<uint4 *>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      } else if (out_align >= 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (2u * j + 1 < n_here) reinterpret_cast<uint32_t *>(dst)[j] = w[j];
+        if (n_here & 1u) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (2u * j + 1 == n_here) dst[2 * j] = static_cast<int16_t>(w[j] & 0xffffu);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (2u * j < n_here) dst[2 * j] = static_cast<int16_t>(w[j] & 0xffffu);
+          if (2u * j + 1 < n_here) dst[2 * j + 1] = static_cast<int16_t>(w[j] >> 16);
+        }
       }
     }
     if (tid == 0) trace_mark(u, 6);
-    asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
-    // staged rows -> global, coalesced along the stream's interleaved output; a row is at most
-    // 128 words, i.e. four words per lane, all four loads in flight before the stores
-    const uint32_t *stage32 = reinterpret_cast<const uint32_t *>(smem);
-    const uint32_t n_elems = n_valid * CH;
-    const uint32_t n_words = n_elems / 2;
-#pragma unroll 2
-    for (uint32_t r = warp; r < static_cast<uint32_t>(kStreams); r += kConvWarps) {
-      const uint32_t s = g * kStreams + r;
-      if (s >= a.n_streams) break;
-      int16_t *dst = a.out + static_cast<size_t>(s) * a.out_stride + static_cast<size_t>(m0) * CH;
-      if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
-        uint32_t w[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t i = lane + 32 * j;
-          if (i < n_words) w[j] = stage32[r * pitch_w + i];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t i = lane + 32 * j;
-          if (i < n_words) reinterpret_cast<uint32_t *>(dst)[i] = w[j];
-        }
-        if ((n_elems & 1u) && lane == 0) dst[n_elems - 1] = static_cast<int16_t>(stage16[r * pitch_w * 2 + n_elems - 1]);
-      } else {
-        for (uint32_t i = lane; i < n_elems; i += 32) dst[i] = static_cast<int16_t>(stage16[r * pitch_w * 2 + i]);
-      }
-    }
     if (tid == 0) trace_mark(u, 7);
   } else if (warp == kTmaWarp) {
     // ================= tap tiles: one bulk copy per stage =================
@@ -498,10 +520,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     const uint32_t id_lo0 = umma_idesc_i8(128, np0, false, true), id_lo1 = umma_idesc_i8(128, np1, false, true);
     const uint32_t id_lq0 = umma_idesc_i8(128, nq0, false, true), id_lq1 = umma_idesc_i8(128, nq1, false, true);
     const uint32_t id_lf = umma_idesc_i8(128, nt, false, true);
-    const uint64_t a_base = umma_smem_desc(smem_u32(smem), kChunkBytesX, 128);
+    const uint64_t a_base = umma_smem_desc(smem_u32(smem), x_lbo(CH), 128);
     const uint64_t b_base = umma_smem_desc(smem_u32(smem) + kXStageBytes, tap_chunk, 128);
     const uint32_t stage_step16 = stage_bytes >> 4;
-    const uint32_t a_ks16 = (2 * kChunkBytesX) >> 4, a_lo16 = kXPlaneBytes >> 4, b_ks16 = (2 * tap_chunk) >> 4;
+    const uint32_t a_ks16 = x_kstep(CH) >> 4, a_lo16 = kXPlaneBytes >> 4, b_ks16 = (2 * tap_chunk) >> 4;
     // One K step = hi plane x B into [0,3nt), lo plane x the same B into [nt,4nt).
     auto kstep = [&](uint64_t a_hi, uint64_t b) {
       const uint64_t a_lo = a_hi + a_lo16;
@@ -680,7 +702,7 @@ uint32_t pick_nt(const UmmaContext &c, uint32_t n_groups, uint32_t n_out) {
     const double ctas = static_cast<double>(tiles) * n_groups;
     const double waves = std::ceil(ctas / c.sm_count);
     const uint32_t ks = umma_ksteps(c.spec.taps, c.spec.num, c.spec.den, nt);
-    const double stage_cycles = std::max(6.0 * nt, (2.0 * kXPlaneBytes + 4.0 * 48.0 * nt) / 30.0);
+    const double stage_cycles = std::max(6.0 * nt, (1.0 * x_stage(2) + 4.0 * 48.0 * nt) / 30.0);
     const double tile_cycles = 5500.0 + stage_cycles * ((ks + 1) / 2) + 10.0 * nt;
     const double cost = waves * tile_cycles;
     if (cost < best_cost) {
@@ -778,13 +800,10 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
     c->ksteps = umma_ksteps(c->spec.taps, c->spec.num, c->spec.den, nt);
     c->tile_bytes = 2 * c->ksteps * 3 * nt * 16;
     c->tmem_cols = pow2_cols(4 * nt);
-    const uint32_t stage_bytes = kXStageBytes + kStageChunks * 3 * nt * 16;
+    const uint32_t stage_bytes = x_stage(static_cast<int>(a.channels)) + kStageChunks * 3 * nt * 16;
     const uint32_t n_iters = (2 * c->ksteps + kStageChunks - 1) / kStageChunks;
     uint32_t stages = std::min<uint32_t>(kMaxStages, kMaxSmem / stage_bytes);
     stages = std::max(1u, std::min(stages, n_iters));
-    // the epilogue stages the output tile over the (drained) ring
-    const uint32_t out_bytes = (a.channels == 2 ? 64u * (nt + 1) : 128u * (nt / 2 + 1)) * 4u;
-    while (stages * stage_bytes < out_bytes) ++stages;
     c->stages = stages;
     c->smem_bytes = stages * stage_bytes;
     if (c->smem_bytes > kMaxSmem) return false;
