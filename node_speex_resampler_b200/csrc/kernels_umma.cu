@@ -13,14 +13,26 @@
 //     A = hi plane (s8) x B rows [d2 | d1 | d0]  -> columns [0, 3nt)
 //     A = lo plane (u8) x the same B             -> columns [nt, 4nt)
 //   The K (window) axis is streamed through a ring of shared-memory stages of 64 frames:
-//     X stage   [plane 2][chunk 4][row 128][16 B]   K-major, no swizzle (LBO 2048, SBO 128)
-//     tap stage [chunk 4][row 3nt][16 B]            one 1-D bulk copy from the tile pool
-// Warp roles: 0-7 fetch int16 PCM (history for frames < 0, the call's input after), split it
-// into byte planes with PRMT and store it in UMMA layout, later run the epilogue
-// (tcgen05.ld, 64-bit recombination, round-half-up + saturate, interleaved int16 stores through
-// shared memory); warp 8 lane 0 issues the tap bulk copies; warp 9 owns TMEM and lane 0
-// issues the MMAs. Stages are handed over with mbarriers (full: 256 converter arrivals + the
-// bulk copy's byte count; empty: tcgen05.commit).
+//     X stage   [plane 2][K step 2][half 2][row 128][16 B]  K-major, no swizzle; row = stream
+//               (mono) or 2*stream + channel (stereo); chunk strides padded so that a converter
+//               store instruction hits 32 distinct banks (x_lbo / x_kstep below)
+//     tap stage [chunk 4][row 3nt][16 B]                   one 1-D bulk copy from the tile pool
+// Warp roles (352 threads):
+//   0-7  converters: fetch int16 PCM (history for frames < 0, the call's input after) with lanes
+//        walking ALONG a stream's segment (one LDG.128 = four whole lines), three stages of loads in
+//        flight in registers, split into byte planes with PRMT, store in UMMA layout; afterwards
+//        the epilogue: tcgen05.ld, 32-bit nested-floor recombination (exact), lane-pair exchange for
+//        stereo, cvt.pack.sat (= WORD2INT's saturation) and 16-byte stores straight to the output;
+//   8    lane 0 owns the mbarriers and issues the tap bulk copies (first ring-full before the
+//        programmatic grid dependency resolves);
+//   9    owns TMEM; the whole warp walks the stages, one elected lane issues the MMAs from
+//        uniform registers (four per K step) and releases stages with tcgen05.commit;
+//   10   slides the history (resample.c:898-899) and publishes the new stream position, beside
+//        the FIR.
+// Stages are handed over with mbarriers (full: 256 converter arrivals + the bulk copy's byte
+// count; empty: tcgen05.commit). Launched with programmatic stream serialization: the next call's
+// grid runs its prologue while this one drains and blocks in griddepcontrol.wait before touching
+// PCM or history. Measured limits and what was tried: DESIGN.md section 4.3.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
