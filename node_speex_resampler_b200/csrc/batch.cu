@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -36,7 +37,16 @@ void set_error(const std::string &msg) { g_last_error = msg; }
     }                                                                                 \
   } while (0)
 
-constexpr int kPipelineDepth = 4;  // slots; kPipelineDepth - 1 calls in flight
+constexpr int kMaxPipelineSlots = 8;
+// slots of the host-buffer pipeline; slots - 1 calls in flight. SPXB_PIPELINE_SLOTS overrides (2..8).
+static int pipeline_slots() {
+  static const int v = [] {
+    const char *e = getenv("SPXB_PIPELINE_SLOTS");
+    const int n = e ? atoi(e) : 4;
+    return n < 2 ? 2 : n > kMaxPipelineSlots ? kMaxPipelineSlots : n;
+  }();
+  return v;
+}
 
 inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
@@ -90,7 +100,7 @@ struct spxb_batch {
   cudaStream_t s_own = nullptr, s_compute = nullptr, s_in = nullptr, s_out = nullptr;
   bool external_stream = false;
   cudaEvent_t ev_state = nullptr;
-  Slot slots[kPipelineDepth];
+  Slot slots[kMaxPipelineSlots];
   uint64_t next_ticket = 1;
   UmmaContext *umma = nullptr;  // tensor kernel state (nullptr: filter not covered)
   int kernel_pref = SPXB_KERNEL_AUTO;
@@ -447,7 +457,7 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
   DeviceGuard g(b->device);
   const uint32_t S = b->n_streams;
   const size_t ch = b->channels;
-  Slot &sl = b->slots[b->next_ticket % kPipelineDepth];
+  Slot &sl = b->slots[b->next_ticket % pipeline_slots()];
   if (int e = retire_slot(b, sl)) return e;
 
   // remember the offered lengths: decide() overwrites the arrays with consumed / written
@@ -634,7 +644,7 @@ long spxb_batch_tensor_trace(spxb_batch *b, uint64_t *dst, size_t cap_words) {
   return umma_read_trace(b->umma, reinterpret_cast<unsigned long long *>(dst), cap_words);
 }
 
-int spxb_batch_pipeline_depth(const spxb_batch *) { return kPipelineDepth - 1; }
+int spxb_batch_pipeline_depth(const spxb_batch *) { return pipeline_slots() - 1; }
 
 int spxb_batch_submit(spxb_batch *b, const int16_t *in, size_t in_stride_frames, uint32_t *in_frames,
                       int16_t *out, size_t out_stride_frames, uint32_t *out_frames,
@@ -664,7 +674,7 @@ int spxb_batch_process_device(spxb_batch *b, const int16_t *d_in, size_t in_stri
                               uint32_t *out_frames) {
   if (!b || !in_frames || !out_frames) return RESAMPLER_ERR_INVALID_ARG;
   DeviceGuard g(b->device);
-  Slot &sl = b->slots[b->next_ticket % kPipelineDepth];
+  Slot &sl = b->slots[b->next_ticket % pipeline_slots()];
   if (int e = retire_slot(b, sl)) return e;
   const uint32_t S = b->n_streams;
   if (!sl.h_calls) {

@@ -69,9 +69,17 @@ __host__ __device__ constexpr uint32_t x_stage(int ch) { return 2 * x_plane(ch);
 constexpr int kMaxStages = 6;
 constexpr uint32_t kMaxSmem = 227u * 1024u - 2048u;              // dynamic part; barriers are static
 
+constexpr uint32_t kInlineTiles = 64;  // tile table carried in the kernel parameters up to this many tiles
+struct InlineTile {
+  int32_t kf0;    // first frame of the tile's K axis (UmmaTile::kf0)
+  uint32_t slot;  // its tap tile in the pool
+};
+
 struct UmmaArgs {
   const UmmaTile *tiles;
   uint32_t n_tiles;
+  uint32_t n_inline;          // != 0: inl[] holds the tile table (no dependent global load, no
+                              // 64-bit division in the prologue)
   uint32_t n_groups;          // series groups in the grid (padded to a multiple of `cluster`)
   uint32_t cluster;           // CTAs per cluster (1, 2 or 4): same tile, consecutive series groups;
                               // each loads 1/cluster of every tap stage and multicasts it
@@ -85,6 +93,7 @@ struct UmmaArgs {
   unsigned long long *trace;  // optional per-CTA timeline (kTraceSlots words per CTA), else nullptr
   uint32_t debug;             // SPXB_UMMA_DEBUG bits (timing experiments only, results are garbage):
                               // 1 = no PCM loads, 2 = no MMAs, 4 = no PCM conversion/stores
+  InlineTile inl[kInlineTiles];
 };
 
 // Timing-experiment knobs cost ~10 % on the long-filter shapes even when off (they perturb the
@@ -195,7 +204,11 @@ __device__ __forceinline__ void slide_rows(const CallArgs &a, uint32_t step, uin
   }
 }
 
-template <int CH>
+// FAST = every input and output row starts on a 16-byte boundary and the CTA is not part of a
+// cluster: the instantiation every BASELINE shape takes. It drops the narrower load / store
+// variants and the multicast paths, which is worth having because warps of five roles run
+// different parts of this kernel at the same time and share one instruction cache.
+template <int CH, bool FAST>
 __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a, const UmmaArgs u) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], acc_bar;
@@ -208,10 +221,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   const uint32_t g = blockIdx.x % u.n_groups, t = blockIdx.x / u.n_groups;
   const StreamCall sc = a.uniform;
   const uint32_t nt = u.nt;
-  // tile geometry in closed form (umma_plan.cpp: plan_umma_tiles), no dependent global load
+  // tile geometry: from the kernel parameters (constant bank), else in closed form
+  // (umma_plan.cpp: plan_umma_tiles) with the tap-tile slot read from the table in HBM
   const uint32_t m0 = t * nt;
   int kf0;
-  {
+  if (u.n_inline) {
+    kf0 = u.inl[t].kf0;
+  } else {
     const unsigned long long tt = static_cast<unsigned long long>(sc.frac0) +
                                   static_cast<unsigned long long>(m0) * a.filt.num;
     const long long q0 = static_cast<long long>(sc.ls0) - (static_cast<long long>(a.filt.taps) - 1) +
@@ -226,12 +242,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   const uint32_t n_chunks = 2 * u.ksteps;
   const uint32_t n_iters = (n_chunks + kStageChunks - 1) / kStageChunks;
   const uint32_t S = u.stages;
-  const uint32_t cta_rank = u.cluster > 1 ? cluster_ctarank() : 0u;
-  const uint16_t cluster_mask = static_cast<uint16_t>((1u << u.cluster) - 1u);
+  const uint32_t cluster = FAST ? 1u : u.cluster;
+  const uint32_t cta_rank = cluster > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cluster_mask = static_cast<uint16_t>((1u << cluster) - 1u);
   // alignment every input row start shares (16-byte items start at multiples of 16 B in a row)
   const uint32_t row_bits = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(a.in)) |
                             (static_cast<uint32_t>(a.in_stride) * 2u);
-  const int in_align = (row_bits & 15u) == 0 ? 16 : (row_bits & 7u) == 0 ? 8 : (row_bits & 3u) == 0 ? 4 : 2;
+  const int in_align = FAST ? 16 : (row_bits & 15u) == 0 ? 16 : (row_bits & 7u) == 0 ? 8 : (row_bits & 3u) == 0 ? 4 : 2;
 
   // Programmatic dependent launch: let the next call's grid start its prologue (barrier init,
   // TMEM allocation) while this grid drains; it blocks in griddepcontrol.wait below until this
@@ -256,28 +273,28 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   if (warp == kTmaWarp && lane == 0) {
     for (uint32_t s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], kConvThreads + 1);
-      mbar_init(&empty_bar[s], u.cluster);  // every CTA of the cluster is done with the slot
+      mbar_init(&empty_bar[s], cluster);  // every CTA of the cluster is done with the slot
     }
     mbar_init(&acc_bar, 1);
     fence_mbar_init();
   }
   // peers multicast into this CTA's stages and arrive on its barriers: all initialised first
-  if (u.cluster > 1) cluster_sync_all();
+  if (cluster > 1) cluster_sync_all();
   auto load_taps = [&](uint32_t it, uint32_t slot, const int8_t *src) {
     const uint32_t chunks_here = min(static_cast<uint32_t>(kStageChunks), n_chunks - it * kStageChunks);
     const uint32_t bytes = chunks_here * tap_chunk;
     uint8_t *dst = smem + slot * stage_bytes + kXStageBytes;
     const int8_t *from = src + static_cast<size_t>(it) * tap_stage;
     mbar_arrive_expect_tx(&full_bar[slot], bytes);
-    if (u.cluster == 1) {
+    if (cluster == 1) {
       bulk_g2s(dst, from, bytes, &full_bar[slot]);
     } else {
-      const uint32_t part = bytes >> (u.cluster >> 1), off = part * cta_rank;  // cluster is 2 or 4
+      const uint32_t part = bytes >> (cluster >> 1), off = part * cta_rank;  // cluster is 2 or 4
       bulk_g2s_multicast(dst + off, from + off, part, &full_bar[slot], cluster_mask);
     }
   };
   if (warp == kTmaWarp && lane == 0) {
-    const int8_t *src = u.pool + static_cast<size_t>(u.tiles[t].slot) * u.tile_bytes;
+    const int8_t *src = u.pool + static_cast<size_t>(u.n_inline ? u.inl[t].slot : u.tiles[t].slot) * u.tile_bytes;
     for (; taps_issued < min(S, n_iters); ++taps_issued) load_taps(taps_issued, taps_issued, src);
     trace_mark(u, 12);
   }
@@ -453,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     int16_t *out_row = a.out + static_cast<size_t>(live_out ? s_out : 0) * a.out_stride + static_cast<size_t>(m0) * CH;
     const uint32_t out_bits = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(a.out)) |
                               (static_cast<uint32_t>(a.out_stride) * 2u);
-    const int out_align = (out_bits & 15u) == 0 ? 16 : (out_bits & 3u) == 0 ? 4 : 2;
+    const int out_align = FAST ? 16 : (out_bits & 15u) == 0 ? 16 : (out_bits & 3u) == 0 ? 4 : 2;
     for (uint32_t cg = warp >> 2; cg * 16 < n_valid; cg += 2) {
       uint32_t p0[16], p1[16], p2[16], p3[16];
       tmem_ld16(lane_addr + cg * 16, p0);
@@ -508,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   } else if (warp == kTmaWarp) {
     // ================= tap tiles: one bulk copy per stage =================
     if (lane == 0) {
-      const int8_t *src = u.pool + static_cast<size_t>(u.tiles[t].slot) * u.tile_bytes;
+      const int8_t *src = u.pool + static_cast<size_t>(u.n_inline ? u.inl[t].slot : u.tiles[t].slot) * u.tile_bytes;
       uint32_t slot = taps_issued % S, par = (taps_issued / S) & 1u;
       for (uint32_t it = taps_issued; it < n_iters; ++it) {
         mbar_wait(&empty_bar[slot], par ^ 1u);
@@ -566,7 +583,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
           }
           if (!(last && odd_tail)) kstep(a_st + a_ks16, b_st + b_ks16);
         }
-        if (u.cluster == 1) umma_commit(&empty_bar[slot]);
+        if (cluster == 1) umma_commit(&empty_bar[slot]);
         else umma_commit_multicast(&empty_bar[slot], cluster_mask);
         if (last) umma_commit(&acc_bar);
       }
@@ -611,7 +628,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem, u.tmem_cols);
   // no CTA may leave while a peer can still multicast into it or arrive on its barriers
-  if (u.cluster > 1) cluster_sync_all();
+  if (cluster > 1) cluster_sync_all();
   if (tid == 0 && u.trace) {
     trace_mark(u, 9);
     unsigned long long gt;
@@ -677,6 +694,7 @@ struct UmmaContext {
   UmmaTile *d_tiles = nullptr;
   size_t tiles_cap = 0;
   uint32_t n_tiles = 0;
+  std::vector<UmmaTile> h_tiles;  // host copy of the planned tile table (kernel parameters)
   uint32_t *d_jobs = nullptr;
   size_t jobs_cap = 0;
   unsigned long long *d_trace = nullptr;  // SPXB_UMMA_TRACE=1: timeline of the last launch
@@ -759,8 +777,10 @@ UmmaContext *umma_create(const FilterSpec &spec, const std::vector<float> &ref_t
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaFuncSetAttribute(umma_fir_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(umma_fir_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(umma_fir_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(umma_fir_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(umma_fir_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(umma_fir_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     configured_dev = dev;
   }
   return c;
@@ -900,6 +920,7 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
                               stream)) != cudaSuccess)
     return false;
   c->n_tiles = static_cast<uint32_t>(tiles.size());
+  c->h_tiles = tiles;
   c->memo = true;
   c->m_ls0 = sc.ls0;
   c->m_frac0 = sc.frac0;
@@ -930,6 +951,15 @@ cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, 
   UmmaArgs u;
   u.tiles = c->d_tiles;
   u.n_tiles = c->n_tiles;
+  static const bool inline_tiles = [] {
+    const char *e = getenv("SPXB_UMMA_INLINE_TILES");
+    return !e || atoi(e) != 0;
+  }();
+  u.n_inline = (inline_tiles && c->n_tiles <= kInlineTiles) ? c->n_tiles : 0u;
+  for (uint32_t i = 0; i < kInlineTiles; ++i) {
+    u.inl[i].kf0 = i < u.n_inline ? c->h_tiles[i].kf0 : 0;
+    u.inl[i].slot = i < u.n_inline ? c->h_tiles[i].slot : 0u;
+  }
   u.n_groups = c->grid_groups;
   u.cluster = c->cluster;
   u.pool = c->d_pool;
@@ -983,8 +1013,20 @@ cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, 
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  cudaError_t e = a.channels == 2 ? cudaLaunchKernelEx(&cfg, umma_fir_kernel<2>, a, u)
-                                  : cudaLaunchKernelEx(&cfg, umma_fir_kernel<1>, a, u);
+  static const bool allow_fast = [] {
+    const char *e = getenv("SPXB_UMMA_FAST");
+    return !e || atoi(e) != 0;
+  }();
+  const uintptr_t row_bits = reinterpret_cast<uintptr_t>(a.in) | (a.in_stride * 2u) |
+                             reinterpret_cast<uintptr_t>(a.out) | (a.out_stride * 2u);
+  const bool fast = allow_fast && c->cluster == 1 && (row_bits & 15u) == 0;
+  cudaError_t e;
+  if (a.channels == 2)
+    e = fast ? cudaLaunchKernelEx(&cfg, umma_fir_kernel<2, true>, a, u)
+             : cudaLaunchKernelEx(&cfg, umma_fir_kernel<2, false>, a, u);
+  else
+    e = fast ? cudaLaunchKernelEx(&cfg, umma_fir_kernel<1, true>, a, u)
+             : cudaLaunchKernelEx(&cfg, umma_fir_kernel<1, false>, a, u);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e == cudaSuccess && launches) *launches += 1;
   return e;

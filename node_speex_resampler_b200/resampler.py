@@ -355,3 +355,46 @@ class SpeexResamplerTransform:
     def pipe(self, chunks: Iterable) -> Iterable[bytes]:
         for c in chunks:
             yield self.transform(c)
+
+
+class SpeexResamplerBatchTransform:
+    """Multi-stream counterpart of SpeexResamplerTransform: every written
+    item is a sequence with one chunk per stream (any byte lengths, possibly empty), every
+    result the list of resampled chunks. Each stream keeps its own alignment carry
+    (src/index.ts:139-154 per stream); all streams of a write go to the GPU in one launch
+    through SpeexResampler.processChunks, so stream i's output equals what its own
+    SpeexResamplerTransform would have produced from the same writes."""
+
+    def __init__(self, streams, channels, inRate, outRate, quality=7):
+        self.streams, self.channels = int(streams), channels
+        self.inRate, self.outRate, self.quality = inRate, outRate, quality
+        self.resamplers = [SpeexResampler(channels, inRate, outRate, quality) for _ in range(self.streams)]
+        self._alignementBuffers = [b""] * self.streams
+
+    def _transform(self, chunks, encoding, callback):
+        if len(chunks) != self.streams:
+            callback(ValueError("SpeexResamplerBatchTransform expects one chunk per stream"), None)
+            return
+        frame_bytes = self.channels * 2
+        whole = []
+        for i, c in enumerate(chunks):
+            data = self._alignementBuffers[i] + _chunk_bytes(c)
+            extraneous = len(data) % frame_bytes
+            self._alignementBuffers[i] = data[len(data) - extraneous:] if extraneous else b""
+            whole.append(data[: len(data) - extraneous] if extraneous else data)
+        try:
+            res = SpeexResampler.processChunks(self.resamplers, whole)
+        except Exception as e:
+            callback(e, None)
+            return
+        callback(None, res)
+
+    def transform(self, chunks) -> List[bytes]:
+        box = {}
+
+        def cb(err, res):
+            box["err"], box["res"] = err, res
+        self._transform(chunks, None, cb)
+        if box["err"] is not None:
+            raise box["err"]
+        return box["res"]

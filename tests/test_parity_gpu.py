@@ -15,7 +15,8 @@ import pytest
 
 from cases import GOLDEN_CHUNKS, GOLDEN_STREAMS, MATRIX, case_id
 from node_speex_resampler_b200 import (KERNEL_AUTO, KERNEL_STRICT, KERNEL_TENSOR, KERNEL_TILED, SpeexResampler,
-                                       SpeexResamplerTransform, StreamBatch, _lib, lib, synth_pcm)
+                                       SpeexResamplerBatchTransform, SpeexResamplerTransform, StreamBatch, _lib, lib,
+                                       synth_pcm)
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -261,6 +262,40 @@ def test_transform_stream_like_reference_test(c):
     din = len(data) / i / 2 / ch
     dout = len(got) / o / 2 / ch
     assert abs(din - dout) < 0.01  # the reference's own assertion (src/test.ts:74)
+
+
+def test_batch_transform_equals_per_stream_transforms():
+    """the multi-stream Transform. Every stream gets its own odd-sized writes
+    (alignment carry per stream, src/index.ts:139-154; empty writes included); stream i's bytes
+    must equal what the oracle gives for the same aligned chunks."""
+    ch, i, o, q, S = 2, 44100, 48000, 7, 6
+    t = SpeexResamplerBatchTransform(S, ch, i, o, q)
+    for r in t.resamplers:
+        r.kernel = KERNEL_STRICT
+    refs = [O.OracleResampler(ch, i, o, q) for _ in range(S)]
+    data = [synth_pcm(1, ch, 9000, i, seed=300 + s)[0].tobytes() for s in range(S)]
+    rng = np.random.default_rng(5)
+    pos = [0] * S
+    carry = [b""] * S
+    got = [b""] * S
+    want = [b""] * S
+    for k in range(14):
+        sizes = rng.choice([0, 1, 3, 4, 882 * 4, 4097, 2999], size=S)
+        chunks = []
+        for s in range(S):
+            c = data[s][pos[s]:pos[s] + int(sizes[s])]
+            pos[s] += len(c)
+            chunks.append(c)
+            buf = carry[s] + c
+            extra = len(buf) % (ch * 2)
+            carry[s] = buf[len(buf) - extra:] if extra else b""
+            want[s] += refs[s].processChunk(buf[: len(buf) - extra])
+        res = t.transform(chunks)
+        for s in range(S):
+            got[s] += res[s]
+    assert got == want
+    with pytest.raises(ValueError):
+        t.transform([b""] * (S - 1))
 
 
 def test_edge_lengths_and_capacities():
