@@ -304,6 +304,26 @@ def ours(args):
            "peak_source": "FFMA probe measured in this run (MEASURED_PEAKS.json has no fp32 entry); "
                           "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
            "flops_per_output_sample": 2 * N}
+    # What a launch that only MOVES the algorithmic bytes costs in the same loop: one device copy
+    # kernel (torch copy_) of bytes/2 in + bytes/2 out, K back to back on the same stream. At C3's
+    # 8.6 MB this is dominated by per-launch latency, not by HBM -- the practical floor of a step.
+    copy_floor = None
+    try:
+        half = int(bytes_per_launch // 2) // 16 * 16
+        c_src = torch.empty((8, half), dtype=torch.uint8, device="cuda")
+        c_dst = torch.empty_like(c_src)
+        for timed in (False, True):
+            e0.record()
+            for k in range(K):
+                c_dst[k % 8].copy_(c_src[k % 8], non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+        copy_floor = {"us_per_launch": e0.elapsed_time(e1) * 1e3 / K, "bytes_moved": 2 * half,
+                      "how": f"torch copy_ of {half} B (read + write = the step's algorithmic bytes), "
+                             f"{K} launches back to back, CUDA events"}
+        del c_src, c_dst
+    except Exception as ex:  # noqa: BLE001
+        copy_floor = {"error": str(ex)}
     if kernel_used == "tensor":
         # binding roofline: max(algorithmic bytes / HBM peak, algorithmic flops / tensor peak)
         bf16_peak = float(peaks.get("bf16_tflops", 1590.0)) * 1e12
@@ -320,10 +340,10 @@ def ours(args):
                             "unit": "Tops/s (int8 MMA, incl. band padding and the 6 digit products)",
                             "peak_nominal": 4500.0, "frac_of_nominal": mma_ops / t_launch / 4.5e15,
                             "geometry": geom},
-                    fp32_fma_equivalent=fma)
+                    fp32_fma_equivalent=fma, copy_same_bytes=copy_floor)
     else:
         roof = dict(fma, bound="fp32_fma", traffic=traffic, traffic_source=traffic_src, launch_us=t_launch * 1e6,
-                    hbm=hbm)
+                    hbm=hbm, copy_same_bytes=copy_floor)
 
     # ---- end to end through the C ABI with pinned host buffers ----
     L.spxb_batch_use_own_stream(batch._h)

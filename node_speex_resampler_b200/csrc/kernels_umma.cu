@@ -28,7 +28,9 @@
 //   9    owns TMEM; the whole warp walks the stages, one elected lane issues the MMAs from
 //        uniform registers (four per K step) and releases stages with tcgen05.commit;
 //   10   slides the history (resample.c:898-899) and publishes the new stream position, beside
-//        the FIR.
+//        the FIR, in units of four streams claimed from a counter in shared memory; for long
+//        histories the converter warps claim units too once their last stage is stored (they
+//        would otherwise idle until the accumulator is complete).
 // Stages are handed over with mbarriers (full: 256 converter arrivals + the bulk copy's byte
 // count; empty: tcgen05.commit). Launched with programmatic stream serialization: the next call's
 // grid runs its prologue while this one drains and blocks in griddepcontrol.wait before touching
@@ -172,9 +174,13 @@ __device__ __forceinline__ void combine16(const uint32_t (&p0)[16], const uint32
 // loaded before any store so that 16 loads per lane are in flight.
 template <typename V>
 __device__ __forceinline__ void slide_rows(const CallArgs &a, uint32_t step, uint32_t first, uint32_t n_mine,
-                                           uint32_t hist_elems, size_t shift, int lane) {
+                                           uint32_t hist_elems, size_t shift, int lane, uint32_t *next_unit) {
   constexpr uint32_t VW = sizeof(V) / 2;  // int16 elements per vector
-  for (uint32_t k0 = 0; k0 < n_mine; k0 += 4) {
+  for (;;) {
+    uint32_t k0 = 0;
+    if (lane == 0) k0 = atomicAdd(next_unit, 4u);
+    k0 = __shfl_sync(0xffffffffu, k0, 0);
+    if (k0 >= n_mine) break;
     for (uint32_t e0 = lane * VW; e0 < hist_elems; e0 += 32 * VW * 4) {
       V val[4][4];
 #pragma unroll
@@ -212,7 +218,7 @@ template <int CH, bool FAST>
 __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a, const UmmaArgs u) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], acc_bar;
-  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t tmem_slot, slide_next;
 
   constexpr int kStreams = kUmmaRows / CH;  // streams per series group
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -276,6 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
       mbar_init(&empty_bar[s], cluster);  // every CTA of the cluster is done with the slot
     }
     mbar_init(&acc_bar, 1);
+    slide_next = 0;
     fence_mbar_init();
   }
   // peers multicast into this CTA's stages and arrive on its barriers: all initialised first
@@ -453,6 +460,18 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     if (tid == 0) trace_mark(u, 4);
     if (tid == kConvThreads - 32) trace_mark(u, 30);
 
+    // out of stages to fill: help with the history slide (long histories, 16-byte vectors only)
+    {
+      const uint32_t hist_elems = a.hist_frames * CH;
+      const size_t shift = static_cast<size_t>(sc.consumed) * CH;
+      if (hist_elems >= 512 && shift % 8 == 0 && in_align == 16) {
+        const uint32_t first = g * kStreams + t;
+        const uint32_t in_group = t < static_cast<uint32_t>(kStreams) ? (kStreams - t + u.n_tiles - 1) / u.n_tiles : 0u;
+        const uint32_t in_batch = first < a.n_streams ? (a.n_streams - first + u.n_tiles - 1) / u.n_tiles : 0u;
+        slide_rows<uint4>(a, u.n_tiles, first, min(in_group, in_batch), hist_elems, shift, lane, &slide_next);
+      }
+    }
+
     // ================= epilogue =================
     mbar_wait(&acc_bar, 0);
     tc_fence_after_sync();
@@ -612,10 +631,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     const uint32_t in_group = t < static_cast<uint32_t>(kStreams) ? (kStreams - t + u.n_tiles - 1) / u.n_tiles : 0u;
     const uint32_t in_batch = first < a.n_streams ? (a.n_streams - first + u.n_tiles - 1) / u.n_tiles : 0u;
     const uint32_t n_mine = min(in_group, in_batch);
-    if (vw == 8) slide_rows<uint4>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane);
-    else if (vw == 4) slide_rows<uint2>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane);
-    else if (vw == 2) slide_rows<uint32_t>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane);
-    else slide_rows<uint16_t>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane);
+    if (vw == 8) slide_rows<uint4>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
+    else if (vw == 4) slide_rows<uint2>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
+    else if (vw == 2) slide_rows<uint32_t>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
+    else slide_rows<uint16_t>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
     for (uint32_t k = lane; k < n_mine; k += 32) {
       const size_t s = first + static_cast<size_t>(k) * u.n_tiles;
       a.last_sample[s] = sc.ls1;
