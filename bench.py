@@ -304,9 +304,9 @@ def ours(args):
            "peak_source": "FFMA probe measured in this run (MEASURED_PEAKS.json has no fp32 entry); "
                           "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
            "flops_per_output_sample": 2 * N}
-    # What a launch that only MOVES the algorithmic bytes costs in the same loop: one device copy
-    # kernel (torch copy_) of bytes/2 in + bytes/2 out, K back to back on the same stream. At C3's
-    # 8.6 MB this is dominated by per-launch latency, not by HBM -- the practical floor of a step.
+    # What a launch that only MOVES the algorithmic bytes costs in the same loop: torch's device copy
+    # kernel over bytes/2 in + bytes/2 out, K back to back on the same stream. At C3's 8.6 MB this
+    # is dominated by per-launch latency, not by HBM -- a practical floor for one step.
     copy_floor = None
     try:
         half = int(bytes_per_launch // 2) // 16 * 16
@@ -319,8 +319,9 @@ def ours(args):
             e1.record()
             torch.cuda.synchronize()
         copy_floor = {"us_per_launch": e0.elapsed_time(e1) * 1e3 / K, "bytes_moved": 2 * half,
-                      "how": f"torch copy_ of {half} B (read + write = the step's algorithmic bytes), "
-                             f"{K} launches back to back, CUDA events"}
+                      "how": f"torch copy_ (at::direct_copy_kernel) of {half} B device to device -- read + write "
+                             f"= the step's algorithmic bytes -- {K} launches back to back on the stream, CUDA "
+                             "events; includes per-launch latency, like the kernel's own number"}
         del c_src, c_dst
     except Exception as ex:  # noqa: BLE001
         copy_floor = {"error": str(ex)}
@@ -340,10 +341,10 @@ def ours(args):
                             "unit": "Tops/s (int8 MMA, incl. band padding and the 6 digit products)",
                             "peak_nominal": 4500.0, "frac_of_nominal": mma_ops / t_launch / 4.5e15,
                             "geometry": geom},
-                    fp32_fma_equivalent=fma, copy_same_bytes=copy_floor)
+                    fp32_fma_equivalent=fma, d2d_memcpy_same_bytes=copy_floor)
     else:
         roof = dict(fma, bound="fp32_fma", traffic=traffic, traffic_source=traffic_src, launch_us=t_launch * 1e6,
-                    hbm=hbm, copy_same_bytes=copy_floor)
+                    hbm=hbm, d2d_memcpy_same_bytes=copy_floor)
 
     # ---- end to end through the C ABI with pinned host buffers ----
     L.spxb_batch_use_own_stream(batch._h)
@@ -358,25 +359,33 @@ def ours(args):
     nout = np.empty(S, np.uint32)
     depth = L.spxb_batch_pipeline_depth(batch._h)
 
+    host_t = {"submit": 0.0, "wait": 0.0}
+
     def e2e_steps(count):
         tickets = []
+        nin_p, nout_p = nin.ctypes.data, nout.ctypes.data
         for k in range(count):
+            ta = time.perf_counter()
             nin.fill(n)
             nout.fill(cap)
             t = C.c_uint64(0)
-            e = L.spxb_batch_submit(batch._h, hin[k % hr], n, nin.ctypes.data, hout[k % hr], cap,
-                                    nout.ctypes.data, C.byref(t))
+            e = L.spxb_batch_submit(batch._h, hin[k % hr], n, nin_p, hout[k % hr], cap, nout_p, C.byref(t))
             if e:
                 raise RuntimeError(_lib.strerror(e) + ": " + _lib.last_error())
             tickets.append(t.value)
+            tb = time.perf_counter()
             if k >= depth:
                 L.spxb_batch_wait(batch._h, tickets[k - depth])
+            tc = time.perf_counter()
+            host_t["submit"] += tb - ta
+            host_t["wait"] += tc - tb
         for t in tickets[-depth:]:
             L.spxb_batch_wait(batch._h, t)
 
     Ke = max(K, 20)
     e2e_steps(max(W, 3))
     batch.synchronize()
+    host_t["submit"] = host_t["wait"] = 0.0
     barrier()
     e0.record()
     tw0 = time.perf_counter()
@@ -395,8 +404,10 @@ def ours(args):
     # memory with nothing else running (PCIe Gen5 x16 on this box), no kernel in between
     pcie = None
     try:
-        h_i = torch.empty(in_bytes, dtype=torch.uint8).pin_memory()
-        h_o = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+        # same number of distinct pinned host buffers as the e2e loop rotates over (a single
+        # re-used buffer stays in the host's last-level cache and overstates the ceiling)
+        h_i = [torch.empty(in_bytes, dtype=torch.uint8).pin_memory() for _ in range(hr)]
+        h_o = [torch.empty(out_bytes, dtype=torch.uint8).pin_memory() for _ in range(hr)]
         d_i = torch.empty(in_bytes, dtype=torch.uint8, device="cuda")
         d_o = torch.empty(out_bytes, dtype=torch.uint8, device="cuda")
         s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
@@ -404,16 +415,16 @@ def ours(args):
         for timed in (False, True):
             torch.cuda.synchronize()
             tp0 = time.perf_counter()
-            for _ in range(nrep):
+            for k in range(nrep):
                 with torch.cuda.stream(s_a):
-                    d_i.copy_(h_i, non_blocking=True)
+                    d_i.copy_(h_i[k % hr], non_blocking=True)
                 with torch.cuda.stream(s_b):
-                    h_o.copy_(d_o, non_blocking=True)
+                    h_o[k % hr].copy_(d_o, non_blocking=True)
             torch.cuda.synchronize()
             tp1 = time.perf_counter()
         per_step = (tp1 - tp0) / nrep
         pcie = {"copy_only_us_per_step": per_step * 1e6, "h2d_GBs": in_bytes / per_step / 1e9,
-                "d2h_GBs": out_bytes / per_step / 1e9,
+                "d2h_GBs": out_bytes / per_step / 1e9, "host_buffers": hr,
                 "ceiling_msamples_per_sec": out_samples_step * world / per_step / 1e6,
                 "e2e_frac_of_ceiling": (e2e_value / (out_samples_step * world / per_step))}
         del h_i, h_o, d_i, d_o
@@ -447,6 +458,7 @@ def ours(args):
                 "e2e": {"value": e2e_value / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": in_bytes,
                         "d2h_bytes_per_step": out_bytes, "steps": Ke, "pipeline_depth": depth,
                         "how": "spxb_batch_submit/wait (C ABI), pinned host buffers, H2D+kernel+D2H per step",
+                        "host_us_per_step": {"submit": host_t["submit"] / Ke * 1e6, "wait": host_t["wait"] / Ke * 1e6},
                         "pcie": pcie},
                 "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

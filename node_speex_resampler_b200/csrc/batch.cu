@@ -486,6 +486,14 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
                                           : round_up(static_cast<size_t>(d.max_n_out) * ch, 8);
   if (int e = grow_device(&sl.d_in, &sl.d_in_cap, std::max<size_t>(dev_in_stride * S, 8))) return e;
   if (int e = grow_device(&sl.d_out, &sl.d_out_cap, std::max<size_t>(dev_out_stride * S, 8))) return e;
+  // size the idle slots alike now, so that no cudaMalloc (a device-wide sync) lands in the middle
+  // of a pipelined run the first time each slot comes up
+  for (int k = 0; k < pipeline_slots(); ++k) {
+    Slot &o = b->slots[k];
+    if (&o == &sl || o.busy) continue;
+    if (int e = grow_device(&o.d_in, &o.d_in_cap, std::max<size_t>(dev_in_stride * S, 8))) return e;
+    if (int e = grow_device(&o.d_out, &o.d_out_cap, std::max<size_t>(dev_out_stride * S, 8))) return e;
+  }
 
   sl.ticket = b->next_ticket++;
   if (ticket) *ticket = sl.ticket;
