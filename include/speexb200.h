@@ -77,6 +77,14 @@ SPXB_API void speex_resampler_get_ratio(SpeexResamplerState *st, uint32_t *ratio
 SPXB_API void speex_resampler_get_quality(SpeexResamplerState *st, int *quality); /* :1165 */
 SPXB_API int speex_resampler_get_input_latency(SpeexResamplerState *st);  /* resample.c:1190 */
 SPXB_API int speex_resampler_get_output_latency(SpeexResamplerState *st); /* resample.c:1195 */
+/* replaces resample.c:1038 of the float build (speex_resampler.h:189-207): float samples in,
+ * the kernels' f32 results out -- no scaling, rounding or saturation -- bit-identical to the
+ * reference's float entry. The first float call moves the state's history to f32 (exactly);
+ * int16 and float calls may then be mixed freely, as with the reference, but the state runs
+ * on the bit-exact strict kernel from then on. */
+SPXB_API int speex_resampler_process_interleaved_float(SpeexResamplerState *st, const float *in,
+                                                       uint32_t *in_len, float *out,
+                                                       uint32_t *out_len);
 SPXB_API int speex_resampler_skip_zeros(SpeexResamplerState *st);         /* resample.c:1200 */
 SPXB_API int speex_resampler_reset_mem(SpeexResamplerState *st);          /* resample.c:1208 */
 
@@ -108,6 +116,12 @@ SPXB_API const char *spxb_last_error(void);
 SPXB_API spxb_batch *spxb_batch_create(uint32_t n_streams, uint32_t channels,
                                        uint32_t in_rate, uint32_t out_rate, int quality,
                                        int device, int *err);
+/* Same, with the history kept as f32 (what the reference's `mem` is): serves float in/out
+ * (spxb_batch_process_f32) and int16 in/out on one state, bit-exactly, on the strict kernel. */
+SPXB_API spxb_batch *spxb_batch_create_f32(uint32_t n_streams, uint32_t channels,
+                                           uint32_t in_rate, uint32_t out_rate, int quality,
+                                           int device, int *err);
+SPXB_API int spxb_batch_is_f32(const spxb_batch *b);
 SPXB_API void spxb_batch_destroy(spxb_batch *b);
 SPXB_API int spxb_batch_set_kernel(spxb_batch *b, int kernel); /* SPXB_KERNEL_* */
 SPXB_API int spxb_batch_get_kernel(const spxb_batch *b);       /* family used by last call */
@@ -128,6 +142,13 @@ SPXB_API long spxb_batch_tensor_trace(spxb_batch *b, uint64_t *dst, size_t cap_w
 SPXB_API int spxb_batch_process(spxb_batch *b, const int16_t *in, size_t in_stride_frames,
                                 uint32_t *in_frames, int16_t *out,
                                 size_t out_stride_frames, uint32_t *out_frames);
+
+/* speex_resampler_process_interleaved_float for every stream of a float batch: HOST float
+ * buffers, strides and lengths in frames as above. Lengths follow the float entry's block walk
+ * (resample.c:927-963: no 1024-frame output block). Synchronous. */
+SPXB_API int spxb_batch_process_f32(spxb_batch *b, const float *in, size_t in_stride_frames,
+                                    uint32_t *in_frames, float *out, size_t out_stride_frames,
+                                    uint32_t *out_frames);
 
 /* Same, split for pipelining host<->device copies against the kernel: submit() stages
  * H2D + kernel + D2H on the batch's streams and returns a ticket at once (in_frames /
@@ -182,6 +203,13 @@ SPXB_API int spxb_batch_get_state(spxb_batch *b, uint32_t stream, int32_t *last_
                                   int16_t *history);
 SPXB_API int spxb_batch_set_state(spxb_batch *b, uint32_t stream, int32_t last_sample,
                                   uint32_t samp_frac_num, const int16_t *history);
+/* float view of the history, for both kinds of batch (set on an int16 batch requires
+ * int16-valued samples) */
+SPXB_API int spxb_batch_get_state_f32(spxb_batch *b, uint32_t stream, int32_t *last_sample,
+                                      uint32_t *samp_frac_num, uint32_t *magic_samples,
+                                      float *history);
+SPXB_API int spxb_batch_set_state_f32(spxb_batch *b, uint32_t stream, int32_t last_sample,
+                                      uint32_t samp_frac_num, const float *history);
 SPXB_API int spxb_batch_reset(spxb_batch *b);      /* resample.c:1208 for every stream */
 SPXB_API int spxb_batch_skip_zeros(spxb_batch *b); /* resample.c:1200 for every stream */
 
@@ -250,6 +278,11 @@ typedef struct {
 SPXB_API int spxb_plan_call(uint32_t in_rate, uint32_t out_rate, int32_t last_sample,
                             uint32_t samp_frac_num, uint32_t n_in, uint32_t out_cap,
                             spxb_call_plan *plan);
+
+/* the same for the float entry, whose output block is unbounded (resample.c:944) */
+SPXB_API int spxb_plan_call_f32(uint32_t in_rate, uint32_t out_rate, int32_t last_sample,
+                                uint32_t samp_frac_num, uint32_t n_in, uint32_t out_cap,
+                                spxb_call_plan *plan);
 
 SPXB_API const char *spxb_version(void);
 

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/speexb200.h"
@@ -65,6 +66,7 @@ struct Slot {
   cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_done = nullptr;
   bool busy = false;
   uint64_t ticket = 0;
+  uint32_t io_words = 1;  // int16 units per sample of the call in flight (2: float in/out)
   // deferred copy-out (pageable or ragged output)
   bool bounce_out = false;
   int16_t *user_out = nullptr;
@@ -83,6 +85,13 @@ struct spxb_batch {
   int sm_count = 148;
   FilterSpec spec;
   uint32_t n_streams = 0, channels = 0;
+  // Sample format. A float batch (spxb_batch_create_f32) keeps its history as f32 -- what the
+  // reference's `mem` is -- and serves float in/out (io_words == 2 during such a call) as well as
+  // int16 in/out, bit-exactly, on the strict kernel. Buffers and strides stay in int16 units; a
+  // float sample occupies two of them.
+  bool f32 = false;
+  uint32_t hist_words = 1;  // int16 units per history sample
+  uint32_t io_words = 1;    // int16 units per in/out sample of the call being issued
   // filter bank in HBM
   float *d_table = nullptr, *d_taps = nullptr, *d_blend = nullptr, *d_band = nullptr;
   uint32_t band_kp = 0, band_pad = 0, band_row = 0;
@@ -106,10 +115,22 @@ struct spxb_batch {
   int kernel_pref = SPXB_KERNEL_AUTO;
   int last_kernel = SPXB_KERNEL_AUTO;
   spxb_counters counters{};
+  // CUDA graphs of hop sequences (spxb_batch_process_device_ring): key -> instantiated graph.
+  // `seen` remembers, per key, how many stream operations / allocations the planner needed the
+  // last time the sequence ran launch by launch (only sequences that needed none are captured).
+  struct RingGraph {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t last_use = 0;
+  };
+  std::unordered_map<std::string, RingGraph> ring_graphs;
+  std::unordered_map<std::string, uint64_t> ring_seen;
+  uint64_t ring_clock = 0;
+  bool dry_run = false;  // plan and advance the host-side state, launch nothing (graph replay)
+  bool defer_pos_mirror = false;  // uniform hops update pos[0] only; mirrored at the end of the sequence
   // memo of the last uniform plan
   bool memo_valid = false;
   StreamPos memo_pos;
-  uint32_t memo_n_in = 0, memo_cap = 0;
+  uint32_t memo_n_in = 0, memo_cap = 0, memo_out_block = 0;
   CallPlan memo_plan;
 };
 
@@ -129,11 +150,14 @@ struct DeviceGuard {
 };
 
 static CallPlan plan_memo(spxb_batch *b, StreamPos p, uint32_t n_in, uint32_t cap) {
+  // the float entry has no 1024-sample output block (resample.c:944)
+  const uint32_t out_block = b->io_words == 2 ? kOutBlockUnbounded : kOutBlock;
   if (b->memo_valid && b->memo_pos.last_sample == p.last_sample &&
       b->memo_pos.samp_frac_num == p.samp_frac_num && b->memo_n_in == n_in &&
-      b->memo_cap == cap)
+      b->memo_cap == cap && b->memo_out_block == out_block)
     return b->memo_plan;
-  CallPlan pl = plan_call(b->spec.num, b->spec.den, p, n_in, cap);
+  CallPlan pl = plan_call(b->spec.num, b->spec.den, p, n_in, cap, out_block);
+  b->memo_out_block = out_block;
   b->memo_valid = true;
   b->memo_pos = p;
   b->memo_n_in = n_in;
@@ -192,7 +216,7 @@ static int retire_slot(spxb_batch *b, Slot &sl) {
   if (!sl.busy) return 0;
   SPXB_CUDA(cudaEventSynchronize(sl.ev_done));
   if (sl.bounce_out && sl.user_out) {
-    const size_t ch = b->channels;
+    const size_t ch = static_cast<size_t>(b->channels) * sl.io_words;
     if (sl.out_counts.empty()) {
       const size_t row = static_cast<size_t>(sl.uniform_out) * ch;
       for (uint32_t s = 0; s < b->n_streams; ++s)
@@ -244,16 +268,19 @@ static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elem
   a.per_stream = d_calls;
   a.uniform = uniform;
   a.max_n_out = max_n_out;
+  a.fmt = !b->f32 ? 0u : (b->io_words == 2 ? 2u : 1u);
 
   uint32_t launches = 0;
   cudaError_t ce = cudaSuccess;
   int used = SPXB_KERNEL_STRICT;
   TiledConfig cfg;
   const int pref = b->kernel_pref;
-  const bool want_tensor = pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TENSOR;
-  const bool want_tiled = pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TILED;
+  // float batches run the strict kernel only (the fast families are built around int16 history)
+  const bool want_tensor = !b->f32 && (pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TENSOR);
+  const bool want_tiled = !b->f32 && (pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TILED);
   if (want_tensor && max_n_out != 0 && umma_prepare(b->umma, a, b->s_compute, &ce)) {
-    ce = launch_umma(b->umma, a, b->s_compute, &launches);
+    if (b->dry_run) launches += 1;
+    else ce = launch_umma(b->umma, a, b->s_compute, &launches);
     used = SPXB_KERNEL_TENSOR;
   } else if (ce != cudaSuccess) {
     // planning failed on a CUDA error (not merely "not covered")
@@ -261,13 +288,15 @@ static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elem
     set_error("SPXB_KERNEL_TENSOR requested but this call does not qualify for the tensor kernel");
     return RESAMPLER_ERR_BAD_STATE;
   } else if (want_tiled && b->d_band && tiled_qualifies(a, b->sm_count, &cfg)) {
-    ce = launch_tiled(a, cfg, b->s_compute, &launches);
+    if (b->dry_run) launches += 1;
+    else ce = launch_tiled(a, cfg, b->s_compute, &launches);
     used = SPXB_KERNEL_TILED;
   } else if (pref == SPXB_KERNEL_TILED && max_n_out != 0) {
     set_error("SPXB_KERNEL_TILED requested but this call does not qualify for the tiled kernel");
     return RESAMPLER_ERR_BAD_STATE;
   } else {
-    ce = launch_strict(a, b->s_compute, &launches);
+    if (b->dry_run) launches += 1;
+    else ce = launch_strict(a, b->s_compute, &launches);
   }
   if (ce != cudaSuccess) {
     set_error(std::string("kernel launch: ") + cudaGetErrorString(ce));
@@ -297,8 +326,10 @@ static Decided decide_uniform(spxb_batch *b, uint32_t n_in, uint32_t cap) {
   d.max_n_out = pl.n_out;
   d.any_work = n_in != 0 && cap != 0;
   if (d.any_work) {
-    // all shadows advance together; keep only pos[0] exact and mirror lazily
-    for (auto &q : b->pos) q = pl.next;
+    // all shadows advance together; inside a hop sequence only pos[0] is kept exact and the
+    // rest are mirrored once at its end (ring_hops)
+    if (b->defer_pos_mirror) b->pos[0] = pl.next;
+    else for (auto &q : b->pos) q = pl.next;
   }
   return d;
 }
@@ -355,6 +386,8 @@ static void free_batch(spxb_batch *b) {
     if (sl.ev_kernel) cudaEventDestroy(sl.ev_kernel);
     if (sl.ev_done) cudaEventDestroy(sl.ev_done);
   }
+  for (auto &kv : b->ring_graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (b->ev_state) cudaEventDestroy(b->ev_state);
   if (b->d_table) cudaFree(b->d_table);
   if (b->d_taps) cudaFree(b->d_taps);
@@ -403,7 +436,7 @@ static int create_batch(spxb_batch *b) {
   // per-phase taps only while the den*N table stays modest (64 MiB); beyond that the strict
   // kernel (which needs only the oversampled prototype) serves the batch
   const uint64_t phase_floats = static_cast<uint64_t>(sp.den) * sp.taps;
-  if (phase_floats * sizeof(float) <= (64ull << 20)) {
+  if (!b->f32 && phase_floats * sizeof(float) <= (64ull << 20)) {
     std::vector<float> taps = build_phase_taps(sp, table);
     SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->d_taps), taps.size() * sizeof(float)));
     SPXB_CUDA(cudaMemcpy(b->d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -418,7 +451,7 @@ static int create_batch(spxb_batch *b) {
     }
   }
   // tensor kernel: fixed-point taps + tap-tile pool (nullptr when the filter is not covered)
-  b->umma = umma_create(sp, table, b->channels, b->sm_count);
+  if (!b->f32) b->umma = umma_create(sp, table, b->channels, b->sm_count);
   if (!sp.direct) {
     std::vector<float> blend(static_cast<size_t>(sp.den) * 4);
     for (uint32_t ph = 0; ph < sp.den; ++ph) {
@@ -431,7 +464,8 @@ static int create_batch(spxb_batch *b) {
 
   // stream state, zeroed: resample.c:721-725 and the calloc'd per-channel arrays :838-843
   b->hist_frames = static_cast<uint32_t>(round_up(sp.taps - 1, 16));  // 16-frame K chunks (tensor kernel)
-  b->hist_stride = static_cast<uint32_t>(round_up(static_cast<size_t>(b->hist_frames) * b->channels, 8));
+  b->hist_stride = static_cast<uint32_t>(
+      round_up(static_cast<size_t>(b->hist_frames) * b->channels * b->hist_words, 8));
   const size_t hist_bytes = static_cast<size_t>(b->n_streams) * b->hist_stride * sizeof(int16_t);
   for (int i = 0; i < 2; ++i) {
     SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->d_hist[i]), std::max<size_t>(hist_bytes, 16)));
@@ -456,9 +490,10 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
                        uint64_t *ticket) {
   DeviceGuard g(b->device);
   const uint32_t S = b->n_streams;
-  const size_t ch = b->channels;
+  const size_t ch = static_cast<size_t>(b->channels) * b->io_words;  // int16 units per frame
   Slot &sl = b->slots[b->next_ticket % pipeline_slots()];
   if (int e = retire_slot(b, sl)) return e;
+  sl.io_words = b->io_words;
 
   // remember the offered lengths: decide() overwrites the arrays with consumed / written
   const bool offered_uniform = [&] {
@@ -590,8 +625,23 @@ const char *spxb_last_error(void) { return g_last_error.c_str(); }
 
 const char *spxb_version(void) { return "speexb200 0.1 (sm_100a)"; }
 
+static spxb_batch *create_any(uint32_t n_streams, uint32_t channels, uint32_t in_rate, uint32_t out_rate,
+                              int quality, int device, bool f32, int *err);
+
 spxb_batch *spxb_batch_create(uint32_t n_streams, uint32_t channels, uint32_t in_rate,
                               uint32_t out_rate, int quality, int device, int *err) {
+  return create_any(n_streams, channels, in_rate, out_rate, quality, device, false, err);
+}
+
+spxb_batch *spxb_batch_create_f32(uint32_t n_streams, uint32_t channels, uint32_t in_rate,
+                                  uint32_t out_rate, int quality, int device, int *err) {
+  return create_any(n_streams, channels, in_rate, out_rate, quality, device, true, err);
+}
+
+int spxb_batch_is_f32(const spxb_batch *b) { return b && b->f32 ? 1 : 0; }
+
+static spxb_batch *create_any(uint32_t n_streams, uint32_t channels, uint32_t in_rate, uint32_t out_rate,
+                              int quality, int device, bool f32, int *err) {
   int e = RESAMPLER_ERR_SUCCESS;
   spxb_batch *b = nullptr;
   FilterSpec spec;
@@ -615,6 +665,8 @@ spxb_batch *spxb_batch_create(uint32_t n_streams, uint32_t channels, uint32_t in
       b->spec = spec;
       b->n_streams = n_streams;
       b->channels = channels;
+      b->f32 = f32;
+      b->hist_words = f32 ? 2 : 1;
       int prev = -1;
       cudaGetDevice(&prev);
       e = create_batch(b);
@@ -677,6 +729,25 @@ int spxb_batch_process(spxb_batch *b, const int16_t *in, size_t in_stride_frames
   return spxb_batch_wait(b, t);
 }
 
+// Float in/out (speex_resampler_process_interleaved_float for every stream): same staging and
+// pipeline as the int16 entry with two int16 units per sample; lengths follow the float entry's
+// block walk (no 1024-frame output block).
+int spxb_batch_process_f32(spxb_batch *b, const float *in, size_t in_stride_frames, uint32_t *in_frames,
+                           float *out, size_t out_stride_frames, uint32_t *out_frames) {
+  if (!b) return RESAMPLER_ERR_INVALID_ARG;
+  if (!b->f32) {
+    set_error("spxb_batch_process_f32 needs a batch made by spxb_batch_create_f32 (float history)");
+    return RESAMPLER_ERR_BAD_STATE;
+  }
+  b->io_words = 2;
+  uint64_t t = 0;
+  int e = submit_host(b, reinterpret_cast<const int16_t *>(in), in_stride_frames, in_frames,
+                      reinterpret_cast<int16_t *>(out), out_stride_frames, out_frames, &t);
+  b->io_words = 1;
+  if (e) return e;
+  return spxb_batch_wait(b, t);
+}
+
 int spxb_batch_process_device(spxb_batch *b, const int16_t *d_in, size_t in_stride_frames,
                               uint32_t *in_frames, int16_t *d_out, size_t out_stride_frames,
                               uint32_t *out_frames) {
@@ -698,7 +769,8 @@ int spxb_batch_process_device(spxb_batch *b, const int16_t *d_in, size_t in_stri
     b->counters.h2d_bytes += S * sizeof(StreamCall);
     sl.busy = true;  // h_calls must outlive the async copy
   }
-  int e = launch_call(b, d_in, in_stride_frames * b->channels, d_out, out_stride_frames * b->channels,
+  int e = launch_call(b, d_in, in_stride_frames * b->channels * b->io_words, d_out,
+                      out_stride_frames * b->channels * b->io_words,
                       d.uniform ? nullptr : sl.d_calls, d.uni, d.max_n_out);
   if (e) return e;
   if (!d.uniform) SPXB_CUDA(cudaEventRecord(sl.ev_done, b->s_compute));
@@ -719,11 +791,41 @@ int spxb_batch_process_device_uniform(spxb_batch *b, const int16_t *d_in, size_t
   if (in_used) *in_used = d.uni.consumed;
   if (out_written) *out_written = d.uni.n_out;
   if (!d.any_work) return 0;
-  int e = launch_call(b, d_in, in_stride_frames * b->channels, d_out, out_stride_frames * b->channels,
+  int e = launch_call(b, d_in, in_stride_frames * b->channels * b->io_words, d_out,
+                      out_stride_frames * b->channels * b->io_words,
                       nullptr, d.uni, d.max_n_out);
   if (e) return e;
   b->counters.calls += 1;
   return 0;
+}
+
+// Hop sequences are launch-bound at small shapes (C3: 7.5 us per 20 ms hop, a third of it launch
+// latency), so a sequence that repeats -- same buffers, same ring phase, same stream position --
+// is captured into a CUDA graph the second time it is seen unchanged and replayed from then on.
+// The host-side planning (lengths, positions, ping-pong) still runs per hop, in dry-run mode, so
+// the batch's state after a replay is by construction what the launches would have left.
+static bool ring_graphs_enabled() {
+  static const bool v = [] {
+    const char *e = getenv("SPXB_RING_GRAPH");
+    return !e || atoi(e) != 0;
+  }();
+  return v;
+}
+
+static int ring_hops(spxb_batch *b, const int16_t *d_in, size_t in_stride_frames, size_t in_slot_elems,
+                     int16_t *d_out, size_t out_stride_frames, size_t out_slot_elems, uint32_t ring,
+                     uint32_t n_in, uint32_t out_cap, uint32_t first_step, uint32_t steps) {
+  int e = 0;
+  b->defer_pos_mirror = true;
+  for (uint32_t k = first_step; k < first_step + steps && !e; ++k) {
+    const size_t slot = k % ring;
+    e = spxb_batch_process_device_uniform(b, d_in + slot * in_slot_elems, in_stride_frames, n_in,
+                                          d_out + slot * out_slot_elems, out_stride_frames, out_cap, nullptr,
+                                          nullptr);
+  }
+  b->defer_pos_mirror = false;
+  for (auto &q : b->pos) q = b->pos[0];
+  return e;
 }
 
 int spxb_batch_process_device_ring(spxb_batch *b, const int16_t *d_in, size_t in_stride_frames,
@@ -731,13 +833,99 @@ int spxb_batch_process_device_ring(spxb_batch *b, const int16_t *d_in, size_t in
                                    size_t out_slot_elems, uint32_t ring, uint32_t n_in, uint32_t out_cap,
                                    uint32_t first_step, uint32_t steps) {
   if (!b || ring == 0) return RESAMPLER_ERR_INVALID_ARG;
-  for (uint32_t k = first_step; k < first_step + steps; ++k) {
-    const size_t slot = k % ring;
-    int e = spxb_batch_process_device_uniform(b, d_in + slot * in_slot_elems, in_stride_frames, n_in,
-                                              d_out + slot * out_slot_elems, out_stride_frames, out_cap,
-                                              nullptr, nullptr);
-    if (e) return e;
+  auto plain = [&] {
+    return ring_hops(b, d_in, in_stride_frames, in_slot_elems, d_out, out_stride_frames, out_slot_elems, ring,
+                     n_in, out_cap, first_step, steps);
+  };
+  // (the legacy default stream cannot be captured)
+  if (!ring_graphs_enabled() || steps < 4 || !b->uniform_pos || b->s_compute == nullptr) return plain();
+
+  // everything the captured launches depend on
+  struct Key {
+    const void *in, *out;
+    size_t in_stride, in_slot, out_stride, out_slot;
+    uint32_t ring, n_in, out_cap, phase, steps;
+    int32_t ls;
+    uint32_t frac;
+    int hist_cur, kernel_pref;
+    uint64_t pool_generation;
+    void *stream;
+  } key;
+  std::memset(&key, 0, sizeof(key));
+  key.in = d_in;
+  key.out = d_out;
+  key.in_stride = in_stride_frames;
+  key.in_slot = in_slot_elems;
+  key.out_stride = out_stride_frames;
+  key.out_slot = out_slot_elems;
+  key.ring = ring;
+  key.n_in = n_in;
+  key.out_cap = out_cap;
+  key.phase = first_step % ring;
+  key.steps = steps;
+  key.ls = b->pos[0].last_sample;
+  key.frac = b->pos[0].samp_frac_num;
+  key.hist_cur = b->hist_cur;
+  key.kernel_pref = b->kernel_pref;
+  key.pool_generation = umma_pool_generation(b->umma);
+  key.stream = b->s_compute;
+  const std::string k(reinterpret_cast<const char *>(&key), sizeof(key));
+  DeviceGuard g(b->device);
+
+  auto hit = b->ring_graphs.find(k);
+  if (hit != b->ring_graphs.end()) {
+    // the GPU starts at once; the host-side bookkeeping of the hops runs beside it
+    hit->second.last_use = ++b->ring_clock;
+    SPXB_CUDA(cudaGraphLaunch(hit->second.exec, b->s_compute));
+    b->dry_run = true;
+    const int e = plain();
+    b->dry_run = false;
+    return e;
   }
+
+  auto seen = b->ring_seen.find(k);
+  const bool capture = seen != b->ring_seen.end() && seen->second == 0;
+  if (!capture) {
+    // launch by launch, remembering whether the planner had to touch the stream on the way
+    const uint64_t ops0 = umma_stream_ops(b->umma);
+    const int e = plain();
+    if (b->ring_seen.size() > 4096) b->ring_seen.clear();
+    b->ring_seen[k] = umma_stream_ops(b->umma) - ops0;
+    return e;
+  }
+
+  // second unchanged sighting: capture the launches (they still execute: the graph is launched below)
+  cudaGraph_t graph = nullptr;
+  SPXB_CUDA(cudaStreamBeginCapture(b->s_compute, cudaStreamCaptureModeThreadLocal));
+  umma_set_frozen(b->umma, true);
+  const int e = plain();
+  umma_set_frozen(b->umma, false);
+  const cudaError_t ce = cudaStreamEndCapture(b->s_compute, &graph);
+  if (e || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (!e) set_error(std::string("ring graph capture: ") + cudaGetErrorString(ce));
+    return e ? e : RESAMPLER_ERR_BAD_STATE;
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ci = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ci != cudaSuccess || !exec) {
+    set_error(std::string("ring graph instantiate: ") + cudaGetErrorString(ci));
+    return RESAMPLER_ERR_BAD_STATE;
+  }
+  if (b->ring_graphs.size() >= 64) {  // evict the least recently used
+    auto victim = b->ring_graphs.begin();
+    for (auto it = b->ring_graphs.begin(); it != b->ring_graphs.end(); ++it)
+      if (it->second.last_use < victim->second.last_use) victim = it;
+    cudaGraphExecDestroy(victim->second.exec);
+    b->ring_graphs.erase(victim);
+  }
+  spxb_batch::RingGraph rg;
+  rg.exec = exec;
+  rg.last_use = ++b->ring_clock;
+  b->ring_graphs.emplace(k, rg);
+  SPXB_CUDA(cudaGraphLaunch(exec, b->s_compute));
   return 0;
 }
 
@@ -773,6 +961,10 @@ int spxb_batch_synchronize(spxb_batch *b) {
 int spxb_batch_get_state(spxb_batch *b, uint32_t stream, int32_t *last_sample, uint32_t *samp_frac_num,
                          uint32_t *magic_samples, int16_t *history) {
   if (!b || stream >= b->n_streams) return RESAMPLER_ERR_INVALID_ARG;
+  if (b->f32 && history) {
+    set_error("this batch keeps a float history: use spxb_batch_get_state_f32");
+    return RESAMPLER_ERR_INVALID_ARG;
+  }
   if (int e = spxb_batch_synchronize(b)) return e;
   DeviceGuard g(b->device);
   if (last_sample)
@@ -795,6 +987,10 @@ int spxb_batch_set_state(spxb_batch *b, uint32_t stream, int32_t last_sample, ui
                          const int16_t *history) {
   if (!b || stream >= b->n_streams || last_sample < 0 || samp_frac_num >= b->spec.den)
     return RESAMPLER_ERR_INVALID_ARG;
+  if (b->f32 && history) {
+    set_error("this batch keeps a float history: use spxb_batch_set_state_f32");
+    return RESAMPLER_ERR_INVALID_ARG;
+  }
   if (int e = spxb_batch_synchronize(b)) return e;
   DeviceGuard g(b->device);
   SPXB_CUDA(cudaMemcpy(b->d_last_sample + stream, &last_sample, sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -812,6 +1008,57 @@ int spxb_batch_set_state(spxb_batch *b, uint32_t stream, int32_t last_sample, ui
   for (uint32_t s = 1; s < b->n_streams && b->uniform_pos; ++s)
     b->uniform_pos = b->pos[s].last_sample == b->pos[0].last_sample &&
                      b->pos[s].samp_frac_num == b->pos[0].samp_frac_num;
+  return 0;
+}
+
+// Float view of a stream's state, for both kinds of batch (an int16 history converts exactly).
+int spxb_batch_get_state_f32(spxb_batch *b, uint32_t stream, int32_t *last_sample, uint32_t *samp_frac_num,
+                             uint32_t *magic_samples, float *history) {
+  if (!b || stream >= b->n_streams) return RESAMPLER_ERR_INVALID_ARG;
+  const size_t live = static_cast<size_t>(b->spec.taps - 1) * b->channels;
+  if (!b->f32) {
+    std::vector<int16_t> h(live ? live : 1);
+    if (int e = spxb_batch_get_state(b, stream, last_sample, samp_frac_num, magic_samples, history ? h.data() : nullptr))
+      return e;
+    if (history)
+      for (size_t i = 0; i < live; ++i) history[i] = static_cast<float>(h[i]);
+    return 0;
+  }
+  if (int e = spxb_batch_get_state(b, stream, last_sample, samp_frac_num, magic_samples, nullptr)) return e;
+  if (history && live) {
+    DeviceGuard g(b->device);
+    const size_t lead = static_cast<size_t>(b->hist_frames - (b->spec.taps - 1)) * b->channels;
+    const float *row = reinterpret_cast<const float *>(b->d_hist[b->hist_cur] + static_cast<size_t>(stream) * b->hist_stride);
+    SPXB_CUDA(cudaMemcpy(history, row + lead, live * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+int spxb_batch_set_state_f32(spxb_batch *b, uint32_t stream, int32_t last_sample, uint32_t samp_frac_num,
+                             const float *history) {
+  if (!b || stream >= b->n_streams) return RESAMPLER_ERR_INVALID_ARG;
+  const size_t live = static_cast<size_t>(b->spec.taps - 1) * b->channels;
+  if (!b->f32) {
+    // an int16 history can only hold what int16 input left there
+    std::vector<int16_t> h(live ? live : 1);
+    if (history)
+      for (size_t i = 0; i < live; ++i) {
+        const float v = history[i];
+        if (!(v >= -32768.f && v <= 32767.f) || v != static_cast<float>(static_cast<int16_t>(v))) {
+          set_error("set_state_f32: history is not int16-valued; use a float batch (spxb_batch_create_f32)");
+          return RESAMPLER_ERR_INVALID_ARG;
+        }
+        h[i] = static_cast<int16_t>(v);
+      }
+    return spxb_batch_set_state(b, stream, last_sample, samp_frac_num, history ? h.data() : nullptr);
+  }
+  if (int e = spxb_batch_set_state(b, stream, last_sample, samp_frac_num, nullptr)) return e;
+  if (history && live) {
+    DeviceGuard g(b->device);
+    const size_t lead = static_cast<size_t>(b->hist_frames - (b->spec.taps - 1)) * b->channels;
+    float *row = reinterpret_cast<float *>(b->d_hist[b->hist_cur] + static_cast<size_t>(stream) * b->hist_stride);
+    SPXB_CUDA(cudaMemcpy(row + lead, history, live * sizeof(float), cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 
@@ -952,8 +1199,21 @@ long spxb_tensor_tap_tile(uint32_t in_rate, uint32_t out_rate, int quality, uint
   return static_cast<long>(bytes);
 }
 
+static int plan_call_any(uint32_t in_rate, uint32_t out_rate, int32_t last_sample, uint32_t samp_frac_num,
+                         uint32_t n_in, uint32_t out_cap, uint32_t out_block, spxb_call_plan *plan);
+
 int spxb_plan_call(uint32_t in_rate, uint32_t out_rate, int32_t last_sample, uint32_t samp_frac_num,
                    uint32_t n_in, uint32_t out_cap, spxb_call_plan *plan) {
+  return plan_call_any(in_rate, out_rate, last_sample, samp_frac_num, n_in, out_cap, kOutBlock, plan);
+}
+
+int spxb_plan_call_f32(uint32_t in_rate, uint32_t out_rate, int32_t last_sample, uint32_t samp_frac_num,
+                       uint32_t n_in, uint32_t out_cap, spxb_call_plan *plan) {
+  return plan_call_any(in_rate, out_rate, last_sample, samp_frac_num, n_in, out_cap, kOutBlockUnbounded, plan);
+}
+
+static int plan_call_any(uint32_t in_rate, uint32_t out_rate, int32_t last_sample, uint32_t samp_frac_num,
+                         uint32_t n_in, uint32_t out_cap, uint32_t out_block, spxb_call_plan *plan) {
   if (!plan || in_rate == 0 || out_rate == 0 || last_sample < 0) return RESAMPLER_ERR_INVALID_ARG;
   FilterSpec s;
   if (int e = derive_filter_spec(in_rate, out_rate, 0, &s)) return e;
@@ -961,7 +1221,7 @@ int spxb_plan_call(uint32_t in_rate, uint32_t out_rate, int32_t last_sample, uin
   StreamPos p;
   p.last_sample = last_sample;
   p.samp_frac_num = samp_frac_num;
-  const CallPlan pl = plan_call(s.num, s.den, p, n_in, out_cap);
+  const CallPlan pl = plan_call(s.num, s.den, p, n_in, out_cap, out_block);
   plan->n_out = pl.n_out;
   plan->consumed = pl.consumed;
   plan->last_sample = pl.next.last_sample;

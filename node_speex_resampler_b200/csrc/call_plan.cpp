@@ -18,7 +18,8 @@ inline uint64_t outputs_before(int64_t ls, uint64_t frac, uint64_t limit, uint64
 
 }  // namespace
 
-CallPlan plan_call(uint32_t num, uint32_t den, StreamPos pos, uint32_t n_in, uint32_t out_cap) {
+CallPlan plan_call(uint32_t num, uint32_t den, StreamPos pos, uint32_t n_in, uint32_t out_cap,
+                   uint32_t out_block) {
   CallPlan plan;
   int64_t ls = pos.last_sample;
   uint64_t frac = pos.samp_frac_num;
@@ -39,7 +40,7 @@ CallPlan plan_call(uint32_t num, uint32_t den, StreamPos pos, uint32_t n_in, uin
   // resample.c:988 `while (ilen && olen)`
   while (left_in != 0 && left_out != 0) {
     const uint64_t take = std::min<uint64_t>(left_in, kInBlock);
-    const uint64_t room = std::min<uint64_t>(left_out, kOutBlock);
+    const uint64_t room = std::min<uint64_t>(left_out, out_block);
     const uint64_t made = std::min(room, outputs_before(ls, frac, take, num, den));
     const uint64_t adv = frac + made * num;
     ls += static_cast<int64_t>(adv / den);

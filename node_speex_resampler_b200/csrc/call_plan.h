@@ -32,6 +32,11 @@ struct CallPlan {
 // Outputs m = 0 .. n_out-1 of the call read the window starting at
 //   p(m) = pos.last_sample + floor((pos.samp_frac_num + m*num) / den)
 // of X = history(N-1 frames) || input, with phase (pos.samp_frac_num + m*num) % den.
-CallPlan plan_call(uint32_t num, uint32_t den, StreamPos pos, uint32_t n_in, uint32_t out_cap);
+// out_block: output frames one block may produce -- kOutBlock on the int16 entry (its 1024-sample
+// stack buffer), unbounded on the float entry, which writes straight into the caller's buffer
+// (resample.c:944 `ochunk = olen`).
+constexpr uint32_t kOutBlockUnbounded = 0xffffffffu;
+CallPlan plan_call(uint32_t num, uint32_t den, StreamPos pos, uint32_t n_in, uint32_t out_cap,
+                   uint32_t out_block = kOutBlock);
 
 }  // namespace spxb

@@ -18,6 +18,7 @@ struct SpeexResamplerState_ {
   uint32_t in_rate = 0, out_rate = 0, channels = 0;
   int quality = 0;
   std::vector<int16_t> silence;  // stands in for in == NULL (resample.c:1007-1010)
+  std::vector<float> fsilence;   // the same for the float entry (resample.c:950-952)
 };
 
 extern "C" {
@@ -91,6 +92,34 @@ int speex_resampler_process_interleaved_int(SpeexResamplerState *st, const int16
   }
   // one stream: the strides are irrelevant, the lengths are the in-out cells
   return spxb_batch_process(st->batch, in, *in_len, in_len, out, *out_len, out_len);
+}
+
+int speex_resampler_process_interleaved_float(SpeexResamplerState *st, const float *in, uint32_t *in_len,
+                                              float *out, uint32_t *out_len) {
+  if (!st || !in_len || !out_len || !out) return RESAMPLER_ERR_INVALID_ARG;
+  if (!spxb_batch_is_f32(st->batch)) {
+    // first float call: the state moves to a float-history batch (int16 history converts exactly)
+    int e = 0;
+    spxb_batch *fb = spxb_batch_create_f32(1, st->channels, st->in_rate, st->out_rate, st->quality, 0, &e);
+    if (!fb) return e ? e : RESAMPLER_ERR_ALLOC_FAILED;
+    const spxb::FilterSpec &s = spxb::batch_spec(st->batch);
+    std::vector<float> hist(static_cast<size_t>(s.taps ? s.taps - 1 : 0) * st->channels + 1);
+    int32_t last = 0;
+    uint32_t frac = 0, magic = 0;
+    e = spxb_batch_get_state_f32(st->batch, 0, &last, &frac, &magic, hist.data());
+    if (!e) e = spxb_batch_set_state_f32(fb, 0, last, frac, hist.data());
+    if (e) {
+      spxb_batch_destroy(fb);
+      return e;
+    }
+    spxb_batch_destroy(st->batch);
+    st->batch = fb;
+  }
+  if (!in) {
+    st->fsilence.assign(static_cast<size_t>(*in_len) * st->channels, 0.f);
+    in = st->fsilence.data();
+  }
+  return spxb_batch_process_f32(st->batch, in, *in_len, in_len, out, *out_len, out_len);
 }
 
 spxb_batch *spxb_resampler_batch(SpeexResamplerState *st) { return st ? st->batch : nullptr; }

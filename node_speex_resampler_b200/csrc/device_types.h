@@ -61,6 +61,12 @@ struct CallArgs {
   const StreamCall *per_stream;  // device array [n_streams], or nullptr when uniform
   StreamCall uniform;            // used when per_stream == nullptr
   uint32_t max_n_out;            // max over streams (grid sizing)
+  // Sample formats (strict kernel only beyond 0). The pointers above stay int16-typed and every
+  // stride stays in int16 units; a float sample simply occupies two of them.
+  //   0  int16 history, int16 in/out                 (the hot path)
+  //   1  float history, int16 in/out                 (a state that has seen float calls)
+  //   2  float history, float in/out, no rounding    (speex_resampler_process_interleaved_float)
+  uint32_t fmt;
 };
 
 }  // namespace spxb

@@ -24,6 +24,23 @@ __device__ __forceinline__ int fetch_sample(const CallArgs &a, uint32_t s, int f
   return a.in[static_cast<size_t>(s) * a.in_stride + static_cast<size_t>(f) * a.channels + c];
 }
 
+// Format-generic variants (CallArgs::fmt): the sample as the f32 the reference holds in `mem`
+// (resample.c:1005 converts int16 input exactly; the float entry stores its input as is).
+template <int FMT>
+__device__ __forceinline__ float fetch_sample_f(const CallArgs &a, uint32_t s, int f, uint32_t c, uint32_t n_in) {
+  if (FMT == 0) return static_cast<float>(fetch_sample(a, s, f, c, n_in));
+  if (f < 0) {
+    const int hf = f + static_cast<int>(a.hist_frames);
+    if (hf < 0) return 0.f;
+    const float *h = reinterpret_cast<const float *>(a.hist_src + static_cast<size_t>(s) * a.hist_stride);
+    return h[static_cast<size_t>(hf) * a.channels + c];
+  }
+  if (static_cast<uint32_t>(f) >= n_in) return 0.f;
+  const size_t e = static_cast<size_t>(f) * a.channels + c;
+  if (FMT == 2) return reinterpret_cast<const float *>(a.in + static_cast<size_t>(s) * a.in_stride)[e];
+  return static_cast<float>(a.in[static_cast<size_t>(s) * a.in_stride + e]);
+}
+
 // 16 bytes of one stream's PCM starting at frame f (CH == 2: 4 frames, CH == 1: 8 frames):
 // history for f < 0, the call's input for f >= 0, zeros outside both.
 // in_align: largest of 16 / 8 / 4 / 2 bytes that every input row start is aligned to.
@@ -91,6 +108,39 @@ __device__ __forceinline__ void slide_history_elem(const CallArgs &a, uint32_t s
   else
     v = a.in[static_cast<size_t>(s) * a.in_stride + (src - hist_elems)];
   a.hist_dst[static_cast<size_t>(s) * a.hist_stride + e] = v;
+}
+
+template <int FMT>
+__device__ __forceinline__ void slide_history_elem_f(const CallArgs &a, uint32_t s, const StreamCall &sc, uint32_t e) {
+  if (FMT == 0) {
+    slide_history_elem(a, s, sc, e);
+    return;
+  }
+  const uint32_t hist_elems = a.hist_frames * a.channels;
+  const size_t src = static_cast<size_t>(sc.consumed) * a.channels + e;
+  float v;
+  if (src < hist_elems)
+    v = reinterpret_cast<const float *>(a.hist_src + static_cast<size_t>(s) * a.hist_stride)[src];
+  else if (FMT == 2)
+    v = reinterpret_cast<const float *>(a.in + static_cast<size_t>(s) * a.in_stride)[src - hist_elems];
+  else
+    v = static_cast<float>(a.in[static_cast<size_t>(s) * a.in_stride + (src - hist_elems)]);
+  reinterpret_cast<float *>(a.hist_dst + static_cast<size_t>(s) * a.hist_stride)[e] = v;
+}
+
+template <int FMT>
+__device__ __forceinline__ void history_block_f(const CallArgs &a, uint32_t blk) {
+  const uint32_t hist_elems = a.hist_frames * a.channels;
+  const uint32_t per_stream = (hist_elems + blockDim.x - 1) / blockDim.x;
+  const uint32_t s = blk / per_stream;
+  if (s >= a.n_streams) return;
+  const uint32_t e = (blk % per_stream) * blockDim.x + threadIdx.x;
+  const StreamCall sc = load_call(a, s);
+  if (e < hist_elems) slide_history_elem_f<FMT>(a, s, sc, e);
+  if (e == 0) {
+    a.last_sample[s] = sc.ls1;
+    a.samp_frac[s] = sc.frac1;
+  }
 }
 
 // Blocks appended to every FIR grid: slide the history of all streams and publish the new

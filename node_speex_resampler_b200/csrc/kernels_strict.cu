@@ -6,10 +6,14 @@
 //   resampler_basic_interpolate_single  :438-496  4 f32 sums over the oversampled prototype,
 //                                                 cubic blend (:318-328) afterwards
 //   resampler_basic_interpolate_double  :501-558  same with f64 sums and an f64 blend
-// followed by WORD2INT (arch.h:208-209) and the interleaved store (:1018-1022).
+// followed by WORD2INT (arch.h:208-209) and the interleaved store (:1018-1022). The same kernels
+// serve the float entry (speex_resampler_process_interleaved_float, :1038-1059 over :927-963):
+// FMT selects float history and float in/out, and the result is stored unrounded.
 // Every multiply/add goes through __fmul_rn/__fadd_rn/__dadd_rn/__dmul_rn so ptxas can never
 // contract them into FMAs. Works for any ratio, any per-stream position; it is also the
 // fallback when a batch does not qualify for the tiled kernel.
+#include <type_traits>
+
 #include "kernels_common.cuh"
 #include "launch.h"
 
@@ -19,7 +23,7 @@ namespace {
 
 constexpr int kStrictThreads = 128;
 
-template <bool kDirect, bool kWide>
+template <bool kDirect, bool kWide, int FMT>
 __device__ __forceinline__ float strict_output(const CallArgs &a, uint32_t s, uint32_t c,
                                                const StreamCall &sc, uint32_t m) {
   const FilterDev &F = a.filt;
@@ -35,17 +39,17 @@ __device__ __forceinline__ float strict_output(const CallArgs &a, uint32_t s, ui
     if (!kWide) {
       float acc = 0.f;
       for (int j = 0; j < N; ++j) {
-        const float x = static_cast<float>(fetch_sample(a, s, q + j, c, sc.n_in));
+        const float x = fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in);
         acc = __fadd_rn(acc, __fmul_rn(__ldg(h + j), x));
       }
       return acc;
     } else {
       double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
       for (int j = 0; j < N; j += 4) {
-        const float x0 = static_cast<float>(fetch_sample(a, s, q + j, c, sc.n_in));
-        const float x1 = static_cast<float>(fetch_sample(a, s, q + j + 1, c, sc.n_in));
-        const float x2 = static_cast<float>(fetch_sample(a, s, q + j + 2, c, sc.n_in));
-        const float x3 = static_cast<float>(fetch_sample(a, s, q + j + 3, c, sc.n_in));
+        const float x0 = fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in);
+        const float x1 = fetch_sample_f<FMT>(a, s, q + j + 1, c, sc.n_in);
+        const float x2 = fetch_sample_f<FMT>(a, s, q + j + 2, c, sc.n_in);
+        const float x3 = fetch_sample_f<FMT>(a, s, q + j + 3, c, sc.n_in);
         a0 = __dadd_rn(a0, static_cast<double>(__fmul_rn(__ldg(h + j), x0)));
         a1 = __dadd_rn(a1, static_cast<double>(__fmul_rn(__ldg(h + j + 1), x1)));
         a2 = __dadd_rn(a2, static_cast<double>(__fmul_rn(__ldg(h + j + 2), x2)));
@@ -62,7 +66,7 @@ __device__ __forceinline__ float strict_output(const CallArgs &a, uint32_t s, ui
     if (!kWide) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       for (int j = 0; j < N; ++j) {
-        const float x = static_cast<float>(fetch_sample(a, s, q + j, c, sc.n_in));
+        const float x = fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in);
         const float *cf = tp + static_cast<size_t>(j) * os;
         a0 = __fadd_rn(a0, __fmul_rn(x, __ldg(cf)));
         a1 = __fadd_rn(a1, __fmul_rn(x, __ldg(cf + 1)));
@@ -76,7 +80,7 @@ __device__ __forceinline__ float strict_output(const CallArgs &a, uint32_t s, ui
     } else {
       double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
       for (int j = 0; j < N; ++j) {
-        const float x = static_cast<float>(fetch_sample(a, s, q + j, c, sc.n_in));
+        const float x = fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in);
         const float *cf = tp + static_cast<size_t>(j) * os;
         a0 = __dadd_rn(a0, static_cast<double>(__fmul_rn(x, __ldg(cf))));
         a1 = __dadd_rn(a1, static_cast<double>(__fmul_rn(x, __ldg(cf + 1))));
@@ -94,12 +98,12 @@ __device__ __forceinline__ float strict_output(const CallArgs &a, uint32_t s, ui
   }
 }
 
-template <bool kDirect, bool kWide>
+template <bool kDirect, bool kWide, int FMT>
 __global__ void __launch_bounds__(kStrictThreads)
     strict_fir_kernel(const CallArgs a, const uint32_t blocks_per_stream,
                       const uint32_t fir_blocks) {
   if (blockIdx.x >= fir_blocks) {
-    history_block(a, blockIdx.x - fir_blocks);
+    history_block_f<FMT>(a, blockIdx.x - fir_blocks);
     return;
   }
   const uint32_t s = blockIdx.x / blocks_per_stream;
@@ -108,8 +112,11 @@ __global__ void __launch_bounds__(kStrictThreads)
   const uint32_t m = e / a.channels;
   const uint32_t c = e % a.channels;
   if (m >= sc.n_out) return;
-  const float y = strict_output<kDirect, kWide>(a, s, c, sc, m);
-  a.out[static_cast<size_t>(s) * a.out_stride + e] = word2int_exact(y);
+  const float y = strict_output<kDirect, kWide, FMT>(a, s, c, sc, m);
+  if (FMT == 2)  // the float entry stores the kernel's result as is (resample.c:927-963)
+    reinterpret_cast<float *>(a.out + static_cast<size_t>(s) * a.out_stride)[e] = y;
+  else
+    a.out[static_cast<size_t>(s) * a.out_stride + e] = word2int_exact(y);
 }
 
 }  // namespace
@@ -129,17 +136,20 @@ cudaError_t launch_strict(const CallArgs &a, cudaStream_t stream, uint32_t *laun
   const uint32_t fir_blocks = static_cast<uint32_t>(fir_blocks64);
   const dim3 grid(static_cast<uint32_t>(total)), block(kStrictThreads);
   const uint32_t bps_arg = bps ? bps : 1;
-  if (a.filt.direct) {
-    if (a.filt.wide_accum)
-      strict_fir_kernel<true, true><<<grid, block, 0, stream>>>(a, bps_arg, fir_blocks);
-    else
-      strict_fir_kernel<true, false><<<grid, block, 0, stream>>>(a, bps_arg, fir_blocks);
-  } else {
-    if (a.filt.wide_accum)
-      strict_fir_kernel<false, true><<<grid, block, 0, stream>>>(a, bps_arg, fir_blocks);
-    else
-      strict_fir_kernel<false, false><<<grid, block, 0, stream>>>(a, bps_arg, fir_blocks);
-  }
+  auto go = [&](auto kernel) { kernel<<<grid, block, 0, stream>>>(a, bps_arg, fir_blocks); };
+  auto by_filter = [&](auto fmt) {
+    constexpr int F = decltype(fmt)::value;
+    if (a.filt.direct) {
+      if (a.filt.wide_accum) go(strict_fir_kernel<true, true, F>);
+      else go(strict_fir_kernel<true, false, F>);
+    } else {
+      if (a.filt.wide_accum) go(strict_fir_kernel<false, true, F>);
+      else go(strict_fir_kernel<false, false, F>);
+    }
+  };
+  if (a.fmt == 2) by_filter(std::integral_constant<int, 2>{});
+  else if (a.fmt == 1) by_filter(std::integral_constant<int, 1>{});
+  else by_filter(std::integral_constant<int, 0>{});
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

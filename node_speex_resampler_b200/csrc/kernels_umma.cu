@@ -714,6 +714,11 @@ struct UmmaContext {
   size_t tiles_cap = 0;
   uint32_t n_tiles = 0;
   std::vector<UmmaTile> h_tiles;  // host copy of the planned tile table (kernel parameters)
+  // CUDA-graph support (batch.cu: ring graphs): while `frozen`, planning must not touch the
+  // stream or allocate (the stream is being captured); stream_ops counts every such operation,
+  // pool_generation changes whenever cached launches would point at stale tap tiles
+  bool frozen = false;
+  uint64_t stream_ops = 0, pool_generation = 0;
   uint32_t *d_jobs = nullptr;
   size_t jobs_cap = 0;
   unsigned long long *d_trace = nullptr;  // SPXB_UMMA_TRACE=1: timeline of the last launch
@@ -728,6 +733,14 @@ struct UmmaContext {
 namespace {
 
 constexpr size_t kMaxPoolBytes = 256ull << 20;
+
+bool inline_tiles_enabled() {
+  static const bool v = [] {
+    const char *e = getenv("SPXB_UMMA_INLINE_TILES");
+    return !e || atoi(e) != 0;
+  }();
+  return v;
+}
 
 uint32_t forced_nt() {
   static const uint32_t v = [] {
@@ -763,6 +776,7 @@ uint32_t pick_nt(const UmmaContext &c, uint32_t n_groups, uint32_t n_out) {
 }
 
 void drop_pool(UmmaContext *c) {
+  c->pool_generation += 1;
   if (c->d_pool) cudaFree(c->d_pool);
   c->d_pool = nullptr;
   c->pool_cap = 0;
@@ -842,9 +856,13 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
     c->fresh_plan = false;
     return true;  // steady state: same tiles as the previous call
   }
-  c->fresh_plan = true;
+  const uint64_t ops_before = c->stream_ops;
 
   const uint32_t nt = pick_nt(*c, n_groups, sc.n_out);
+  if (nt != c->nt && c->frozen) {
+    *err = cudaErrorNotSupported;
+    return false;
+  }
   if (nt != c->nt) {
     drop_pool(c);
     c->nt = nt;
@@ -887,7 +905,14 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
     jobs.push_back(keys[i].delta);
   }
   if (next_slot * static_cast<size_t>(c->tile_bytes) > kMaxPoolBytes) return false;
+  const bool table_in_params = inline_tiles_enabled() && tiles.size() <= kInlineTiles;
+  if (c->frozen && (!jobs.empty() || next_slot > c->pool_cap || !table_in_params)) {
+    *err = cudaErrorNotSupported;  // would need the stream / an allocation while it is being captured
+    return false;
+  }
   if (next_slot > c->pool_cap) {
+    c->stream_ops += 1;
+    c->pool_generation += 1;
     // grow: existing tiles are rebuilt rather than copied (rare; geometry changes only)
     const size_t want = std::max(next_slot, c->pool_cap * 2);
     const size_t cap = std::min(want, kMaxPoolBytes / c->tile_bytes);
@@ -905,6 +930,7 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
     c->pool_cap = cap;
   }
   if (!jobs.empty()) {
+    c->stream_ops += 1;
     const size_t n_jobs = jobs.size() / 3;
     if (n_jobs > c->jobs_cap) {
       if (c->d_jobs) {
@@ -926,18 +952,25 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
     if ((*err = cudaGetLastError()) != cudaSuccess) return false;
     for (auto &kv : fresh) c->slot_of.emplace(kv.first, kv.second);
   }
-  if (tiles.size() > c->tiles_cap) {
-    if (c->d_tiles) {
-      cudaStreamSynchronize(stream);
-      cudaFree(c->d_tiles);
+  // the tile table travels in the kernel parameters when it fits; only longer tables go to HBM
+  if (!table_in_params) {
+    c->stream_ops += 1;
+    if (tiles.size() > c->tiles_cap) {
+      if (c->d_tiles) {
+        cudaStreamSynchronize(stream);
+        cudaFree(c->d_tiles);
+      }
+      c->tiles_cap = std::max<size_t>(tiles.size(), 64);
+      if ((*err = cudaMalloc(reinterpret_cast<void **>(&c->d_tiles), c->tiles_cap * sizeof(UmmaTile))) != cudaSuccess)
+        return false;
     }
-    c->tiles_cap = std::max<size_t>(tiles.size(), 64);
-    if ((*err = cudaMalloc(reinterpret_cast<void **>(&c->d_tiles), c->tiles_cap * sizeof(UmmaTile))) != cudaSuccess)
+    if ((*err = cudaMemcpyAsync(c->d_tiles, tiles.data(), tiles.size() * sizeof(UmmaTile), cudaMemcpyHostToDevice,
+                                stream)) != cudaSuccess)
       return false;
   }
-  if ((*err = cudaMemcpyAsync(c->d_tiles, tiles.data(), tiles.size() * sizeof(UmmaTile), cudaMemcpyHostToDevice,
-                              stream)) != cudaSuccess)
-    return false;
+  // a re-plan that uploaded or built something launches without the programmatic edge (the next
+  // kernel's prologue reads the tile table / tap pool before its grid dependency resolves)
+  c->fresh_plan = c->stream_ops != ops_before;
   c->n_tiles = static_cast<uint32_t>(tiles.size());
   c->h_tiles = tiles;
   c->memo = true;
@@ -966,15 +999,17 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
   return true;
 }
 
+void umma_set_frozen(UmmaContext *c, bool frozen) {
+  if (c) c->frozen = frozen;
+}
+uint64_t umma_stream_ops(const UmmaContext *c) { return c ? c->stream_ops : 0; }
+uint64_t umma_pool_generation(const UmmaContext *c) { return c ? c->pool_generation : 0; }
+
 cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, uint32_t *launches) {
   UmmaArgs u;
   u.tiles = c->d_tiles;
   u.n_tiles = c->n_tiles;
-  static const bool inline_tiles = [] {
-    const char *e = getenv("SPXB_UMMA_INLINE_TILES");
-    return !e || atoi(e) != 0;
-  }();
-  u.n_inline = (inline_tiles && c->n_tiles <= kInlineTiles) ? c->n_tiles : 0u;
+  u.n_inline = (inline_tiles_enabled() && c->n_tiles <= kInlineTiles) ? c->n_tiles : 0u;
   for (uint32_t i = 0; i < kInlineTiles; ++i) {
     u.inl[i].kf0 = i < u.n_inline ? c->h_tiles[i].kf0 : 0;
     u.inl[i].slot = i < u.n_inline ? c->h_tiles[i].slot : 0u;

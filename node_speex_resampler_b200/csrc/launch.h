@@ -43,6 +43,12 @@ int umma_shift(const UmmaContext *c);
 void umma_geometry(const UmmaContext *c, uint32_t out[6]);
 bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaError_t *err);
 cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, uint32_t *launches);
+// CUDA-graph support: while frozen, umma_prepare refuses (cudaErrorNotSupported) any call that
+// would need the stream or an allocation; stream_ops counts such operations since creation;
+// pool_generation changes whenever earlier launches' tap-tile pointers go stale.
+void umma_set_frozen(UmmaContext *c, bool frozen);
+uint64_t umma_stream_ops(const UmmaContext *c);
+uint64_t umma_pool_generation(const UmmaContext *c);
 // SPXB_UMMA_TRACE=1: clock64 timeline of the last launch, 32 words per CTA (debug only)
 long umma_read_trace(const UmmaContext *c, unsigned long long *dst, size_t cap_words);
 

@@ -156,11 +156,17 @@ class StreamBatch:
     """n_streams streams of one (channels, inRate, outRate, quality) on one GPU, processed
     together. Backed by spxb_batch_* (include/speexb200.h part 2)."""
 
-    def __init__(self, n_streams, channels, inRate, outRate, quality=7, device=0):
+    def __init__(self, n_streams, channels, inRate, outRate, quality=7, device=0, sample_format="s16"):
         L = _lib.lib()
         err = C.c_int(0)
-        self._h = L.spxb_batch_create(int(n_streams), int(channels), int(inRate), int(outRate),
-                                      int(quality), int(device), C.byref(err))
+        if sample_format not in ("s16", "f32"):
+            raise ValueError("sample_format is 's16' or 'f32'")
+        # 'f32': float history (the reference's own `mem` type); serves process_f32 -- the Speex
+        # float entry -- and int16 calls on one state, bit-exactly, on the strict kernel
+        self.sample_format = sample_format
+        create = L.spxb_batch_create_f32 if sample_format == "f32" else L.spxb_batch_create
+        self._h = create(int(n_streams), int(channels), int(inRate), int(outRate),
+                         int(quality), int(device), C.byref(err))
         if not self._h:
             detail = _lib.last_error()
             raise RuntimeError(_lib.strerror(err.value) + (f" ({detail})" if detail else ""))
@@ -273,6 +279,23 @@ class StreamBatch:
         out = np.zeros((self.n_streams, out_stride * self.channels), dtype=np.int16)
         e = L.spxb_batch_process(self._h, pcm.ctypes.data, in_stride, nin.ctypes.data,
                                  out.ctypes.data, out_stride, nout.ctypes.data)
+        if e:
+            raise RuntimeError(_lib.strerror(e) + ": " + _lib.last_error())
+        return out, nin, nout
+
+    def process_f32(self, pcm: np.ndarray, in_frames, out_cap):
+        """speex_resampler_process_interleaved_float for every stream (float batch only):
+        pcm float32 [n_streams, stride_frames*channels]; results are the kernels' f32 values,
+        unrounded. Returns (out, consumed[n], written[n]) like process()."""
+        L = _lib.lib()
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32).reshape(self.n_streams, -1)
+        in_stride = pcm.shape[1] // self.channels
+        nin = np.ascontiguousarray(np.broadcast_to(np.asarray(in_frames, dtype=np.uint32), (self.n_streams,))).copy()
+        nout = np.ascontiguousarray(np.broadcast_to(np.asarray(out_cap, dtype=np.uint32), (self.n_streams,))).copy()
+        out_stride = max(int(nout.max()), 1)
+        out = np.zeros((self.n_streams, out_stride * self.channels), dtype=np.float32)
+        e = L.spxb_batch_process_f32(self._h, pcm.ctypes.data, in_stride, nin.ctypes.data,
+                                     out.ctypes.data, out_stride, nout.ctypes.data)
         if e:
             raise RuntimeError(_lib.strerror(e) + ": " + _lib.last_error())
         return out, nin, nout

@@ -60,6 +60,9 @@ def _load_oracle():
         L.orc_process_interleaved_int16.restype = C.c_int
         L.orc_process_interleaved_int16.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32),
                                                     C.c_void_p, C.POINTER(C.c_uint32)]
+        L.orc_process_interleaved_float.restype = C.c_int
+        L.orc_process_interleaved_float.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32),
+                                                    C.c_void_p, C.POINTER(C.c_uint32)]
         L.orc_get_params.argtypes = [C.c_void_p, C.POINTER(OrcParams)]
         L.orc_table.restype = C.POINTER(C.c_float)
         L.orc_table.argtypes = [C.c_void_p]
@@ -84,6 +87,9 @@ def _load_ref():
         L.speex_resampler_destroy.argtypes = [C.c_void_p]
         L.speex_resampler_process_interleaved_int.restype = C.c_int
         L.speex_resampler_process_interleaved_int.argtypes = [
+            C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_uint32)]
+        L.speex_resampler_process_interleaved_float.restype = C.c_int
+        L.speex_resampler_process_interleaved_float.argtypes = [
             C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_uint32)]
         L.speex_resampler_strerror.restype = C.c_char_p
         L.speex_resampler_strerror.argtypes = [C.c_int]
@@ -172,6 +178,17 @@ class OracleResampler:
         assert e == 0, e
         return out[: n_out.value * self.channels].copy(), n_in.value, n_out.value
 
+    def process_float(self, pcm: np.ndarray, out_cap_frames: int):
+        """speex_resampler_process_interleaved_float contract (float build). pcm: float32."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32).reshape(-1)
+        n_in = C.c_uint32(pcm.size // self.channels)
+        n_out = C.c_uint32(out_cap_frames)
+        out = np.empty(max(1, out_cap_frames * self.channels), dtype=np.float32)
+        e = self.L.orc_process_interleaved_float(self.h, pcm.ctypes.data, C.byref(n_in),
+                                                 out.ctypes.data, C.byref(n_out))
+        assert e == 0, e
+        return out[: n_out.value * self.channels].copy(), n_in.value, n_out.value
+
     def processChunk(self, chunk) -> bytes:
         b = bytes(chunk) if not isinstance(chunk, np.ndarray) else chunk.tobytes()
         if len(b) % (self.channels * 2) != 0:
@@ -231,6 +248,17 @@ class RefResampler:
         n_out = C.c_uint32(out_cap_frames)
         out = np.empty(max(1, out_cap_frames * self.channels), dtype=np.int16)
         e = self.L.speex_resampler_process_interleaved_int(
+            self.h, pcm.ctypes.data, C.byref(n_in), out.ctypes.data, C.byref(n_out))
+        if e != 0:
+            raise RuntimeError(self.L.speex_resampler_strerror(e).decode())
+        return out[: n_out.value * self.channels].copy(), n_in.value, n_out.value
+
+    def process_float(self, pcm: np.ndarray, out_cap_frames: int):
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32).reshape(-1)
+        n_in = C.c_uint32(pcm.size // self.channels)
+        n_out = C.c_uint32(out_cap_frames)
+        out = np.empty(max(1, out_cap_frames * self.channels), dtype=np.float32)
+        e = self.L.speex_resampler_process_interleaved_float(
             self.h, pcm.ctypes.data, C.byref(n_in), out.ctypes.data, C.byref(n_out))
         if e != 0:
             raise RuntimeError(self.L.speex_resampler_strerror(e).decode())

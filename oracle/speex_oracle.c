@@ -377,6 +377,56 @@ static void run_channel(orc_resampler *r, uint32_t ch, const int16_t *in, uint32
   *out_frames -= left_out;
 }
 
+/* One channel of a strided float stream; resample.c:927-963, the NATIVE entry of the float
+ * build (speex_resampler_process_float): the same 160-frame input blocks, but an output block
+ * is all the capacity that is left (there is no 1024-sample stack buffer on this path) and the
+ * kernel's f32 results are stored as they are -- no scaling, rounding or saturation. */
+static int run_channel_float(orc_resampler *r, uint32_t ch, const float *in, uint32_t stride,
+                             uint32_t *in_frames, float *out, uint32_t *out_frames) {
+  float *x = r->work + (size_t)ch * r->work_len;
+  const uint32_t hist = r->N - 1;
+  uint32_t left_in = *in_frames, left_out = *out_frames;
+  float *ybuf = (float *)malloc(sizeof(float) * (left_out ? left_out : 1));
+  if (!ybuf) return ORC_ERR_ALLOC;
+
+  while (left_in && left_out) {
+    uint32_t take = left_in > ORC_IN_BLOCK ? ORC_IN_BLOCK : left_in;
+    if (in)
+      for (uint32_t j = 0; j < take; j++) x[hist + j] = in[(size_t)j * stride];
+    else
+      for (uint32_t j = 0; j < take; j++) x[hist + j] = 0;
+
+    uint32_t made = run_kernel(r, ch, x, take, ybuf, left_out); /* :944 ochunk = olen */
+    uint32_t used = take;
+    if (r->pos[ch] < (int32_t)take) used = (uint32_t)r->pos[ch];
+    r->pos[ch] -= (int32_t)used;
+    for (uint32_t j = 0; j < hist; j++) x[j] = x[j + used];
+
+    for (uint32_t j = 0; j < made; j++) out[(size_t)j * stride] = ybuf[j];
+    left_in -= used;
+    left_out -= made;
+    out += (size_t)made * stride;
+    if (in) in += (size_t)used * stride;
+  }
+  free(ybuf);
+  *in_frames -= left_in;
+  *out_frames -= left_out;
+  return ORC_OK;
+}
+
+int orc_process_interleaved_float(orc_resampler *r, const float *in, uint32_t *in_frames, float *out,
+                                  uint32_t *out_frames) {
+  /* resample.c:1038-1059 in the float build: channel loop as for int16 */
+  const uint32_t n_in = *in_frames, cap = *out_frames;
+  for (uint32_t c = 0; c < r->channels; c++) {
+    *in_frames = n_in;
+    *out_frames = cap;
+    int e = run_channel_float(r, c, in ? in + c : NULL, r->channels, in_frames, out + c, out_frames);
+    if (e) return e;
+  }
+  return ORC_OK;
+}
+
 int orc_process_interleaved_int16(orc_resampler *r, const int16_t *in, uint32_t *in_frames,
                                   int16_t *out, uint32_t *out_frames) {
   /* resample.c:1061-1082: every channel restarts from the caller's lengths; the

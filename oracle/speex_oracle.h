@@ -64,6 +64,12 @@ int orc_process_interleaved_int16(orc_resampler *r, const int16_t *in,
                                   uint32_t *in_frames, int16_t *out,
                                   uint32_t *out_frames);
 
+/* same contract as speex_resampler_process_interleaved_float of the float build
+ * (resample.c:1038-1059 over :927-963): float samples in, the kernels' f32 results out
+ * unrounded; int16 and float calls may be mixed on one state (the history is float). */
+int orc_process_interleaved_float(orc_resampler *r, const float *in, uint32_t *in_frames,
+                                  float *out, uint32_t *out_frames);
+
 void orc_get_params(const orc_resampler *r, orc_params *p);
 const float *orc_table(const orc_resampler *r);
 /* per-channel streaming state: last_sample, samp_frac_num and the N-1 history

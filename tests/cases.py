@@ -34,3 +34,23 @@ GOLDEN_STREAMS = 2
 def case_id(c):
     ch, i, o, q, _ = c
     return f"{ch}ch_{i}to{o}_q{q}"
+
+
+# Float-entry golden vectors (oracle/gen_golden_f32.py -> tests/golden/vectors_f32.npz): MATRIX
+# rows covering the four reference kernels, each driven through this sequence of calls on ONE
+# state -- (kind, input frames, output capacity in frames), kind "f" = float entry, "i" = int16
+# entry. Capacities 40 and 1500 bind on some rows, which is where the float entry's block walk
+# (no 1024-frame output block, resample.c:944) differs from the int16 entry's.
+F32_ROWS = [0, 2, 3, 4, 17, 20, 24]
+F32_CALLS = [("f", 480, 4000), ("i", 441, 4000), ("f", 7, 4000), ("f", 300, 40), ("i", 1, 4000),
+             ("f", 882, 1500), ("f", 0, 10), ("i", 200, 0), ("f", 333, 4000)]
+
+
+def f32_input(row, call, kind, n, ch, in_rate):
+    """seeded input of one call: int16 PCM for "i", non-integer floats of PCM scale for "f" """
+    import numpy as np
+    from node_speex_resampler_b200.signals import synth_pcm
+    pcm = synth_pcm(1, ch, max(n, 1), in_rate, seed=0xF32 + 100 * row + call)[0][: n * ch]
+    if kind == "i":
+        return pcm
+    return (pcm.astype(np.float32) * np.float32(0.731) + np.float32(0.123)).astype(np.float32)

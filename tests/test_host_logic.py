@@ -156,3 +156,23 @@ def test_no_gpu_fails_loudly_not_silently():
         SpeexResampler(2, 44100, 48000).processChunk(b"\0" * 8)
     with pytest.raises(RuntimeError, match="no CUDA device"):
         SpeexResampler.initPromise.result()
+
+
+def test_call_plan_float_entry_walk_matches_oracle():
+    """lengths and next position of the float entry (unbounded output block, resample.c:944)
+    against the oracle's float path, capacity-bound calls included"""
+    from oracle import oracle as O
+    L = lib()
+    rng = np.random.default_rng(9)
+    for i, o in ((8000, 96000), (44100, 48000), (48000, 16000), (96000, 44100), (8000, 48000)):
+        r = O.OracleResampler(1, i, o, 3)
+        for k in range(40):
+            n = int(rng.choice([0, 1, 159, 160, 161, 480, 1000]))
+            cap = int(rng.choice([0, 1, 100, 1023, 1024, 1025, 1500, 5000]))
+            ls, fr, _ = r.state(0)
+            plan = _lib.CallPlan()
+            assert L.spxb_plan_call_f32(i, o, ls, fr, n, cap, C.byref(plan)) == 0
+            _, used, made = r.process_float(np.zeros(n, np.float32), cap)
+            ls1, fr1, _ = r.state(0)
+            assert (plan.consumed, plan.n_out, plan.last_sample, plan.samp_frac_num) == (used, made, ls1, fr1), \
+                (i, o, k, n, cap)

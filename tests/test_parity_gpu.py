@@ -411,3 +411,114 @@ def test_speex_c_api_getters_and_skip_zeros():
     L.spxb_plan_call(44100, 48000, 64, 0, 882, 2000, C.byref(pl))
     assert (n_in.value, n_out.value) == (pl.consumed, pl.n_out)
     L.speex_resampler_destroy(st)
+
+
+@pytest.mark.parametrize("kernel", [KERNEL_TENSOR, KERNEL_STRICT], ids=["tensor", "strict"])
+def test_device_ring_graph_replay_equals_single_hops(kernel):
+    """spxb_batch_process_device_ring captures a repeating hop sequence into a CUDA graph (second
+    unchanged sighting) and replays it afterwards. Every round -- launch by launch, captured,
+    replayed -- must leave the same outputs and the same stream state as single uniform hops."""
+    torch = pytest.importorskip("torch")
+    L = lib()
+    S, ch, i, o, q, n, cap = 70, 2, 44100, 48000, 7, 882, 960
+    ring, steps, rounds = 4, 8, 5
+    a, b = StreamBatch(S, ch, i, o, q), StreamBatch(S, ch, i, o, q)
+    a.set_kernel(kernel)
+    b.set_kernel(kernel)
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    for h in (a, b):
+        assert L.spxb_batch_set_stream(h._h, C.c_void_p(ts.cuda_stream)) == 0
+    x = np.stack([synth_pcm(S, ch, n, i, seed=51, start_frame=k * n) for k in range(ring)])
+    d_in = torch.from_numpy(x).cuda()
+    d_ring = torch.zeros((ring, S, cap * ch), dtype=torch.int16, device="cuda")
+    d_one = torch.zeros((ring, S, cap * ch), dtype=torch.int16, device="cuda")
+    in_slot, out_slot = S * n * ch, S * cap * ch
+    for r in range(rounds):
+        first = r * steps
+        assert L.spxb_batch_process_device_ring(b._h, d_in.data_ptr(), n, in_slot, d_ring.data_ptr(), cap, out_slot,
+                                                ring, n, cap, first, steps) == 0, _lib.last_error()
+        for k in range(first, first + steps):
+            sl = k % ring
+            assert L.spxb_batch_process_device_uniform(a._h, d_in[sl].data_ptr(), n, n, d_one[sl].data_ptr(), cap,
+                                                       cap, None, None) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(d_ring, d_one), r
+        assert b.counters().kernel_launches == a.counters().kernel_launches
+        sa, sb = a.get_state(3), b.get_state(3)
+        assert sa[:3] == sb[:3] and np.array_equal(sa[3], sb[3]), r
+        d_ring.zero_()
+        d_one.zero_()
+    a.close()
+    b.close()
+
+
+# ---- float entry (SURVEY 8f row 3) ---------------------------------------------------------
+from cases import F32_CALLS, F32_ROWS, f32_input  # noqa: E402
+
+VEC_F32 = np.load(os.path.join(os.path.dirname(__file__), "golden", "vectors_f32.npz"))
+
+
+@pytest.mark.parametrize("row", F32_ROWS, ids=lambda r: case_id(MATRIX[r]))
+def test_c_api_float_entry_matches_golden_bit_exact(row):
+    """speex_resampler_process_interleaved_float and ..._int mixed on ONE state through the C
+    ABI, against vectors from the reference's own float build: every f32 bit and every length,
+    capacity-bound calls included (float entry block walk, resample.c:927-963)."""
+    L = lib()
+    ch, i, o, q, _ = MATRIX[row]
+    key = case_id(MATRIX[row])
+    err = C.c_int(0)
+    st = L.speex_resampler_init(ch, i, o, q, C.byref(err))
+    assert st and err.value == 0
+    try:
+        for k, (kind, n, cap) in enumerate(F32_CALLS):
+            x = f32_input(row, k, kind, n, ch, i)
+            xin = x if x.size else np.zeros(1, x.dtype)
+            out = np.zeros(max(cap * ch, 1), np.float32 if kind == "f" else np.int16)
+            n_in, n_out = C.c_uint32(n), C.c_uint32(cap)
+            fn = L.speex_resampler_process_interleaved_float if kind == "f" else L.speex_resampler_process_interleaved_int
+            assert fn(st, xin.ctypes.data, C.byref(n_in), out.ctypes.data, C.byref(n_out)) == 0, _lib.last_error()
+            assert [n_in.value, n_out.value] == VEC_F32[f"{key}/call{k}/lens"].tolist(), (key, k)
+            want = VEC_F32[f"{key}/call{k}/out"]
+            got = out[: n_out.value * ch]
+            assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), (key, k)
+    finally:
+        L.speex_resampler_destroy(st)
+
+
+def test_float_batch_matches_oracle_per_stream():
+    """spxb_batch_process_f32 over a ragged batch: every stream equals its own oracle float
+    state bit for bit, int16 calls interleaved on the same (float-history) batch"""
+    ch, i, o, q, S = 2, 44100, 48000, 7, 9
+    b = StreamBatch(S, ch, i, o, q, sample_format="f32")
+    refs = [O.OracleResampler(ch, i, o, q) for _ in range(S)]
+    rng = np.random.default_rng(3)
+    for k in range(8):
+        n_in = rng.choice([0, 1, 160, 441, 500], size=S).astype(np.uint32)
+        cap = rng.choice([0, 37, 480, 600], size=S).astype(np.uint32)
+        pcm = synth_pcm(S, ch, 500, i, seed=70 + k)
+        if k % 3 == 2:  # an int16 call on the float-history batch
+            out, used, made = b.process(pcm, n_in, cap)
+            for s in range(S):
+                y, u, m = refs[s].process(pcm[s, : n_in[s] * ch], int(cap[s]))
+                assert (u, m) == (int(used[s]), int(made[s])), (k, s)
+                assert np.array_equal(y, out[s, : m * ch]), (k, s)
+        else:
+            x = (pcm.astype(np.float32) * np.float32(1.0 / 32768.0)).astype(np.float32)
+            out, used, made = b.process_f32(x, n_in, cap)
+            for s in range(S):
+                y, u, m = refs[s].process_float(x[s, : n_in[s] * ch], int(cap[s]))
+                assert (u, m) == (int(used[s]), int(made[s])), (k, s)
+                assert np.array_equal(y.view(np.uint32), out[s, : m * ch].view(np.uint32)), (k, s)
+    # the float view of the state round-trips
+    L = lib()
+    info = b.filter_info()
+    hist = np.zeros((info.filt_len - 1) * ch, np.float32)
+    ls, fr, mg = C.c_int32(), C.c_uint32(), C.c_uint32()
+    assert L.spxb_batch_get_state_f32(b._h, 4, C.byref(ls), C.byref(fr), C.byref(mg), hist.ctypes.data) == 0
+    rl, rf, rh = refs[4].state(0)
+    assert (ls.value, fr.value) == (rl, rf)
+    assert np.array_equal(hist[0::ch].view(np.uint32), rh.view(np.uint32))
+    with pytest.raises(RuntimeError):
+        StreamBatch(2, ch, i, o, q).process_f32(np.zeros((2, 8), np.float32), 4, 8)
+    b.close()
