@@ -1,13 +1,16 @@
 """ctypes drivers for the CPU oracle -- TEST INFRASTRUCTURE ONLY.
 
-Two checkers live here:
+Three checkers live here:
 
 * ``OracleResampler``  -> oracle/liboracle.so, our C restatement (speex_oracle.c)
 * ``RefResampler``     -> oracle/_ref/libspeex_ref.so, the reference's own
   deps/speex/resample.c compiled natively by oracle/Makefile (exists only where
   that build ran; it travels to the GPU box as a prebuilt, git-ignored .so)
+* ``WasmResampler``    -> oracle/_ref/libspeex_wasm.so, the reference's SHIPPED WebAssembly
+  module (embedded in src/speex_wasm.js), translated to C by oracle/wasm2c_lite.py and driven
+  through its own malloc / length cells like src/index.ts does; same build and travel rules
 
-Both expose the reference wrapper's ``processChunk`` rule (src/index.ts:50-116)
+All expose the reference wrapper's ``processChunk`` rule (src/index.ts:50-116)
 so tests read like src/test.ts. Nothing in node_speex_resampler_b200/ imports
 this module; only tests/, __graft_entry__.smoke() and bench.py's CPU legs do.
 """
@@ -26,7 +29,8 @@ REF_SO = os.path.join(HERE, "_ref", "libspeex_ref.so")
 
 
 def build(quiet: bool = True) -> None:
-    """Compile liboracle.so (always) and _ref/libspeex_ref.so (when /root/reference exists)."""
+    """Compile liboracle.so (always) and _ref/libspeex_ref.so + _ref/libspeex_wasm.so (when
+    /root/reference exists)."""
     subprocess.run(["make", "-C", HERE] + (["-s"] if quiet else []), check=True,
                    stdout=subprocess.DEVNULL if quiet else None)
 
@@ -271,6 +275,130 @@ class RefResampler:
         cap = self._rule.capacity_frames(len(b))
         out, _, _ = self.process(np.frombuffer(b, dtype=np.int16), cap)
         return out.tobytes()
+
+
+WASM_SO = os.path.join(HERE, "_ref", "libspeex_wasm.so")
+_wasm = None
+
+
+def have_wasm() -> bool:
+    return os.path.exists(WASM_SO)
+
+
+def _load_wasm():
+    global _wasm
+    if _wasm is None:
+        if not os.path.exists(WASM_SO):
+            raise FileNotFoundError(f"{WASM_SO} not built (reference tree absent?)")
+        L = C.CDLL(WASM_SO)
+        u32 = C.c_uint32
+        L.wasm_memory.restype = C.POINTER(C.c_uint8)
+        L.wasm_memory_bytes.restype = u32
+        L.wasm_malloc.restype = u32
+        L.wasm_malloc.argtypes = [u32]
+        L.wasm_free.argtypes = [u32]
+        L.wasm_speex_resampler_init.restype = u32
+        L.wasm_speex_resampler_init.argtypes = [u32, u32, u32, u32, u32]
+        L.wasm_speex_resampler_destroy.argtypes = [u32]
+        L.wasm_speex_resampler_process_interleaved_int.restype = u32
+        L.wasm_speex_resampler_process_interleaved_int.argtypes = [u32, u32, u32, u32, u32]
+        L.wasm_speex_resampler_strerror.restype = u32
+        L.wasm_speex_resampler_strerror.argtypes = [u32]
+        _wasm = L
+    return _wasm
+
+
+class WasmResampler:
+    """The reference's SHIPPED WebAssembly module (translated to C by oracle/wasm2c_lite.py,
+    oracle/_ref/libspeex_wasm.so), driven exactly as src/index.ts:50-116 drives it: staging
+    buffers malloc'd in linear memory, i32 length cells, the grow-only capacity rule."""
+
+    def __init__(self, channels, in_rate, out_rate, quality=7):
+        self.L = _load_wasm()
+        self.channels, self.in_rate, self.out_rate, self.quality = channels, in_rate, out_rate, quality
+        self._ptr = 0
+        self._in_ptr = self._out_ptr = -1
+        self._in_size = self._out_size = -1
+        self._rule = _ChunkRule(channels, in_rate, out_rate)
+
+    def __del__(self):
+        try:
+            for p in (self._in_ptr, self._out_ptr):
+                if p != -1:
+                    self.L.wasm_free(p)
+            if self._ptr:
+                self.L.wasm_speex_resampler_destroy(self._ptr)
+                self._ptr = 0
+        except Exception:
+            pass
+
+    def _mem(self):
+        n = self.L.wasm_memory_bytes()
+        return np.ctypeslib.as_array(self.L.wasm_memory(), shape=(n,))
+
+    def _init(self):
+        L = self.L
+        err_ptr = L.wasm_malloc(4)
+        self._ptr = L.wasm_speex_resampler_init(self.channels, self.in_rate, self.out_rate, self.quality, err_ptr)
+        err = int(self._mem()[err_ptr:err_ptr + 4].view(np.int32)[0])
+        if err != 0:
+            self._ptr = 0
+            raise RuntimeError(self.strerror(err))
+        self._in_len_ptr, self._out_len_ptr = L.wasm_malloc(4), L.wasm_malloc(4)
+
+    def strerror(self, err: int) -> str:
+        p = self.L.wasm_speex_resampler_strerror(err)
+        m = self._mem()
+        q = p
+        while m[q]:
+            q += 1
+        return bytes(m[p:q]).decode()
+
+    def process(self, pcm: np.ndarray, out_cap_frames: int):
+        """speex_resampler_process_interleaved_int inside the module's linear memory"""
+        L = self.L
+        if not self._ptr:
+            self._init()
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1)
+        nbytes, obytes = pcm.size * 2, max(out_cap_frames * self.channels * 2, 2)
+        if self._in_size < nbytes:
+            if self._in_ptr != -1:
+                L.wasm_free(self._in_ptr)
+            self._in_ptr, self._in_size = L.wasm_malloc(max(nbytes, 2)), nbytes
+        if self._out_size < obytes:
+            if self._out_ptr != -1:
+                L.wasm_free(self._out_ptr)
+            self._out_ptr, self._out_size = L.wasm_malloc(obytes), obytes
+        m = self._mem()
+        m[self._in_ptr:self._in_ptr + nbytes] = pcm.view(np.uint8)
+        m[self._in_len_ptr:self._in_len_ptr + 4].view(np.uint32)[0] = pcm.size // self.channels
+        m[self._out_len_ptr:self._out_len_ptr + 4].view(np.uint32)[0] = out_cap_frames
+        e = L.wasm_speex_resampler_process_interleaved_int(self._ptr, self._in_ptr, self._in_len_ptr, self._out_ptr,
+                                                           self._out_len_ptr)
+        if e != 0:
+            raise RuntimeError(self.strerror(e))
+        m = self._mem()
+        used = int(m[self._in_len_ptr:self._in_len_ptr + 4].view(np.uint32)[0])
+        made = int(m[self._out_len_ptr:self._out_len_ptr + 4].view(np.uint32)[0])
+        out = m[self._out_ptr:self._out_ptr + made * self.channels * 2].view(np.int16).copy()
+        return out, used, made
+
+    def processChunk(self, chunk) -> bytes:
+        b = bytes(chunk) if not isinstance(chunk, np.ndarray) else chunk.tobytes()
+        if len(b) % (self.channels * 2) != 0:
+            raise ValueError("Chunk length should be a multiple of channels * 2 bytes")
+        cap = self._rule.capacity_frames(len(b))
+        out, _, _ = self.process(np.frombuffer(b, dtype=np.int16), cap)
+        return out.tobytes()
+
+    def table(self) -> np.ndarray:
+        """the module's sinc table (wasm32 struct: sinc_table @76, sinc_table_length @80)"""
+        if not self._ptr:
+            self._init()
+        m = self._mem()
+        p = int(m[self._ptr + 76:self._ptr + 80].view(np.uint32)[0])
+        n = int(m[self._ptr + 80:self._ptr + 84].view(np.uint32)[0])
+        return m[p:p + 4 * n].view(np.float32).copy()
 
 
 def best_cpu_resampler():

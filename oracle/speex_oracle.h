@@ -16,7 +16,10 @@
  * assert duration). This restatement is pinned bit-for-bit against a native
  * gcc build of the reference's own resample.c (oracle/_ref, see Makefile) on the
  * reference's three resources/ .pcm fixtures and on seeded synthetic inputs;
- * the resulting hashes are frozen in tests/golden/.
+ * the resulting hashes are frozen in tests/golden/. It is also pinned against the
+ * reference's SHIPPED WebAssembly module, executed through oracle/wasm2c_lite.py
+ * (oracle/_ref/libspeex_wasm.so): tables and PCM bit-identical on the whole parity
+ * matrix and on the fixtures (tests/test_oracle.py).
  */
 #ifndef SPEEX_ORACLE_H
 #define SPEEX_ORACLE_H

@@ -522,3 +522,31 @@ def test_float_batch_matches_oracle_per_stream():
     with pytest.raises(RuntimeError):
         StreamBatch(2, ch, i, o, q).process_f32(np.zeros((2, 8), np.float32), 4, 8)
     b.close()
+
+
+@pytest.mark.skipif(not O.have_wasm(), reason="oracle/_ref/libspeex_wasm.so not present")
+@pytest.mark.parametrize("c", [MATRIX[k] for k in (0, 2, 3, 4, 17, 18)], ids=case_id)
+def test_gpu_matches_the_shipped_wasm_module(c):
+    """north star: "output must match the reference WASM resampler". The module embedded in the
+    reference's src/speex_wasm.js, executed through oracle/wasm2c_lite.py's translation: the strict
+    kernel is bit-exact against it, the tensor kernel within 1 LSB and above 90 dB SNR."""
+    ch, i, o, q, _ = c
+    S, n = 3, 882
+    cap = int(np.ceil(n * o / i)) + 1
+    strict, fast = StreamBatch(S, ch, i, o, q), StreamBatch(S, ch, i, o, q)
+    strict.set_kernel(KERNEL_STRICT)
+    refs = [O.WasmResampler(ch, i, o, q) for _ in range(S)]
+    for k in range(4):
+        pcm = synth_pcm(S, ch, n, i, seed=500 + k, start_frame=k * n)
+        ys, us, ms = strict.process(pcm, n, cap)
+        yf, uf, mf = fast.process(pcm, n, cap)
+        for s in range(S):
+            y, u, m = refs[s].process(pcm[s], cap)
+            assert (u, m) == (int(us[s]), int(ms[s])) == (int(uf[s]), int(mf[s]))
+            assert np.array_equal(y, ys[s, : m * ch]), (k, s)
+            d = y.astype(np.int32) - yf[s, : m * ch].astype(np.int32)
+            assert np.abs(d).max() <= 1, (k, s)
+            if k:
+                assert O.snr_db(y, yf[s, : m * ch]) >= 90.0
+    strict.close()
+    fast.close()
