@@ -281,7 +281,9 @@ def ours(args):
     kernel_used = {0: "auto", 1: "strict", 2: "tiled", 3: "tensor"}[batch.last_kernel()]
 
     # ---- roofline of the FIR kernel ----
-    fp32_peak = L.spxb_measure_fp32_peak(8192)
+    # --lean: no auxiliary kernels (FFMA peak probe, device-copy floor), so that an ncu launch list
+    # of the command holds the step's own kernels only
+    fp32_peak = 148 * 128 * 2 * 1.965e9 if args.lean else L.spxb_measure_fp32_peak(8192)
     flops_per_launch = out_samples_step * 2.0 * N
     t_launch = sec / K
     bytes_per_launch = (out_samples_step * 2.0 + S * n * ch * 2.0 + 2.0 * S * ch * (N - 1) * 2.0)
@@ -315,6 +317,8 @@ def ours(args):
     # is dominated by per-launch latency, not by HBM -- a practical floor for one step.
     copy_floor = None
     try:
+        if args.lean:
+            raise RuntimeError("skipped (--lean)")
         half = int(bytes_per_launch // 2) // 16 * 16
         c_src = torch.empty((8, half), dtype=torch.uint8, device="cuda")
         c_dst = torch.empty_like(c_src)
@@ -483,6 +487,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "strict", "tiled", "tensor"])
     ap.add_argument("--min-seconds", type=float, default=1.0, help="clock-sampling window for the timed regions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lean", action="store_true", help="skip the auxiliary probes (FFMA peak, device-copy floor)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -138,18 +138,35 @@ class SpeexResampler:
     # -- batched entry (north star: processChunks) -------------------------------
     @staticmethod
     def processChunks(resamplers: Sequence["SpeexResampler"], chunks: Sequence) -> List[bytes]:
-        """Resample chunk i with resampler i, all streams in one launch. The result equals
-        ``[r.processChunk(c) for r, c in zip(resamplers, chunks)]``. The resamplers must
-        share (channels, inRate, outRate, quality); the first call binds them to one
-        device batch, later calls must pass the same list."""
+        """Resample chunk i with resampler i in as few launches as possible. The result equals
+        ``[r.processChunk(c) for r, c in zip(resamplers, chunks)]``. Streams that share
+        (channels, inRate, outRate, quality) form one device batch (one launch); the first call
+        binds them to it, later calls must pass the same resamplers in the same order."""
         if len(resamplers) != len(chunks):
             raise ValueError("processChunks needs one chunk per resampler")
         if not resamplers:
             return []
-        group = resamplers[0]._group
-        if group is None or group.members is not resamplers and list(group.members) != list(resamplers):
-            group = StreamBatch._adopt(resamplers)
-        return group.processChunks(chunks)
+        # group by configuration, keeping the caller's order inside each group
+        by_config = {}
+        for idx, r in enumerate(resamplers):
+            by_config.setdefault((r.channels, r.inRate, r.outRate, r.quality), []).append(idx)
+        if len(by_config) == 1:
+            members = resamplers
+            idx_lists = [None]
+        else:
+            idx_lists = list(by_config.values())
+        out: List[bytes] = [b""] * len(resamplers)
+        for idx in idx_lists:
+            members = resamplers if idx is None else [resamplers[k] for k in idx]
+            group = members[0]._group
+            if group is None or (group.members is not members and list(group.members) != list(members)):
+                group = StreamBatch._adopt(members)
+            res = group.processChunks(chunks if idx is None else [chunks[k] for k in idx])
+            if idx is None:
+                return res
+            for k, y in zip(idx, res):
+                out[k] = y
+        return out
 
 
 class StreamBatch:

@@ -59,3 +59,14 @@ def test_typescript_surface_matches_the_reference_contract():
     assert re.search(r"Math\.trunc\(this\._outBufferSize / this\.channels / BYTES_PER_SAMPLE\)", ts)
     py = open(os.path.join(ROOT, "node_speex_resampler_b200", "resampler.py")).read()
     assert "math.ceil(nbytes * self.outRate / self.inRate)" in py
+
+
+def test_addon_selftest_builds_and_fails_loudly_without_a_gpu():
+    """the addon linked with the in-process N-API stand-in (bindings/node/test/fake_napi.c); the
+    GPU suite runs it for real (tests/test_parity_gpu.py::test_node_addon_executes_like_the_mirror)"""
+    import __graft_entry__ as G
+    exe = G.build_node_addon_selftest()
+    import node_speex_resampler_b200 as pkg
+    if pkg.lib().spxb_device_count() <= 0:
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 3 and "no CUDA device" in r.stdout

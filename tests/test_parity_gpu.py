@@ -550,3 +550,65 @@ def test_gpu_matches_the_shipped_wasm_module(c):
                 assert O.snr_db(y, yf[s, : m * ch]) >= 90.0
     strict.close()
     fast.close()
+
+
+def test_process_chunks_groups_mixed_configurations():
+    """processChunks over resamplers of different (channels, rates, quality): each configuration
+    becomes one device batch; results equal per-stream processChunk, in the caller's order"""
+    cfgs = [(2, 44100, 48000, 7), (1, 48000, 16000, 10), (2, 44100, 48000, 7), (1, 24000, 48000, 5),
+            (1, 48000, 16000, 10), (2, 44100, 48000, 7)]
+    rs = [SpeexResampler(*c) for c in cfgs]
+    for r in rs:
+        r.kernel = KERNEL_STRICT
+    refs = [O.OracleResampler(*c) for c in cfgs]
+    for k in range(3):
+        chunks = [synth_pcm(1, c[0], 480 + 7 * s, c[1], seed=800 + 10 * k + s)[0].tobytes()
+                  for s, c in enumerate(cfgs)]
+        got = SpeexResampler.processChunks(rs, chunks)
+        for s in range(len(cfgs)):
+            assert got[s] == refs[s].processChunk(chunks[s]), (k, s)
+
+
+def test_node_addon_executes_like_the_mirror():
+    """bindings/node/src/addon.c EXECUTED (through the in-process N-API stand-in, no Node in this
+    image) with the calls index.ts makes -- init, process, batchCreate/Process/Adopt, the two error
+    paths -- must return byte for byte what the Python mirror returns for the same inputs."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bindings", "node", "test",
+                       "addon_selftest")
+    if not os.path.exists(exe):
+        pytest.skip("addon_selftest not built (python -c 'import __graft_entry__ as g; g.build()')")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = dict((ln.split()[0], ln.split(None, 1)[1]) for ln in r.stdout.strip().split("\n") if " " in ln)
+    assert lines["init_error"] == "1 Invalid argument."
+    assert lines["align_error"] == "1 Chunk length should be a multiple of channels * 2 bytes"
+
+    ch, i, o, q = 2, 44100, 48000, 7
+
+    def pcm(s, first_frame, frames):
+        k = (np.arange(frames * ch, dtype=np.uint64) + first_frame * ch + 1) * 2654435761 + s * 40503
+        v = (k & 0xFFFFFFFF).astype(np.uint32)
+        v ^= v >> np.uint32(15)
+        return ((v & 0x3FFF).astype(np.int32) - 8192).astype(np.int16).tobytes()
+
+    def line(y):
+        return f"{len(y) // (ch * 2)} {O.fnv1a64(y)}"
+
+    single = SpeexResampler(ch, i, o, q)
+    pos = 0
+    for k, n in enumerate((882, 441, 7, 882)):
+        assert lines[f"single{k}"] == line(single.processChunk(pcm(0, pos, n))), k
+        pos += n
+    rs = [SpeexResampler(ch, i, o, q) for _ in range(8)]
+    posb = [0] * 8
+    for tag, frames in (("batchA", lambda s: 882), ("batchB", lambda s: 300 + 41 * s)):
+        chunks = [pcm(10 + s, posb[s], frames(s)) for s in range(8)]
+        for s in range(8):
+            posb[s] += frames(s)
+        got = SpeexResampler.processChunks(rs, chunks)
+        for s in range(8):
+            assert lines[f"{tag}{s}"] == line(got[s]), (tag, s)
+    pair = [SpeexResampler(ch, i, o, q), single]
+    got = SpeexResampler.processChunks(pair, [pcm(30, 0, 882), pcm(0, pos, 882)])
+    assert lines["adopt0"] == line(got[0]) and lines["adopt1"] == line(got[1])
