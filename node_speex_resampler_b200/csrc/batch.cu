@@ -63,6 +63,8 @@ struct Slot {
   size_t h_out_cap = 0;
   StreamCall *h_calls = nullptr;  // pinned, n_streams
   StreamCall *d_calls = nullptr;
+  uint32_t *h_ids = nullptr;      // pinned, n_streams: stream-id lists of a ragged call's cohorts
+  uint32_t *d_ids = nullptr;
   cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_done = nullptr;
   bool busy = false;
   uint64_t ticket = 0;
@@ -236,9 +238,15 @@ static int retire_slot(spxb_batch *b, Slot &sl) {
 
 // Build the kernel arguments for a call whose per-stream plans are already decided, launch
 // the FIR (+ fused history slide) on the compute stream and flip the history ping-pong.
+struct RaggedHost {  // host copy of a ragged call's per-stream plans + this slot's id-list buffers
+  const StreamCall *calls = nullptr;
+  uint32_t *h_ids = nullptr, *d_ids = nullptr;
+};
+static int launch_grouped(spxb_batch *b, const CallArgs &a, const RaggedHost &rh, uint32_t *launches, bool *done);
+
 static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elems, int16_t *d_out,
                        size_t out_stride_elems, const StreamCall *d_calls,
-                       const StreamCall &uniform, uint32_t max_n_out) {
+                       const StreamCall &uniform, uint32_t max_n_out, const RaggedHost &rh = RaggedHost()) {
   CallArgs a;
   a.filt.num = b->spec.num;
   a.filt.den = b->spec.den;
@@ -269,6 +277,8 @@ static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elem
   a.uniform = uniform;
   a.max_n_out = max_n_out;
   a.fmt = !b->f32 ? 0u : (b->io_words == 2 ? 2u : 1u);
+  a.ids = nullptr;
+  a.n_ids = 0;
 
   uint32_t launches = 0;
   cudaError_t ce = cudaSuccess;
@@ -278,7 +288,14 @@ static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elem
   // float batches run the strict kernel only (the fast families are built around int16 history)
   const bool want_tensor = !b->f32 && (pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TENSOR);
   const bool want_tiled = !b->f32 && (pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TILED);
-  if (want_tensor && max_n_out != 0 && umma_prepare(b->umma, a, b->s_compute, &ce)) {
+  bool grouped = false;
+  if (want_tensor && d_calls && rh.calls && max_n_out != 0 && b->umma && !b->dry_run) {
+    // ragged batch: groups of streams that share one position run on the tensor kernel
+    if (int e = launch_grouped(b, a, rh, &launches, &grouped)) return e;
+  }
+  if (grouped) {
+    used = SPXB_KERNEL_TENSOR;
+  } else if (want_tensor && max_n_out != 0 && umma_prepare(b->umma, a, b->s_compute, &ce)) {
     if (b->dry_run) launches += 1;
     else ce = launch_umma(b->umma, a, b->s_compute, &launches);
     used = SPXB_KERNEL_TENSOR;
@@ -305,6 +322,106 @@ static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elem
   b->last_kernel = used;
   b->counters.kernel_launches += launches;
   b->hist_cur ^= 1;
+  return 0;
+}
+
+// A ragged batch is rarely random: streams that were fed the same chunk sizes since they started
+// move in cohorts that share (last_sample, samp_frac_num) and the call's lengths. Cohorts of at
+// least kMinCohort streams (at most kMaxCohorts of them) each get one tensor-kernel launch over
+// their stream-id list; whatever is left goes to the strict kernel in one launch over its list.
+// *done stays false (nothing launched) when no cohort qualifies; the caller then takes the
+// whole batch to the strict kernel as before.
+static int launch_grouped(spxb_batch *b, const CallArgs &a, const RaggedHost &rh, uint32_t *launches, bool *done) {
+  constexpr uint32_t kMinCohort = 32, kMaxCohorts = 8;
+  *done = false;
+  const uint32_t S = b->n_streams;
+  const StreamCall *h_calls = rh.calls;
+  struct Cohort {
+    StreamCall call;
+    std::vector<uint32_t> ids;
+  };
+  auto same = [](const StreamCall &x, const StreamCall &y) { return std::memcmp(&x, &y, sizeof(StreamCall)) == 0; };
+  std::vector<Cohort> cohorts;
+  std::unordered_map<uint64_t, std::vector<uint32_t>> by_hash;  // plan hash -> cohort indices
+  uint32_t last = 0xffffffffu;  // neighbours are usually in the same cohort
+  for (uint32_t s = 0; s < S; ++s) {
+    // (streams that sit this call out form a cohort too: their history still has to cross to the
+    // other half of the ping-pong, which the strict launch over the remainder does)
+    const StreamCall &c = h_calls[s];
+    if (last != 0xffffffffu && same(cohorts[last].call, c)) {
+      cohorts[last].ids.push_back(s);
+      continue;
+    }
+    uint64_t h = 0xcbf29ce484222325ull;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(&c);
+    for (size_t k = 0; k < sizeof(StreamCall) / 4; ++k) h = (h ^ w[k]) * 0x100000001b3ull;
+    std::vector<uint32_t> &cands = by_hash[h];
+    uint32_t found = 0xffffffffu;
+    for (uint32_t k : cands)
+      if (same(cohorts[k].call, c)) found = k;
+    if (found == 0xffffffffu) {
+      found = static_cast<uint32_t>(cohorts.size());
+      cands.push_back(found);
+      cohorts.push_back(Cohort{c, {}});
+      if (cohorts.size() > 4 * kMaxCohorts + S / kMinCohort) return 0;  // too fragmented to be worth grouping
+    }
+    cohorts[found].ids.push_back(s);
+    last = found;
+  }
+  std::vector<uint32_t> big;
+  for (uint32_t k = 0; k < cohorts.size(); ++k)
+    if (cohorts[k].ids.size() >= kMinCohort && cohorts[k].call.n_out != 0) big.push_back(k);
+  if (big.empty() || big.size() > kMaxCohorts) return 0;
+  uint32_t *h_ids = rh.h_ids, *d_ids = rh.d_ids;
+  // layout of the id list: [cohort big[0]] [cohort big[1]] ... [everything else]
+  std::vector<uint32_t> offset(big.size() + 1, 0);
+  uint32_t n = 0;
+  std::vector<bool> is_big(cohorts.size(), false);
+  for (uint32_t k = 0; k < big.size(); ++k) {
+    is_big[big[k]] = true;
+    offset[k] = n;
+    for (uint32_t s : cohorts[big[k]].ids) h_ids[n++] = s;
+  }
+  offset[big.size()] = n;
+  for (uint32_t k = 0; k < cohorts.size(); ++k)
+    if (!is_big[k])
+      for (uint32_t s : cohorts[k].ids) h_ids[n++] = s;
+  const uint32_t n_listed = n;
+  SPXB_CUDA(cudaMemcpyAsync(d_ids, h_ids, n_listed * sizeof(uint32_t), cudaMemcpyHostToDevice, b->s_compute));
+  b->counters.h2d_bytes += n_listed * sizeof(uint32_t);
+
+  std::vector<uint32_t> fallback;  // cohorts the tensor planner turned down
+  for (uint32_t k = 0; k < big.size(); ++k) {
+    CallArgs g = a;
+    g.per_stream = nullptr;
+    g.uniform = cohorts[big[k]].call;
+    g.max_n_out = g.uniform.n_out;
+    g.ids = d_ids + offset[k];
+    g.n_ids = offset[k + 1] - offset[k];
+    cudaError_t ce = cudaSuccess;
+    if (umma_prepare(b->umma, g, b->s_compute, &ce)) {
+      ce = launch_umma(b->umma, g, b->s_compute, launches);
+    } else if (ce == cudaSuccess) {
+      // not covered (e.g. the tile pool is full): the strict kernel takes this cohort too
+      g.per_stream = a.per_stream;
+      ce = launch_strict(g, b->s_compute, launches);
+    }
+    if (ce != cudaSuccess) {
+      set_error(std::string("kernel launch (cohort): ") + cudaGetErrorString(ce));
+      return RESAMPLER_ERR_BAD_STATE;
+    }
+  }
+  if (n_listed > offset[big.size()]) {
+    CallArgs r = a;
+    r.ids = d_ids + offset[big.size()];
+    r.n_ids = n_listed - offset[big.size()];
+    const cudaError_t ce = launch_strict(r, b->s_compute, launches);
+    if (ce != cudaSuccess) {
+      set_error(std::string("kernel launch (remainder): ") + cudaGetErrorString(ce));
+      return RESAMPLER_ERR_BAD_STATE;
+    }
+  }
+  *done = true;
   return 0;
 }
 
@@ -382,12 +499,15 @@ static void free_batch(spxb_batch *b) {
     if (sl.h_out) cudaFreeHost(sl.h_out);
     if (sl.h_calls) cudaFreeHost(sl.h_calls);
     if (sl.d_calls) cudaFree(sl.d_calls);
+    if (sl.h_ids) cudaFreeHost(sl.h_ids);
+    if (sl.d_ids) cudaFree(sl.d_ids);
     if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
     if (sl.ev_kernel) cudaEventDestroy(sl.ev_kernel);
     if (sl.ev_done) cudaEventDestroy(sl.ev_done);
   }
   for (auto &kv : b->ring_graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+
   if (b->ev_state) cudaEventDestroy(b->ev_state);
   if (b->d_table) cudaFree(b->d_table);
   if (b->d_taps) cudaFree(b->d_taps);
@@ -508,6 +628,8 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
   if (!sl.h_calls) {
     SPXB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_calls), S * sizeof(StreamCall), cudaHostAllocDefault));
     SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&sl.d_calls), S * sizeof(StreamCall)));
+    SPXB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_ids), S * sizeof(uint32_t), cudaHostAllocDefault));
+    SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&sl.d_ids), S * sizeof(uint32_t)));
   }
   Decided d = decide(b, in_frames, out_frames, sl.h_calls);
 
@@ -570,7 +692,8 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
   // ---- kernel ----
   SPXB_CUDA(cudaStreamWaitEvent(b->s_compute, sl.ev_h2d, 0));
   if (int e = launch_call(b, sl.d_in, dev_in_stride, sl.d_out, dev_out_stride,
-                          d.uniform ? nullptr : sl.d_calls, d.uni, d.max_n_out))
+                          d.uniform ? nullptr : sl.d_calls, d.uni, d.max_n_out,
+                          d.uniform ? RaggedHost() : RaggedHost{sl.h_calls, sl.h_ids, sl.d_ids}))
     return e;
   SPXB_CUDA(cudaEventRecord(sl.ev_kernel, b->s_compute));
 
@@ -759,6 +882,8 @@ int spxb_batch_process_device(spxb_batch *b, const int16_t *d_in, size_t in_stri
   if (!sl.h_calls) {
     SPXB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_calls), S * sizeof(StreamCall), cudaHostAllocDefault));
     SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&sl.d_calls), S * sizeof(StreamCall)));
+    SPXB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_ids), S * sizeof(uint32_t), cudaHostAllocDefault));
+    SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&sl.d_ids), S * sizeof(uint32_t)));
   }
   Decided d = decide(b, in_frames, out_frames, sl.h_calls);
   if (!d.any_work) return 0;
@@ -771,7 +896,8 @@ int spxb_batch_process_device(spxb_batch *b, const int16_t *d_in, size_t in_stri
   }
   int e = launch_call(b, d_in, in_stride_frames * b->channels * b->io_words, d_out,
                       out_stride_frames * b->channels * b->io_words,
-                      d.uniform ? nullptr : sl.d_calls, d.uni, d.max_n_out);
+                      d.uniform ? nullptr : sl.d_calls, d.uni, d.max_n_out,
+                      d.uniform ? RaggedHost() : RaggedHost{sl.h_calls, sl.h_ids, sl.d_ids});
   if (e) return e;
   if (!d.uniform) SPXB_CUDA(cudaEventRecord(sl.ev_done, b->s_compute));
   b->counters.calls += 1;

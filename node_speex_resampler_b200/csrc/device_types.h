@@ -67,6 +67,11 @@ struct CallArgs {
   //   1  float history, int16 in/out                 (a state that has seen float calls)
   //   2  float history, float in/out, no rounding    (speex_resampler_process_interleaved_float)
   uint32_t fmt;
+  // Optional subset: when ids != nullptr the launch covers streams ids[0 .. n_ids) only (device
+  // array), in that order, instead of 0 .. n_streams. Used to run the groups of a ragged batch
+  // that share one position on the tensor kernel, and the remainder on the strict kernel.
+  const uint32_t *ids;
+  uint32_t n_ids;
 };
 
 }  // namespace spxb

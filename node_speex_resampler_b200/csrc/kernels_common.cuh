@@ -11,6 +11,10 @@ __device__ __forceinline__ StreamCall load_call(const CallArgs &a, uint32_t s) {
   return a.per_stream ? a.per_stream[s] : a.uniform;
 }
 
+// streams a launch covers, and the i-th of them (CallArgs::ids)
+__device__ __forceinline__ uint32_t launch_rows(const CallArgs &a) { return a.ids ? a.n_ids : a.n_streams; }
+__device__ __forceinline__ uint32_t launch_stream(const CallArgs &a, uint32_t i) { return a.ids ? a.ids[i] : i; }
+
 // X~[f] of (stream s, channel c): history for f < 0, this call's input for 0 <= f < n_in,
 // 0 beyond (only ever multiplied by zero taps or discarded).
 __device__ __forceinline__ int fetch_sample(const CallArgs &a, uint32_t s, int f, uint32_t c,
@@ -132,8 +136,9 @@ template <int FMT>
 __device__ __forceinline__ void history_block_f(const CallArgs &a, uint32_t blk) {
   const uint32_t hist_elems = a.hist_frames * a.channels;
   const uint32_t per_stream = (hist_elems + blockDim.x - 1) / blockDim.x;
-  const uint32_t s = blk / per_stream;
-  if (s >= a.n_streams) return;
+  const uint32_t row = blk / per_stream;
+  if (row >= launch_rows(a)) return;
+  const uint32_t s = launch_stream(a, row);
   const uint32_t e = (blk % per_stream) * blockDim.x + threadIdx.x;
   const StreamCall sc = load_call(a, s);
   if (e < hist_elems) slide_history_elem_f<FMT>(a, s, sc, e);

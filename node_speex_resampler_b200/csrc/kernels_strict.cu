@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kStrictThreads)
     history_block_f<FMT>(a, blockIdx.x - fir_blocks);
     return;
   }
-  const uint32_t s = blockIdx.x / blocks_per_stream;
+  const uint32_t s = launch_stream(a, blockIdx.x / blocks_per_stream);
   const uint32_t e = (blockIdx.x % blocks_per_stream) * kStrictThreads + threadIdx.x;
   const StreamCall sc = load_call(a, s);
   const uint32_t m = e / a.channels;
@@ -123,13 +123,13 @@ __global__ void __launch_bounds__(kStrictThreads)
 
 uint32_t hist_blocks(const CallArgs &a, uint32_t threads) {
   const uint32_t hist_elems = a.hist_frames * a.channels;
-  return a.n_streams * ((hist_elems + threads - 1) / threads);
+  return (a.ids ? a.n_ids : a.n_streams) * ((hist_elems + threads - 1) / threads);
 }
 
 cudaError_t launch_strict(const CallArgs &a, cudaStream_t stream, uint32_t *launches) {
   const uint64_t elems = static_cast<uint64_t>(a.max_n_out) * a.channels;
   const uint32_t bps = static_cast<uint32_t>((elems + kStrictThreads - 1) / kStrictThreads);
-  const uint64_t fir_blocks64 = static_cast<uint64_t>(a.n_streams) * bps;
+  const uint64_t fir_blocks64 = static_cast<uint64_t>(a.ids ? a.n_ids : a.n_streams) * bps;
   const uint64_t total = fir_blocks64 + hist_blocks(a, kStrictThreads);
   if (total == 0) return cudaSuccess;
   if (total > 0x7fffffffull) return cudaErrorInvalidConfiguration;

@@ -185,7 +185,7 @@ __device__ __forceinline__ void slide_rows(const CallArgs &a, uint32_t step, uin
       V val[4][4];
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        const size_t s = first + static_cast<size_t>(k0 + kk) * step;
+        const size_t s = k0 + kk < n_mine ? launch_stream(a, first + (k0 + kk) * step) : 0;
         const int16_t *hsrc = a.hist_src + s * a.hist_stride;
         const int16_t *isrc = a.in + s * a.in_stride;
 #pragma unroll
@@ -198,7 +198,7 @@ __device__ __forceinline__ void slide_rows(const CallArgs &a, uint32_t step, uin
       }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        const size_t s = first + static_cast<size_t>(k0 + kk) * step;
+        const size_t s = k0 + kk < n_mine ? launch_stream(a, first + (k0 + kk) * step) : 0;
         int16_t *hdst = a.hist_dst + s * a.hist_stride;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   const uint32_t n_chunks = 2 * u.ksteps;
   const uint32_t n_iters = (n_chunks + kStageChunks - 1) / kStageChunks;
   const uint32_t S = u.stages;
+  const uint32_t n_rows = launch_rows(a);  // streams this launch covers (a subset when a.ids is set)
   const uint32_t cluster = FAST ? 1u : u.cluster;
   const uint32_t cta_rank = cluster > 1 ? cluster_ctarank() : 0u;
   const uint16_t cluster_mask = static_cast<uint16_t>((1u << cluster) - 1u);
@@ -326,14 +327,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   int f_next = kf0 + conv_p * FPI;     // its first frame: history for f < 0, this call's input after
   auto input_ptr = [&](int i, int f) {
     const uint32_t sg = g * kStreams + static_cast<uint32_t>((4 * (warp & 7) + i) * SPI + lane / PPS);
-    const size_t r = sg < a.n_streams ? sg : 0;
+    const size_t r = launch_stream(a, sg < n_rows ? sg : 0);
     return reinterpret_cast<const char *>(a.in + r * a.in_stride + static_cast<ptrdiff_t>(f) * CH);
   };
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
     const uint32_t sl = static_cast<uint32_t>((4 * (warp & 7) + i) * SPI + lane / PPS);
     const uint32_t sg = g * kStreams + sl;
-    const size_t r = sg < a.n_streams ? sg : 0;
+    const size_t r = launch_stream(a, sg < n_rows ? sg : 0);
     cur[i] = f_next < 0 ? reinterpret_cast<const char *>(a.hist_src + r * a.hist_stride +
                                                          (static_cast<ptrdiff_t>(a.hist_frames) + f_next) * CH)
                         : input_ptr(i, f_next);
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
       if (hist_elems >= 512 && shift % 8 == 0 && in_align == 16) {
         const uint32_t first = g * kStreams + t;
         const uint32_t in_group = t < static_cast<uint32_t>(kStreams) ? (kStreams - t + u.n_tiles - 1) / u.n_tiles : 0u;
-        const uint32_t in_batch = first < a.n_streams ? (a.n_streams - first + u.n_tiles - 1) / u.n_tiles : 0u;
+        const uint32_t in_batch = first < n_rows ? (n_rows - first + u.n_tiles - 1) / u.n_tiles : 0u;
         slide_rows<uint4>(a, u.n_tiles, first, min(in_group, in_batch), hist_elems, shift, lane, &slide_next);
       }
     }
@@ -485,8 +486,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const uint32_t sl_out = CH == 2 ? row >> 1 : row, ch_out = CH == 2 ? (row & 1u) : 0u;
     const uint32_t s_out = g * kStreams + sl_out;
-    const bool live_out = s_out < a.n_streams;
-    int16_t *out_row = a.out + static_cast<size_t>(live_out ? s_out : 0) * a.out_stride + static_cast<size_t>(m0) * CH;
+    const bool live_out = s_out < n_rows;
+    int16_t *out_row = a.out + static_cast<size_t>(launch_stream(a, live_out ? s_out : 0)) * a.out_stride +
+                       static_cast<size_t>(m0) * CH;
     const uint32_t out_bits = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(a.out)) |
                               (static_cast<uint32_t>(a.out_stride) * 2u);
     const int out_align = FAST ? 16 : (out_bits & 15u) == 0 ? 16 : (out_bits & 3u) == 0 ? 4 : 2;
@@ -629,14 +631,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     // streams of this CTA: sl = t + k * n_tiles while the stream exists
     const uint32_t first = g * kStreams + t;
     const uint32_t in_group = t < static_cast<uint32_t>(kStreams) ? (kStreams - t + u.n_tiles - 1) / u.n_tiles : 0u;
-    const uint32_t in_batch = first < a.n_streams ? (a.n_streams - first + u.n_tiles - 1) / u.n_tiles : 0u;
+    const uint32_t in_batch = first < n_rows ? (n_rows - first + u.n_tiles - 1) / u.n_tiles : 0u;
     const uint32_t n_mine = min(in_group, in_batch);
     if (vw == 8) slide_rows<uint4>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
     else if (vw == 4) slide_rows<uint2>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
     else if (vw == 2) slide_rows<uint32_t>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
     else slide_rows<uint16_t>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
     for (uint32_t k = lane; k < n_mine; k += 32) {
-      const size_t s = first + static_cast<size_t>(k) * u.n_tiles;
+      const size_t s = launch_stream(a, first + k * u.n_tiles);
       a.last_sample[s] = sc.ls1;
       a.samp_frac[s] = sc.frac1;
     }
@@ -849,7 +851,8 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
   if ((reinterpret_cast<uintptr_t>(a.hist_src) & 15) != 0 || a.hist_stride % 8 != 0 || a.hist_frames % 16 != 0)
     return false;
   if (a.uniform.n_in > 0x3fffffffu || a.uniform.ls0 > 0x3fffffff || a.uniform.ls0 < 0) return false;
-  const uint32_t n_groups = (a.n_streams * a.channels + kUmmaRows - 1) / kUmmaRows;
+  const uint32_t n_rows = a.ids ? a.n_ids : a.n_streams;
+  const uint32_t n_groups = (n_rows * a.channels + kUmmaRows - 1) / kUmmaRows;
   const StreamCall &sc = a.uniform;
   if (c->memo && c->m_ls0 == sc.ls0 && c->m_frac0 == sc.frac0 && c->m_n_out == sc.n_out &&
       c->m_hist_frames == a.hist_frames && c->m_groups == n_groups) {

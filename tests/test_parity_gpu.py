@@ -612,3 +612,44 @@ def test_node_addon_executes_like_the_mirror():
     pair = [SpeexResampler(ch, i, o, q), single]
     got = SpeexResampler.processChunks(pair, [pcm(30, 0, 882), pcm(0, pos, 882)])
     assert lines["adopt0"] == line(got[0]) and lines["adopt1"] == line(got[1])
+
+
+def test_ragged_batch_cohorts_take_the_tensor_kernel():
+    """A batch whose streams move in a few cohorts (same chunk sizes, different start times): each
+    cohort of >= 32 streams gets a tensor-kernel launch over its stream-id list, the stragglers
+    (and streams sitting a call out) one strict launch. Every stream must match its own oracle
+    (<= 1 LSB; stragglers bit-exact) and carry its state across calls."""
+    ch, i, o, q = 2, 44100, 48000, 5
+    S = 150
+    b = StreamBatch(S, ch, i, o, q)
+    refs = [O.OracleResampler(ch, i, o, q) for _ in range(S)]
+    cohort = np.zeros(S, np.int64)
+    cohort[40:110] = 1          # a second cohort, three calls behind the first
+    cohort[110:145] = 2         # a third one with another chunk size
+    cohort[145:] = 3            # five stragglers: ragged, strict kernel
+    rng = np.random.default_rng(8)
+    launches0 = b.counters().kernel_launches
+    for k in range(7):
+        n_in = np.zeros(S, np.uint32)
+        n_in[cohort == 0] = 1000
+        n_in[cohort == 1] = 1000 if k >= 3 else 0
+        n_in[cohort == 2] = 777
+        n_in[cohort == 3] = rng.integers(1, 900, size=5)
+        cap = np.ceil(n_in * (o / i)).astype(np.uint32) + 1
+        pcm = synth_pcm(S, ch, 1000, i, seed=600 + k)
+        out, used, made = b.process(pcm, n_in, cap)
+        assert b.last_kernel() == KERNEL_TENSOR
+        for s in range(S):
+            y, u, m = refs[s].process(pcm[s, : n_in[s] * ch], int(cap[s]))
+            assert (u, m) == (int(used[s]), int(made[s])), (k, s)
+            d = np.abs(y.astype(np.int32) - out[s, : m * ch].astype(np.int32))
+            assert d.max(initial=0) <= (0 if cohort[s] == 3 else 1), (k, s, int(d.max(initial=0)))
+    # cohort launches + one strict launch per call, never one launch per stream
+    assert b.counters().kernel_launches - launches0 <= 7 * 4
+    # a uniform call afterwards goes back to a single launch
+    c0 = b.counters().kernel_launches
+    b2 = StreamBatch(64, ch, i, o, q)
+    b2.process(synth_pcm(64, ch, 500, i, seed=1), 500, 600)
+    assert b2.counters().kernel_launches == 1 and c0 > 0
+    b.close()
+    b2.close()
