@@ -106,9 +106,15 @@ struct UmmaArgs {
 #define SPXB_DEBUG_BITS(u) 0u
 #endif
 constexpr int kTraceSlots = 32;
-__device__ __forceinline__ void trace_mark(const UmmaArgs &u, int slot) {
-  if (u.trace) u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + slot] = static_cast<unsigned long long>(clock64());
+// The timeline marks exist only in the PACED instantiations of the kernel (see umma_fir_kernel):
+// inside it SPXB_TRACE_PTR(u) is u.trace, elsewhere a compile-time null and the marks vanish.
+#define SPXB_TRACE_PTR(u) (PACED ? (u).trace : static_cast<unsigned long long *>(nullptr))
+template <bool PACED>
+__device__ __forceinline__ void trace_mark_t(const UmmaArgs &u, int slot) {
+  if (SPXB_TRACE_PTR(u))
+    SPXB_TRACE_PTR(u)[static_cast<size_t>(blockIdx.x) * kTraceSlots + slot] = static_cast<unsigned long long>(clock64());
 }
+#define trace_mark(u, slot) trace_mark_t<PACED>(u, slot)
 
 // 16 bytes of one stream's input, sample by sample: the first `n` int16 samples at p, zeros after
 // (kept out of line: only the item holding the end of a row, or 2-byte aligned rows, come here)
@@ -169,23 +175,33 @@ __device__ __forceinline__ void combine16(const uint32_t (&p0)[16], const uint32
   }
 }
 
-// History slide of the streams first, first + step, ... (n_mine of them) by one warp: vectors of
-// type V (the widest the shift and the row alignment allow), four streams x four vectors per lane
-// loaded before any store so that 16 loads per lane are in flight.
-template <typename V>
-__device__ __forceinline__ void slide_rows(const CallArgs &a, uint32_t step, uint32_t first, uint32_t n_mine,
-                                           uint32_t hist_elems, size_t shift, int lane, uint32_t *next_unit) {
+// History slide of the streams first, first + step, ... (n_total of them) by whichever warps are
+// free, claiming from one packed counter (low half: streams taken from the front, high half:
+// streams taken from the back). The history warp takes four streams at a time from the front
+// (four streams x four vectors of type V -- the widest the shift and the row alignment allow --
+// per lane loaded before any store: 16 loads in flight); converter warps that have run out of
+// stages take single streams from the back. The history warp's loads queue behind the converters'
+// in the SM's memory pipeline, and by how much depends on the build (identical code has been
+// measured 2x apart), so without the second end it can become the straggler the whole CTA waits for.
+template <typename V, bool IDS, bool FRONT>
+__device__ __forceinline__ void slide_rows(const CallArgs &a, uint32_t step, uint32_t first, uint32_t n_total,
+                                           uint32_t hist_elems, size_t shift, int lane, uint32_t *claims) {
   constexpr uint32_t VW = sizeof(V) / 2;  // int16 elements per vector
   for (;;) {
-    uint32_t k0 = 0;
-    if (lane == 0) k0 = atomicAdd(next_unit, 4u);
-    k0 = __shfl_sync(0xffffffffu, k0, 0);
-    if (k0 >= n_mine) break;
+    uint32_t old = 0;
+    if (lane == 0) old = atomicAdd(claims, FRONT ? 4u : 0x10000u);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    const uint32_t from_front = old & 0xffffu, from_back = old >> 16;
+    if (from_front + from_back >= n_total) break;
+    // this unit: streams k0 .. n_mine-1
+    const uint32_t k0 = FRONT ? from_front : n_total - 1 - from_back;
+    const uint32_t n_mine = FRONT ? min(n_total - from_back, from_front + 4u) : k0 + 1;
     for (uint32_t e0 = lane * VW; e0 < hist_elems; e0 += 32 * VW * 4) {
       V val[4][4];
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        const size_t s = k0 + kk < n_mine ? launch_stream(a, first + (k0 + kk) * step) : 0;
+        const size_t s = !IDS ? first + static_cast<size_t>(k0 + kk) * step
+                              : k0 + kk < n_mine ? a.ids[first + (k0 + kk) * step] : 0;
         const int16_t *hsrc = a.hist_src + s * a.hist_stride;
         const int16_t *isrc = a.in + s * a.in_stride;
 #pragma unroll
@@ -198,7 +214,8 @@ __device__ __forceinline__ void slide_rows(const CallArgs &a, uint32_t step, uin
       }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        const size_t s = k0 + kk < n_mine ? launch_stream(a, first + (k0 + kk) * step) : 0;
+        const size_t s = !IDS ? first + static_cast<size_t>(k0 + kk) * step
+                              : k0 + kk < n_mine ? a.ids[first + (k0 + kk) * step] : 0;
         int16_t *hdst = a.hist_dst + s * a.hist_stride;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -214,7 +231,17 @@ __device__ __forceinline__ void slide_rows(const CallArgs &a, uint32_t step, uin
 // cluster: the instantiation every BASELINE shape takes. It drops the narrower load / store
 // variants and the multicast paths, which is worth having because warps of five roles run
 // different parts of this kernel at the same time and share one instruction cache.
-template <int CH, bool FAST>
+// IDS = the launch covers the stream subset a.ids[0 .. a.n_ids) (a cohort of a ragged batch); the
+// plain instantiation carries no indirection at all (it costs the long-filter shapes 25 %).
+// PACED = the instantiation for long K loops (more than kLeanStages stages). It is the kernel with
+// its timeline probes compiled in (never taken unless SPXB_UMMA_TRACE is set) and the converters
+// asking for the stage three ahead BEFORE they hand the current one over. Measured, same source
+// otherwise: the probes make each converter thread wait on its in-flight loads at four points per
+// stage, and on 13-16-stage loops (C4, C5) that pacing is worth 6 % -- without it the history warp
+// and the tap stream starve behind the converters' loads -- while on C3's 4-stage loop the lean
+// instantiation (no probes, stage handed over first) is 9 % faster (profiles/umma_paced_ab_r1.log).
+constexpr uint32_t kLeanStages = 8;
+template <int CH, bool FAST, bool IDS, bool PACED>
 __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a, const UmmaArgs u) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], acc_bar;
@@ -248,7 +275,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   const uint32_t n_chunks = 2 * u.ksteps;
   const uint32_t n_iters = (n_chunks + kStageChunks - 1) / kStageChunks;
   const uint32_t S = u.stages;
-  const uint32_t n_rows = launch_rows(a);  // streams this launch covers (a subset when a.ids is set)
+  const uint32_t n_rows = IDS ? a.n_ids : a.n_streams;  // streams this launch covers
+  auto stream_of = [&](uint32_t i) -> size_t { return IDS ? a.ids[i] : i; };
   const uint32_t cluster = FAST ? 1u : u.cluster;
   const uint32_t cta_rank = cluster > 1 ? cluster_ctarank() : 0u;
   const uint16_t cluster_mask = static_cast<uint16_t>((1u << cluster) - 1u);
@@ -263,13 +291,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) {
     trace_mark(u, 0);
-    if (u.trace) {
+    if (SPXB_TRACE_PTR(u)) {
       unsigned long long gt;
       uint32_t smid;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + 14] = gt;
-      u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + 16] = smid;
+      SPXB_TRACE_PTR(u)[static_cast<size_t>(blockIdx.x) * kTraceSlots + 14] = gt;
+      SPXB_TRACE_PTR(u)[static_cast<size_t>(blockIdx.x) * kTraceSlots + 16] = smid;
     }
   }
   // The tap-tile producer owns the barriers: it initialises them and has the first tap stages
@@ -327,14 +355,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   int f_next = kf0 + conv_p * FPI;     // its first frame: history for f < 0, this call's input after
   auto input_ptr = [&](int i, int f) {
     const uint32_t sg = g * kStreams + static_cast<uint32_t>((4 * (warp & 7) + i) * SPI + lane / PPS);
-    const size_t r = launch_stream(a, sg < n_rows ? sg : 0);
+    const size_t r = stream_of(sg < n_rows ? sg : 0);
     return reinterpret_cast<const char *>(a.in + r * a.in_stride + static_cast<ptrdiff_t>(f) * CH);
   };
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
     const uint32_t sl = static_cast<uint32_t>((4 * (warp & 7) + i) * SPI + lane / PPS);
     const uint32_t sg = g * kStreams + sl;
-    const size_t r = launch_stream(a, sg < n_rows ? sg : 0);
+    const size_t r = stream_of(sg < n_rows ? sg : 0);
     cur[i] = f_next < 0 ? reinterpret_cast<const char *>(a.hist_src + r * a.hist_stride +
                                                          (static_cast<ptrdiff_t>(a.hist_frames) + f_next) * CH)
                         : input_ptr(i, f_next);
@@ -432,17 +460,24 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     uint8_t *cstage = smem;
     auto stage_step = [&](uint32_t it, uint4 (&raw)[kItems]) {
       const uint32_t slot = cslot, par = cpar ^ 1u;
-      const bool tr = u.trace && tid == 0 && it == 6;
+      const bool tr = SPXB_TRACE_PTR(u) && tid == 0 && it == 6;
       if (tr) trace_mark(u, 17);
       mbar_wait(&empty_bar[slot], par ^ 1u);
       if (tr) trace_mark(u, 18);
       if (!(SPXB_DEBUG_BITS(u) & 4u)) convert_store(cstage, raw);
       if (tr) trace_mark(u, 19);
-      if (it + 3 < n_iters) fetch(raw);
-      if (tr) trace_mark(u, 10);
-      fence_proxy_async_smem();
-      mbar_arrive(&full_bar[slot]);
-      if (tr) trace_mark(u, 31);
+      if (PACED) {
+        if (it + 3 < n_iters) fetch(raw);
+        if (tr) trace_mark(u, 10);
+        fence_proxy_async_smem();
+        mbar_arrive(&full_bar[slot]);
+        if (tr) trace_mark(u, 31);
+      } else {
+        // short loops: the tensor core gets the stage first, then the loads for three stages ahead go out
+        fence_proxy_async_smem();
+        mbar_arrive(&full_bar[slot]);
+        if (it + 3 < n_iters) fetch(raw);
+      }
       cstage += stage_bytes;
       if (++cslot == S) {
         cslot = 0;
@@ -469,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
         const uint32_t first = g * kStreams + t;
         const uint32_t in_group = t < static_cast<uint32_t>(kStreams) ? (kStreams - t + u.n_tiles - 1) / u.n_tiles : 0u;
         const uint32_t in_batch = first < n_rows ? (n_rows - first + u.n_tiles - 1) / u.n_tiles : 0u;
-        slide_rows<uint4>(a, u.n_tiles, first, min(in_group, in_batch), hist_elems, shift, lane, &slide_next);
+        slide_rows<uint4, IDS, false>(a, u.n_tiles, first, min(in_group, in_batch), hist_elems, shift, lane, &slide_next);
       }
     }
 
@@ -487,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     const uint32_t sl_out = CH == 2 ? row >> 1 : row, ch_out = CH == 2 ? (row & 1u) : 0u;
     const uint32_t s_out = g * kStreams + sl_out;
     const bool live_out = s_out < n_rows;
-    int16_t *out_row = a.out + static_cast<size_t>(launch_stream(a, live_out ? s_out : 0)) * a.out_stride +
+    int16_t *out_row = a.out + stream_of(live_out ? s_out : 0) * a.out_stride +
                        static_cast<size_t>(m0) * CH;
     const uint32_t out_bits = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(a.out)) |
                               (static_cast<uint32_t>(a.out_stride) * 2u);
@@ -588,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     for (uint32_t it = 0; it < n_iters; ++it) {
       mbar_wait(&full_bar[slot], par);
       tc_fence_after_sync();
-      if (u.trace && lane == 0 && it < 12) trace_mark(u, 20 + it);
+      if (SPXB_TRACE_PTR(u) && lane == 0 && it < 12) trace_mark(u, 20 + it);
       const bool last = it + 1 == n_iters;
       if (elect_one()) {
         if (!(SPXB_DEBUG_BITS(u) & 2u)) {
@@ -633,12 +668,12 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     const uint32_t in_group = t < static_cast<uint32_t>(kStreams) ? (kStreams - t + u.n_tiles - 1) / u.n_tiles : 0u;
     const uint32_t in_batch = first < n_rows ? (n_rows - first + u.n_tiles - 1) / u.n_tiles : 0u;
     const uint32_t n_mine = min(in_group, in_batch);
-    if (vw == 8) slide_rows<uint4>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
-    else if (vw == 4) slide_rows<uint2>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
-    else if (vw == 2) slide_rows<uint32_t>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
-    else slide_rows<uint16_t>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
+    if (vw == 8) slide_rows<uint4, IDS, true>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
+    else if (vw == 4) slide_rows<uint2, IDS, true>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
+    else if (vw == 2) slide_rows<uint32_t, IDS, true>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
+    else slide_rows<uint16_t, IDS, true>(a, u.n_tiles, first, n_mine, hist_elems, shift, lane, &slide_next);
     for (uint32_t k = lane; k < n_mine; k += 32) {
-      const size_t s = launch_stream(a, first + k * u.n_tiles);
+      const size_t s = stream_of(first + k * u.n_tiles);
       a.last_sample[s] = sc.ls1;
       a.samp_frac[s] = sc.frac1;
     }
@@ -650,11 +685,11 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   if (warp == kMmaWarp) tmem_dealloc(tmem, u.tmem_cols);
   // no CTA may leave while a peer can still multicast into it or arrive on its barriers
   if (cluster > 1) cluster_sync_all();
-  if (tid == 0 && u.trace) {
+  if (tid == 0 && SPXB_TRACE_PTR(u)) {
     trace_mark(u, 9);
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + 15] = gt;
+    SPXB_TRACE_PTR(u)[static_cast<size_t>(blockIdx.x) * kTraceSlots + 15] = gt;
   }
 }
 
@@ -812,10 +847,21 @@ UmmaContext *umma_create(const FilterSpec &spec, const std::vector<float> &ref_t
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaFuncSetAttribute(umma_fir_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(umma_fir_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(umma_fir_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaFuncSetAttribute(umma_fir_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    auto big_smem = [](auto kernel) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    };
+    big_smem(umma_fir_kernel<1, false, false, false>);
+    big_smem(umma_fir_kernel<1, false, false, true>);
+    big_smem(umma_fir_kernel<2, false, false, false>);
+    big_smem(umma_fir_kernel<2, false, false, true>);
+    big_smem(umma_fir_kernel<1, true, false, false>);
+    big_smem(umma_fir_kernel<1, true, false, true>);
+    big_smem(umma_fir_kernel<2, true, false, false>);
+    big_smem(umma_fir_kernel<2, true, false, true>);
+    big_smem(umma_fir_kernel<1, false, true, false>);
+    big_smem(umma_fir_kernel<1, false, true, true>);
+    big_smem(umma_fir_kernel<2, false, true, false>);
+    big_smem(umma_fir_kernel<2, false, true, true>);
     configured_dev = dev;
   }
   return c;
@@ -1077,13 +1123,26 @@ cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, 
   const uintptr_t row_bits = reinterpret_cast<uintptr_t>(a.in) | (a.in_stride * 2u) |
                              reinterpret_cast<uintptr_t>(a.out) | (a.out_stride * 2u);
   const bool fast = allow_fast && c->cluster == 1 && (row_bits & 15u) == 0;
+  // long K loops take the paced instantiation (and so does a traced launch: the marks live there)
+  const uint32_t n_stages_run = (2 * c->ksteps + kStageChunks - 1) / kStageChunks;
+  static const int forced_paced = [] {
+    const char *e = getenv("SPXB_UMMA_PACED");
+    return e ? atoi(e) : -1;
+  }();
+  const bool paced = u.trace != nullptr || (forced_paced >= 0 ? forced_paced != 0 : n_stages_run > kLeanStages);
+  auto launch = [&](auto kernel) { return cudaLaunchKernelEx(&cfg, kernel, a, u); };
+  auto by_pace = [&](auto lean_kernel, auto paced_kernel) { return paced ? launch(paced_kernel) : launch(lean_kernel); };
   cudaError_t e;
-  if (a.channels == 2)
-    e = fast ? cudaLaunchKernelEx(&cfg, umma_fir_kernel<2, true>, a, u)
-             : cudaLaunchKernelEx(&cfg, umma_fir_kernel<2, false>, a, u);
-  else
-    e = fast ? cudaLaunchKernelEx(&cfg, umma_fir_kernel<1, true>, a, u)
-             : cudaLaunchKernelEx(&cfg, umma_fir_kernel<1, false>, a, u);
+  if (a.ids) {  // a cohort of a ragged batch: the generic instantiation with the id indirection
+    e = a.channels == 2 ? by_pace(umma_fir_kernel<2, false, true, false>, umma_fir_kernel<2, false, true, true>)
+                        : by_pace(umma_fir_kernel<1, false, true, false>, umma_fir_kernel<1, false, true, true>);
+  } else if (a.channels == 2) {
+    e = fast ? by_pace(umma_fir_kernel<2, true, false, false>, umma_fir_kernel<2, true, false, true>)
+             : by_pace(umma_fir_kernel<2, false, false, false>, umma_fir_kernel<2, false, false, true>);
+  } else {
+    e = fast ? by_pace(umma_fir_kernel<1, true, false, false>, umma_fir_kernel<1, true, false, true>)
+             : by_pace(umma_fir_kernel<1, false, false, false>, umma_fir_kernel<1, false, false, true>);
+  }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e == cudaSuccess && launches) *launches += 1;
   return e;

@@ -653,3 +653,36 @@ def test_ragged_batch_cohorts_take_the_tensor_kernel():
     assert b2.counters().kernel_launches == 1 and c0 > 0
     b.close()
     b2.close()
+
+
+def test_one_shot_long_chunk_on_the_tensor_kernel():
+    """the reference's own test feeds a whole file to ONE processChunk (src/test.ts:31-32): a long
+    one-shot call has far more output tiles than fit the kernel-parameter tile table, so the tensor
+    kernel reads its tile table from HBM -- same results as chunked calls and as the oracle"""
+    ch, i, o, q = 2, 44100, 48000, 7
+    frames = 60000
+    x = synth_pcm(2, ch, frames, i, seed=91)
+    b = StreamBatch(2, ch, i, o, q)
+    b.set_kernel(KERNEL_TENSOR)
+    cap = int(np.ceil(frames * o / i))
+    out, used, made = b.process(x, frames, cap)
+    assert b.tensor_geometry()["tiles"] > 64
+    for s in range(2):
+        y, u, m = O.OracleResampler(ch, i, o, q).process(x[s], cap)
+        assert (u, m) == (int(used[s]), int(made[s]))
+        d = np.abs(y.astype(np.int32) - out[s, : m * ch].astype(np.int32))
+        assert d.max() <= 1 and O.snr_db(y, out[s, : m * ch]) >= 90.0
+    # the same stream in 20 ms hops ends in the same state and produces the same samples
+    c = StreamBatch(2, ch, i, o, q)
+    c.set_kernel(KERNEL_TENSOR)
+    parts = []
+    for k in range(0, frames, 882):
+        n = min(882, frames - k)
+        yo, _, mo = c.process(x[:, k * ch:(k + n) * ch], n, 962)
+        parts.append(yo[:, : int(mo[0]) * ch])
+    hops = np.concatenate(parts, axis=1)
+    assert hops.shape[1] == int(made[0]) * ch
+    assert np.abs(hops.astype(np.int32) - out[:, : hops.shape[1]].astype(np.int32)).max() <= 1
+    assert b.get_state(1)[:2] == c.get_state(1)[:2]
+    b.close()
+    c.close()
