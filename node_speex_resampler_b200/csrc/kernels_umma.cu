@@ -28,9 +28,11 @@
 //   9    owns TMEM; the whole warp walks the stages, one elected lane issues the MMAs from
 //        uniform registers (four per K step) and releases stages with tcgen05.commit;
 //   10   slides the history (resample.c:898-899) and publishes the new stream position, beside
-//        the FIR, in units of four streams claimed from a counter in shared memory; for long
-//        histories the converter warps claim units too once their last stage is stored (they
-//        would otherwise idle until the accumulator is complete).
+//        the FIR, four streams at a time from the front of the CTA's share; for long histories
+//        the converter warps take single streams from its back once their last stage is stored
+//        (they would otherwise idle until the accumulator is complete).
+// Instantiations: CH (mono / stereo) x FAST (all rows 16-byte aligned, no cluster) x IDS (the launch
+// covers a stream-id list: one cohort of a ragged batch) x PACED (long K loops; see the kernel).
 // Stages are handed over with mbarriers (full: 256 converter arrivals + the bulk copy's byte
 // count; empty: tcgen05.commit). Launched with programmatic stream serialization: the next call's
 // grid runs its prologue while this one drains and blocks in griddepcontrol.wait before touching
