@@ -19,7 +19,7 @@
 //     tap stage [chunk 4][row 3nt][16 B]                   one 1-D bulk copy from the tile pool
 // Warp roles (352 threads):
 //   0-7  converters: fetch int16 PCM (history for frames < 0, the call's input after) with lanes
-//        walking ALONG a stream's segment (one LDG.128 = four whole lines), three stages of loads in
+//        walking ALONG a stream's segment (one LDG.128 = four whole lines), two stages of loads in
 //        flight in registers, split into byte planes with PRMT, store in UMMA layout; afterwards
 //        the epilogue: tcgen05.ld, 32-bit nested-floor recombination (exact), lane-pair exchange for
 //        stereo, cvt.pack.sat (= WORD2INT's saturation) and 16-byte stores straight to the output;
@@ -237,11 +237,16 @@ __device__ __forceinline__ void slide_rows(const CallArgs &a, uint32_t step, uin
 // plain instantiation carries no indirection at all (it costs the long-filter shapes 25 %).
 // PACED = the instantiation for long K loops (more than kLeanStages stages). It is the kernel with
 // its timeline probes compiled in (never taken unless SPXB_UMMA_TRACE is set) and the converters
-// asking for the stage three ahead BEFORE they hand the current one over. Measured, same source
-// otherwise: the probes make each converter thread wait on its in-flight loads at four points per
-// stage, and on 13-16-stage loops (C4, C5) that pacing is worth 6 % -- without it the history warp
-// and the tap stream starve behind the converters' loads -- while on C3's 4-stage loop the lean
-// instantiation (no probes, stage handed over first) is 9 % faster (profiles/umma_paced_ab_r1.log).
+// asking for the stage two ahead BEFORE they hand the current one over. Measured, same source
+// otherwise: on the 13-16-stage loops of C4 / C5 this instantiation is 8 % faster than the lean one
+// (12.6 / 76.8 us against 13.7 / 83.3 us), on C3's 4-stage loop the lean one (no probes, stage
+// handed over first) is 10 % faster (6.3 against 7.0 us). Which probes matter was bisected
+// (profiles/umma_paced_ab_r1.log): not the ones that used to sit inside the converters' stage
+// step (removed: without them the paced kernel gained another 2 %), but the ones around the
+// converter loop (slots 2, 3, 4, 30) -- a clock read between the two unrolled stage steps and at
+// the loop's ends changes how ptxas schedules the loop; explicit clock-read fences at the end of
+// every stage step do not reproduce it. The mechanism is not understood; the two instantiations
+// are kept because both measurements are solid.
 constexpr uint32_t kLeanStages = 8;
 template <int CH, bool FAST, bool IDS, bool PACED>
 __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a, const UmmaArgs u) {
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     tmem_relinquish();
   }
 
-  // ---- converter state: PCM items in flight, three stages deep ----
+  // ---- converter state: PCM items in flight, two stages deep ----
   // A stage is 64 frames of 128 series = kStreams stream segments of 64*CH*2 bytes. Lanes of a
   // warp walk ALONG a segment in 16-byte items (PPS items per stream, SPI streams per warp
   // instruction), so one LDG.128 covers four full 128-byte lines; each thread owns kItems items
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     conv_off[i] = (j >> 1) * x_kstep(CH) + (j & 1) * x_lbo(CH) + sl * (16 * CH) + byte_in_row;
   }
   constexpr int kStageFrames = kStageChunks * kUmmaChunkFrames;  // 64
-  uint4 raw0[kItems], raw1[kItems], raw2[kItems];  // three stages of loads in flight
+  uint4 raw0[kItems], raw1[kItems];  // two stages of loads in flight (three measured no better)
   // fetch the next stage (stages are fetched strictly in order): pointers just advance by one
   // stage of bytes, except once, where a thread's frames cross from the history into the input
   auto fetch = [&](uint4 (&raw)[kItems]) {
@@ -421,11 +426,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
   // call's grid (which reads the history buffer this call overwrites, and writes the one this call
   // reads) must have completed before any global access below.
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  // the first three stages' loads go out before the setup barrier
+  // the first two stages' loads go out before the setup barrier
   if (warp < kConvWarps) {
     fetch(raw0);
     if (n_iters > 1) fetch(raw1);
-    if (n_iters > 2) fetch(raw2);
   }
 
   tc_fence_before_sync();
@@ -462,23 +466,17 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     uint8_t *cstage = smem;
     auto stage_step = [&](uint32_t it, uint4 (&raw)[kItems]) {
       const uint32_t slot = cslot, par = cpar ^ 1u;
-      const bool tr = SPXB_TRACE_PTR(u) && tid == 0 && it == 6;
-      if (tr) trace_mark(u, 17);
       mbar_wait(&empty_bar[slot], par ^ 1u);
-      if (tr) trace_mark(u, 18);
       if (!(SPXB_DEBUG_BITS(u) & 4u)) convert_store(cstage, raw);
-      if (tr) trace_mark(u, 19);
       if (PACED) {
-        if (it + 3 < n_iters) fetch(raw);
-        if (tr) trace_mark(u, 10);
+        if (it + 2 < n_iters) fetch(raw);
         fence_proxy_async_smem();
         mbar_arrive(&full_bar[slot]);
-        if (tr) trace_mark(u, 31);
       } else {
-        // short loops: the tensor core gets the stage first, then the loads for three stages ahead go out
+        // short loops: the tensor core gets the stage first, then the loads for two stages ahead go out
         fence_proxy_async_smem();
         mbar_arrive(&full_bar[slot]);
-        if (it + 3 < n_iters) fetch(raw);
+        if (it + 2 < n_iters) fetch(raw);
       }
       cstage += stage_bytes;
       if (++cslot == S) {
@@ -489,11 +487,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_fir_kernel(const CallArgs a,
     };
 
     if (tid == 0) trace_mark(u, 2);
-    for (uint32_t it = 0; it < n_iters; it += 3) {
+    for (uint32_t it = 0; it < n_iters; it += 2) {
       stage_step(it, raw0);
       if (tid == 0 && it == 0) trace_mark(u, 3);
       if (it + 1 < n_iters) stage_step(it + 1, raw1);
-      if (it + 2 < n_iters) stage_step(it + 2, raw2);
     }
     if (tid == 0) trace_mark(u, 4);
     if (tid == kConvThreads - 32) trace_mark(u, 30);

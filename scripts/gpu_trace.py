@@ -16,8 +16,7 @@ SHAPES = {"C3": (1024, 2, 44100, 48000, 7, 882), "C4": (4096, 1, 48000, 16000, 1
           "C5": (8192, 2, 96000, 44100, 10, 1920)}
 NAMES = {0: "start", 1: "setup done", 2: "fetch0 issued", 3: "stage0 stored", 4: "convert loop end",
          5: "acc ready (conv)", 6: "epilogue math done", 7: "outputs stored", 8: "history done", 9: "exit",
-         17: "conv it6: enter", 18: "conv it6: slot empty", 19: "conv it6: stored", 10: "conv it6: fetch issued",
-         31: "conv it6: arrived", 30: "convert loop end (warp 7)", 11: "mma: all issued", 12: "tma: first bulk", 13: "tma: last bulk"}
+         30: "convert loop end (warp 7)", 11: "mma: all issued", 12: "tma: first bulk", 13: "tma: last bulk"}
 for it in range(12):
     NAMES[20 + it] = f"mma: stage {it} full"
 L = pkg.lib()
