@@ -99,6 +99,44 @@ def lagged(lag):
     return run
 
 
+def same_stream_d2h():
+    """(g) D2H rides the compute stream right behind the kernel: one event per step"""
+    for k in range(STEPS):
+        with torch.cuda.stream(s_in):
+            d_i[k % 4].copy_(h_i[k % HR], non_blocking=True)
+            e1 = torch.cuda.Event()
+            e1.record()
+        with torch.cuda.stream(s_k):
+            s_k.wait_event(e1)
+            d_o[k % 4][:in_bytes].copy_(d_i[k % 4], non_blocking=True)
+            h_o[k % HR].copy_(d_o[k % 4], non_blocking=True)
+
+
+s_k2 = torch.cuda.Stream()
+
+
+def two_compute_streams():
+    """(h) kernels alternate between two compute streams (chained by a kernel-to-kernel event);
+    each stream carries its own D2H behind its kernel"""
+    prev = None
+    for k in range(STEPS):
+        with torch.cuda.stream(s_in):
+            d_i[k % 4].copy_(h_i[k % HR], non_blocking=True)
+            e1 = torch.cuda.Event()
+            e1.record()
+        sk = s_k if k % 2 == 0 else s_k2
+        with torch.cuda.stream(sk):
+            sk.wait_event(e1)
+            if prev is not None:
+                sk.wait_event(prev)
+            d_o[k % 4][:in_bytes].copy_(d_i[k % 4], non_blocking=True)
+            prev = torch.cuda.Event()
+            prev.record()
+            h_o[k % HR].copy_(d_o[k % 4], non_blocking=True)
+
+
+timed(same_stream_d2h, "(g) H2D | kernel + D2H on one compute stream")
+timed(two_compute_streams, "(h) H2D | kernel + D2H alternating on two compute streams")
 timed(only("h2d"), "(f1) H2D only")
 timed(only("d2h"), "(f2) D2H only")
 timed(free_running, "(a) free-running H2D || D2H")
