@@ -47,6 +47,9 @@ WORKLOADS = {
     "C3": (1024, 2, 44100, 48000, 7, 882),
     "C4": (4096, 1, 48000, 16000, 10, 960),
     "C5": (8192, 2, 96000, 44100, 10, 1920),
+    # not BASELINE shapes: mid-length filters used to place the lean / paced kernel threshold
+    "X6": (1024, 2, 44100, 48000, 10, 882),   # N = 256: 6 stages
+    "X8": (2048, 1, 32000, 16000, 10, 640),   # N = 512, mono, 2:1
 }
 L2_BYTES = 126 * 1024 * 1024
 
@@ -447,7 +450,7 @@ def ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         S_, ch_, i_, o_, q_, n_ = WORKLOADS[wl]
-        per_step_core_s = {"C3": 0.75, "C4": 0.9, "C5": 30.0}[wl]
+        per_step_core_s = {"C3": 0.75, "C4": 0.9, "C5": 30.0}.get(wl, 2.0)
         cores = os.cpu_count() or 1
         cpu_steps = max(1, int(20.0 * cores / per_step_core_s / cores)) if wl != "C5" else 1
         cpu_steps = max(1, min(cpu_steps, int(15.0 * cores / per_step_core_s)))
