@@ -85,6 +85,20 @@ SPXB_API int speex_resampler_get_output_latency(SpeexResamplerState *st); /* res
 SPXB_API int speex_resampler_process_interleaved_float(SpeexResamplerState *st, const float *in,
                                                        uint32_t *in_len, float *out,
                                                        uint32_t *out_len);
+/* replaces resample.c:799 / :1107 / :1084 / :1153 (speex_resampler.h:140-147, 226-235, 262-276).
+ * The ratio may be given apart from the nominal rates; the filter depends on the reduced ratio.
+ * set_rate / set_rate_frac / set_quality rebuild the filter exactly as the reference does while
+ * no sample has been resampled yet (memory zeroed, last_sample kept); changing the filter
+ * MID-STREAM (the reference's "magic samples", resample.c:727-782) is not implemented and
+ * returns RESAMPLER_ERR_BAD_STATE with the state untouched -- the TypeScript wrapper never
+ * does it. */
+SPXB_API SpeexResamplerState *speex_resampler_init_frac(uint32_t nb_channels, uint32_t ratio_num,
+                                                        uint32_t ratio_den, uint32_t in_rate,
+                                                        uint32_t out_rate, int quality, int *err);
+SPXB_API int speex_resampler_set_rate(SpeexResamplerState *st, uint32_t in_rate, uint32_t out_rate);
+SPXB_API int speex_resampler_set_rate_frac(SpeexResamplerState *st, uint32_t ratio_num,
+                                           uint32_t ratio_den, uint32_t in_rate, uint32_t out_rate);
+SPXB_API int speex_resampler_set_quality(SpeexResamplerState *st, int quality);
 SPXB_API int speex_resampler_skip_zeros(SpeexResamplerState *st);         /* resample.c:1200 */
 SPXB_API int speex_resampler_reset_mem(SpeexResamplerState *st);          /* resample.c:1208 */
 

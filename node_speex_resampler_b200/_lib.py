@@ -26,6 +26,8 @@ DECLARED_SYMBOLS = (
     "spxb_batch_counters", "spxb_host_alloc", "spxb_host_free", "spxb_filter_describe",
     "spxb_filter_table", "spxb_filter_phase_taps", "spxb_filter_fixed_taps", "spxb_tensor_plan",
     "spxb_tensor_tap_tile", "spxb_plan_call", "spxb_version", "spxb_resampler_batch",
+    "speex_resampler_init_frac", "speex_resampler_set_rate", "speex_resampler_set_rate_frac",
+    "speex_resampler_set_quality",
     "speex_resampler_process_interleaved_float", "spxb_batch_create_f32", "spxb_batch_is_f32",
     "spxb_batch_process_f32", "spxb_batch_get_state_f32", "spxb_batch_set_state_f32", "spxb_plan_call_f32",
 )
@@ -109,6 +111,11 @@ def _bind(L):
     L.spxb_tensor_tap_tile.argtypes = [u32, u32, C.c_int, u32, u32, u32, vp, sz]
     L.spxb_plan_call.argtypes = [u32, u32, i32, u32, u32, u32, C.POINTER(CallPlan)]
     L.spxb_plan_call_f32.argtypes = [u32, u32, i32, u32, u32, u32, C.POINTER(CallPlan)]
+    L.speex_resampler_init_frac.restype = vp
+    L.speex_resampler_init_frac.argtypes = [u32, u32, u32, u32, u32, C.c_int, pint]
+    L.speex_resampler_set_rate.argtypes = [vp, u32, u32]
+    L.speex_resampler_set_rate_frac.argtypes = [vp, u32, u32, u32, u32]
+    L.speex_resampler_set_quality.argtypes = [vp, C.c_int]
     L.speex_resampler_process_interleaved_float.restype = C.c_int
     L.speex_resampler_process_interleaved_float.argtypes = [vp, vp, pu32, vp, pu32]
     L.spxb_batch_create_f32.restype = vp

@@ -1360,4 +1360,5 @@ static int plan_call_any(uint32_t in_rate, uint32_t out_rate, int32_t last_sampl
 // exposed to capi.cpp
 namespace spxb {
 const FilterSpec &batch_spec(const spxb_batch *b) { return b->spec; }
+int batch_kernel_pref(const spxb_batch *b) { return b->kernel_pref; }
 }

@@ -9,14 +9,20 @@
 #include "../../include/speexb200.h"
 #include "filter_bank.h"
 
+#include <string>
+
 namespace spxb {
 const FilterSpec &batch_spec(const spxb_batch *b);
+int batch_kernel_pref(const spxb_batch *b);
+void set_error(const std::string &msg);
 }
 
 struct SpeexResamplerState_ {
   spxb_batch *batch = nullptr;
   uint32_t in_rate = 0, out_rate = 0, channels = 0;
+  uint32_t ratio_num = 0, ratio_den = 0;  // as given (the filter depends on their reduced ratio only)
   int quality = 0;
+  bool started = false;  // a call has reached the resampling loop (resample.c:881 `st->started = 1`)
   std::vector<int16_t> silence;  // stands in for in == NULL (resample.c:1007-1010)
   std::vector<float> fsilence;   // the same for the float entry (resample.c:950-952)
 };
@@ -25,8 +31,13 @@ extern "C" {
 
 SpeexResamplerState *speex_resampler_init(uint32_t nb_channels, uint32_t in_rate, uint32_t out_rate,
                                           int quality, int *err) {
+  return speex_resampler_init_frac(nb_channels, in_rate, out_rate, in_rate, out_rate, quality, err);
+}
+
+SpeexResamplerState *speex_resampler_init_frac(uint32_t nb_channels, uint32_t ratio_num, uint32_t ratio_den,
+                                               uint32_t in_rate, uint32_t out_rate, int quality, int *err) {
   // resample.c:804-809: argument check precedes any allocation
-  if (nb_channels == 0 || in_rate == 0 || out_rate == 0 || quality > 10 || quality < 0) {
+  if (nb_channels == 0 || ratio_num == 0 || ratio_den == 0 || quality > 10 || quality < 0) {
     if (err) *err = RESAMPLER_ERR_INVALID_ARG;
     return nullptr;
   }
@@ -37,7 +48,7 @@ SpeexResamplerState *speex_resampler_init(uint32_t nb_channels, uint32_t in_rate
   }
   int e = 0;
   int device = 0;
-  st->batch = spxb_batch_create(1, nb_channels, in_rate, out_rate, quality, device, &e);
+  st->batch = spxb_batch_create(1, nb_channels, ratio_num, ratio_den, quality, device, &e);
   if (!st->batch) {
     delete st;
     if (err) *err = e ? e : RESAMPLER_ERR_ALLOC_FAILED;
@@ -45,6 +56,8 @@ SpeexResamplerState *speex_resampler_init(uint32_t nb_channels, uint32_t in_rate
   }
   st->in_rate = in_rate;
   st->out_rate = out_rate;
+  st->ratio_num = ratio_num;
+  st->ratio_den = ratio_den;
   st->channels = nb_channels;
   st->quality = quality;
   if (err) *err = RESAMPLER_ERR_SUCCESS;
@@ -79,6 +92,65 @@ int speex_resampler_get_output_latency(SpeexResamplerState *st) {
   return static_cast<int>(((s.taps / 2) * s.den + (s.num >> 1)) / s.num);
 }
 
+// Filter changes (resample.c:1107-1163). Before the first sample has been resampled the reference
+// only rebuilds the filter and zeroes its memory (resample.c:721-725), which is what happens here:
+// a fresh batch for the new ratio / quality, keeping last_sample (skip_zeros may have set it).
+// AFTER that the reference splices the old filter memory into the new one ("magic samples",
+// resample.c:727-782, :904-922) -- not implemented: RESAMPLER_ERR_BAD_STATE, state untouched.
+static int refilter(SpeexResamplerState *st, uint32_t ratio_num, uint32_t ratio_den, int quality) {
+  if (st->started) {
+    spxb::set_error("changing the rate or quality after samples have been resampled (magic samples) is not supported");
+    return RESAMPLER_ERR_BAD_STATE;
+  }
+  int e = 0;
+  const bool f32 = spxb_batch_is_f32(st->batch) != 0;
+  spxb_batch *nb = f32 ? spxb_batch_create_f32(1, st->channels, ratio_num, ratio_den, quality, 0, &e)
+                       : spxb_batch_create(1, st->channels, ratio_num, ratio_den, quality, 0, &e);
+  if (!nb) return e ? e : RESAMPLER_ERR_ALLOC_FAILED;
+  int32_t last = 0;
+  uint32_t frac = 0, magic = 0;
+  e = spxb_batch_get_state(st->batch, 0, &last, &frac, &magic, nullptr);
+  if (!e) e = spxb_batch_set_state(nb, 0, last, 0, nullptr);
+  if (e) {
+    spxb_batch_destroy(nb);
+    return e;
+  }
+  spxb_batch_set_kernel(nb, spxb::batch_kernel_pref(st->batch));
+  spxb_batch_destroy(st->batch);
+  st->batch = nb;
+  return RESAMPLER_ERR_SUCCESS;
+}
+
+int speex_resampler_set_rate_frac(SpeexResamplerState *st, uint32_t ratio_num, uint32_t ratio_den, uint32_t in_rate,
+                                  uint32_t out_rate) {
+  if (!st || ratio_num == 0 || ratio_den == 0) return RESAMPLER_ERR_INVALID_ARG;
+  if (st->in_rate == in_rate && st->out_rate == out_rate && st->ratio_num == ratio_num && st->ratio_den == ratio_den)
+    return RESAMPLER_ERR_SUCCESS;
+  // the same reduced ratio keeps the filter (resample.c compares the given numbers, then reduces;
+  // rebuilding an identical filter before the first sample is not observable)
+  const spxb::FilterSpec &s = spxb::batch_spec(st->batch);
+  const bool same_ratio = static_cast<uint64_t>(ratio_num) * s.den == static_cast<uint64_t>(ratio_den) * s.num;
+  if (!same_ratio)
+    if (int e = refilter(st, ratio_num, ratio_den, st->quality)) return e;
+  st->in_rate = in_rate;
+  st->out_rate = out_rate;
+  st->ratio_num = ratio_num;
+  st->ratio_den = ratio_den;
+  return RESAMPLER_ERR_SUCCESS;
+}
+
+int speex_resampler_set_rate(SpeexResamplerState *st, uint32_t in_rate, uint32_t out_rate) {
+  return speex_resampler_set_rate_frac(st, in_rate, out_rate, in_rate, out_rate);  // resample.c:1084-1087
+}
+
+int speex_resampler_set_quality(SpeexResamplerState *st, int quality) {
+  if (!st || quality > 10 || quality < 0) return RESAMPLER_ERR_INVALID_ARG;
+  if (st->quality == quality) return RESAMPLER_ERR_SUCCESS;
+  if (int e = refilter(st, st->ratio_num, st->ratio_den, quality)) return e;
+  st->quality = quality;
+  return RESAMPLER_ERR_SUCCESS;
+}
+
 int speex_resampler_skip_zeros(SpeexResamplerState *st) { return spxb_batch_skip_zeros(st->batch); }
 
 int speex_resampler_reset_mem(SpeexResamplerState *st) { return spxb_batch_reset(st->batch); }
@@ -90,6 +162,7 @@ int speex_resampler_process_interleaved_int(SpeexResamplerState *st, const int16
     st->silence.assign(static_cast<size_t>(*in_len) * st->channels, 0);
     in = st->silence.data();
   }
+  if (*in_len != 0 && *out_len != 0) st->started = true;
   // one stream: the strides are irrelevant, the lengths are the in-out cells
   return spxb_batch_process(st->batch, in, *in_len, in_len, out, *out_len, out_len);
 }
@@ -100,7 +173,7 @@ int speex_resampler_process_interleaved_float(SpeexResamplerState *st, const flo
   if (!spxb_batch_is_f32(st->batch)) {
     // first float call: the state moves to a float-history batch (int16 history converts exactly)
     int e = 0;
-    spxb_batch *fb = spxb_batch_create_f32(1, st->channels, st->in_rate, st->out_rate, st->quality, 0, &e);
+    spxb_batch *fb = spxb_batch_create_f32(1, st->channels, st->ratio_num, st->ratio_den, st->quality, 0, &e);
     if (!fb) return e ? e : RESAMPLER_ERR_ALLOC_FAILED;
     const spxb::FilterSpec &s = spxb::batch_spec(st->batch);
     std::vector<float> hist(static_cast<size_t>(s.taps ? s.taps - 1 : 0) * st->channels + 1);
@@ -112,6 +185,7 @@ int speex_resampler_process_interleaved_float(SpeexResamplerState *st, const flo
       spxb_batch_destroy(fb);
       return e;
     }
+    if (spxb::batch_kernel_pref(st->batch) == SPXB_KERNEL_STRICT) spxb_batch_set_kernel(fb, SPXB_KERNEL_STRICT);
     spxb_batch_destroy(st->batch);
     st->batch = fb;
   }
@@ -119,6 +193,7 @@ int speex_resampler_process_interleaved_float(SpeexResamplerState *st, const flo
     st->fsilence.assign(static_cast<size_t>(*in_len) * st->channels, 0.f);
     in = st->fsilence.data();
   }
+  if (*in_len != 0 && *out_len != 0) st->started = true;
   return spxb_batch_process_f32(st->batch, in, *in_len, in_len, out, *out_len, out_len);
 }
 

@@ -686,3 +686,57 @@ def test_one_shot_long_chunk_on_the_tensor_kernel():
     assert b.get_state(1)[:2] == c.get_state(1)[:2]
     b.close()
     c.close()
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not present")
+def test_c_api_filter_changes_before_the_first_sample_match_the_reference():
+    """init_frac / set_quality / set_rate / set_rate_frac / skip_zeros before any sample has been
+    resampled (resample.c:1107-1163 with update_filter's !started branch): same lengths and bytes
+    as the reference's own build given the same call sequence; the mid-stream change (magic
+    samples) is refused without touching the state."""
+    L, R = lib(), O._load_ref()
+    R.speex_resampler_init_frac.restype = C.c_void_p
+    R.speex_resampler_init_frac.argtypes = [C.c_uint32] * 5 + [C.c_int, C.POINTER(C.c_int)]
+    for fn in (R.speex_resampler_set_quality, R.speex_resampler_set_rate, R.speex_resampler_set_rate_frac,
+               R.speex_resampler_skip_zeros):
+        fn.restype = C.c_int
+    R.speex_resampler_set_quality.argtypes = [C.c_void_p, C.c_int]
+    R.speex_resampler_set_rate.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    R.speex_resampler_set_rate_frac.argtypes = [C.c_void_p] + [C.c_uint32] * 4
+    R.speex_resampler_skip_zeros.argtypes = [C.c_void_p]
+    ch = 2
+    err = C.c_int(0)
+    ours = L.speex_resampler_init_frac(ch, 441, 480, 44100, 48000, 7, C.byref(err))
+    ref = R.speex_resampler_init_frac(ch, 441, 480, 44100, 48000, 7, C.byref(err))
+    assert ours and ref
+    assert L.spxb_batch_set_kernel(L.spxb_resampler_batch(ours), KERNEL_STRICT) == 0
+    for lib_, st in ((L, ours), (R, ref)):
+        assert lib_.speex_resampler_set_quality(st, 3) == 0
+        assert lib_.speex_resampler_skip_zeros(st) == 0          # last_sample = filt_len / 2 of the q3 filter
+        assert lib_.speex_resampler_set_rate(st, 48000, 16000) == 0
+        assert lib_.speex_resampler_set_quality(st, 10) == 0
+        assert lib_.speex_resampler_set_rate_frac(st, 320, 147, 96000, 44100) == 0
+        assert lib_.speex_resampler_set_quality(st, 11) == 3      # RESAMPLER_ERR_INVALID_ARG
+    num, den = C.c_uint32(), C.c_uint32()
+    L.speex_resampler_get_ratio(ours, C.byref(num), C.byref(den))
+    assert (num.value, den.value) == (320, 147)
+    x = synth_pcm(1, ch, 3000, 96000, seed=77)[0]
+    pos = 0
+    for n, cap in ((1000, 600), (7, 600), (1500, 300), (493, 600)):
+        chunk = np.ascontiguousarray(x[pos * ch:(pos + n) * ch])
+        pos += n
+        res = []
+        for lib_, st in ((L, ours), (R, ref)):
+            out = np.zeros(cap * ch, np.int16)
+            n_in, n_out = C.c_uint32(n), C.c_uint32(cap)
+            assert lib_.speex_resampler_process_interleaved_int(st, chunk.ctypes.data, C.byref(n_in), out.ctypes.data,
+                                                                C.byref(n_out)) == 0
+            res.append((n_in.value, n_out.value, out[: n_out.value * ch].copy()))
+        assert res[0][:2] == res[1][:2]
+        assert np.array_equal(res[0][2], res[1][2])
+    # mid-stream: refused, and the stream carries on as if nothing had been asked
+    assert L.speex_resampler_set_quality(ours, 5) == 2            # RESAMPLER_ERR_BAD_STATE
+    assert "magic samples" in _lib.last_error()
+    assert L.speex_resampler_set_rate_frac(ours, 640, 294, 96000, 44100) == 0   # same reduced ratio: no filter change
+    L.speex_resampler_destroy(ours)
+    R.speex_resampler_destroy(ref)
