@@ -176,3 +176,22 @@ def test_call_plan_float_entry_walk_matches_oracle():
             ls1, fr1, _ = r.state(0)
             assert (plan.consumed, plan.n_out, plan.last_sample, plan.samp_frac_num) == (used, made, ls1, fr1), \
                 (i, o, k, n, cap)
+
+
+def test_init_frac_argument_checks_precede_any_allocation():
+    """resample.c:804-809 for the _frac entry: zero channels / ratio terms, quality outside 0..10 ->
+    NULL + RESAMPLER_ERR_INVALID_ARG, with or without a GPU"""
+    L = lib()
+    for args in ((0, 441, 480, 44100, 48000, 7), (2, 0, 480, 44100, 48000, 7), (2, 441, 0, 44100, 48000, 7),
+                 (2, 441, 480, 44100, 48000, 11), (2, 441, 480, 44100, 48000, -1)):
+        err = C.c_int(0)
+        assert not L.speex_resampler_init_frac(*args, C.byref(err))
+        assert err.value == 3
+    # the nominal rates are informational: zero rates pass the argument check (resample.c:804)
+    err = C.c_int(0)
+    st = L.speex_resampler_init_frac(1, 3, 1, 0, 0, 4, C.byref(err))
+    if L.spxb_device_count() <= 0:
+        assert not st and err.value == 1      # no device: ALLOC_FAILED, never a CPU fallback
+    else:
+        assert st and err.value == 0
+        L.speex_resampler_destroy(st)
