@@ -53,10 +53,9 @@ class SpeexResampler {
   static initPromise = globalModulePromise as Promise<any>;
 
   /**
-    * @param channels Number of channels, minimum is 1, no maximum
-    * @param inRate frequency in Hz for the input chunk
-    * @param outRate frequency in Hz for the target chunk
-    * @param quality number from 1 to 10, default to 7, 1 is fast but of bad quality, 10 is slow but best quality
+    * channels: interleaved channel count (>= 1); inRate / outRate: sample rates in Hz;
+    * quality: Speex quality 0..10 (7 when omitted; higher = longer filter).
+    * Nothing is allocated until the first chunk arrives.
     */
   constructor(
     public channels,
@@ -84,10 +83,7 @@ class SpeexResampler {
     }
   }
 
-  /**
-    * Resample a chunk of audio.
-    * @param chunk interleaved PCM data in signed 16bits int
-    */
+  /** One call = one chunk of interleaved little-endian int16 PCM in, the resampled chunk out. */
   processChunk(chunk: Buffer): Buffer {
     this._check(chunk);
     if (this._batch) {
@@ -208,10 +204,9 @@ export class SpeexResamplerTransform extends Transform {
   _alignementBuffer: Buffer;
 
   /**
-    * @param channels Number of channels, minimum is 1, no maximum
-    * @param inRate frequency in Hz for the input chunk
-    * @param outRate frequency in Hz for the target chunk
-    * @param quality number from 1 to 10, default to 7, 1 is fast but of bad quality, 10 is slow but best quality
+    * channels: interleaved channel count (>= 1); inRate / outRate: sample rates in Hz;
+    * quality: Speex quality 0..10 (7 when omitted; higher = longer filter).
+    * Nothing is allocated until the first chunk arrives.
     */
   constructor(public channels, public inRate, public outRate, public quality = 7) {
     super();
