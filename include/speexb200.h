@@ -87,11 +87,13 @@ SPXB_API int speex_resampler_process_interleaved_float(SpeexResamplerState *st, 
                                                        uint32_t *out_len);
 /* replaces resample.c:799 / :1107 / :1084 / :1153 (speex_resampler.h:140-147, 226-235, 262-276).
  * The ratio may be given apart from the nominal rates; the filter depends on the reduced ratio.
- * set_rate / set_rate_frac / set_quality rebuild the filter exactly as the reference does while
- * no sample has been resampled yet (memory zeroed, last_sample kept); changing the filter
- * MID-STREAM (the reference's "magic samples", resample.c:727-782) is not implemented and
- * returns RESAMPLER_ERR_BAD_STATE with the state untouched -- the TypeScript wrapper never
- * does it. */
+ * set_rate / set_rate_frac / set_quality follow the reference call for call: before the first
+ * resampled sample the filter is rebuilt and its memory zeroed; mid-stream a change that keeps
+ * the filter length (any ratio change while up-sampling, e.g. clock-drift correction) rescales
+ * samp_frac_num, and one that lengthens it re-anchors the history behind zeros and advances
+ * last_sample by half the growth (resample.c:727-758, :1131-1140). A mid-stream change that
+ * SHORTENS the filter (the reference's "magic samples", resample.c:759-776, :904-922) is not
+ * implemented: RESAMPLER_ERR_BAD_STATE, state untouched. */
 SPXB_API SpeexResamplerState *speex_resampler_init_frac(uint32_t nb_channels, uint32_t ratio_num,
                                                         uint32_t ratio_den, uint32_t in_rate,
                                                         uint32_t out_rate, int quality, int *err);

@@ -2,6 +2,7 @@
 // bound at src/index.ts:6-16) plus the read-only rest of deps/speex/speex_resampler.h, each
 // implemented over a one-stream device batch. Same signatures, length conventions and error
 // codes as deps/speex/resample.c; the arithmetic runs on the GPU (no CPU path).
+#include <algorithm>
 #include <cstdint>
 #include <new>
 #include <vector>
@@ -92,25 +93,53 @@ int speex_resampler_get_output_latency(SpeexResamplerState *st) {
   return static_cast<int>(((s.taps / 2) * s.den + (s.num >> 1)) / s.num);
 }
 
-// Filter changes (resample.c:1107-1163). Before the first sample has been resampled the reference
-// only rebuilds the filter and zeroes its memory (resample.c:721-725), which is what happens here:
-// a fresh batch for the new ratio / quality, keeping last_sample (skip_zeros may have set it).
-// AFTER that the reference splices the old filter memory into the new one ("magic samples",
-// resample.c:727-782, :904-922) -- not implemented: RESAMPLER_ERR_BAD_STATE, state untouched.
+// Filter changes (resample.c:1107-1163 over update_filter's memory branches, :703-782).
+//  * before the first sample has been resampled: the filter is rebuilt and its memory zeroed
+//    (:721-725) -- a fresh batch for the new ratio / quality, keeping last_sample;
+//  * mid-stream, same filter length (any ratio change while up-sampling: clock-drift correction):
+//    only the table changes; history and last_sample stay, samp_frac_num is rescaled to the new
+//    denominator (:1131-1140, multiply_frac :593-603);
+//  * mid-stream, longer filter (:727-758 with no magic samples pending): the old history moves to
+//    the end of the new one behind zeros and last_sample advances by half the growth;
+//  * mid-stream, shorter filter: the reference keeps the surplus history as "magic samples" that
+//    are resampled before the next input (:759-776, :904-922) -- not implemented:
+//    RESAMPLER_ERR_BAD_STATE, state untouched.
 static int refilter(SpeexResamplerState *st, uint32_t ratio_num, uint32_t ratio_den, int quality) {
-  if (st->started) {
-    spxb::set_error("changing the rate or quality after samples have been resampled (magic samples) is not supported");
+  spxb::FilterSpec next;
+  if (int e = spxb::derive_filter_spec(ratio_num, ratio_den, quality, &next)) return e;
+  const spxb::FilterSpec old = spxb::batch_spec(st->batch);
+  if (st->started && next.taps < old.taps) {
+    spxb::set_error("shortening the filter after samples have been resampled (magic samples) is not supported");
     return RESAMPLER_ERR_BAD_STATE;
   }
-  int e = 0;
   const bool f32 = spxb_batch_is_f32(st->batch) != 0;
+  int32_t last = 0;
+  uint32_t frac = 0, magic = 0;
+  const size_t old_live = static_cast<size_t>(old.taps - 1) * st->channels;
+  const size_t new_live = static_cast<size_t>(next.taps - 1) * st->channels;
+  std::vector<float> hist_f(f32 ? old_live + 1 : 1), grown_f(f32 ? new_live + 1 : 1, 0.f);
+  std::vector<int16_t> hist_i(f32 ? 1 : old_live + 1), grown_i(f32 ? 1 : new_live + 1, 0);
+  int e = f32 ? spxb_batch_get_state_f32(st->batch, 0, &last, &frac, &magic, st->started ? hist_f.data() : nullptr)
+              : spxb_batch_get_state(st->batch, 0, &last, &frac, &magic, st->started ? hist_i.data() : nullptr);
+  if (e) return e;
+  if (st->started) {
+    // :1131-1140: samp_frac_num * den_new / den_old (it is < den_old, so the product fits 64 bits), clamped
+    uint64_t scaled = static_cast<uint64_t>(frac) * next.den / old.den;
+    if (frac != 0 && frac > 0xffffffffu / next.den) return RESAMPLER_ERR_OVERFLOW;  // multiply_frac's check
+    if (scaled >= next.den) scaled = next.den - 1;
+    frac = static_cast<uint32_t>(scaled);
+    const size_t pad = new_live - old_live;  // >= 0: growth or same length
+    if (f32) std::copy(hist_f.begin(), hist_f.begin() + old_live, grown_f.begin() + pad);
+    else std::copy(hist_i.begin(), hist_i.begin() + old_live, grown_i.begin() + pad);
+    last += static_cast<int32_t>((next.taps - old.taps) / 2);  // :748
+  } else {
+    frac = 0;
+  }
   spxb_batch *nb = f32 ? spxb_batch_create_f32(1, st->channels, ratio_num, ratio_den, quality, 0, &e)
                        : spxb_batch_create(1, st->channels, ratio_num, ratio_den, quality, 0, &e);
   if (!nb) return e ? e : RESAMPLER_ERR_ALLOC_FAILED;
-  int32_t last = 0;
-  uint32_t frac = 0, magic = 0;
-  e = spxb_batch_get_state(st->batch, 0, &last, &frac, &magic, nullptr);
-  if (!e) e = spxb_batch_set_state(nb, 0, last, 0, nullptr);
+  e = f32 ? spxb_batch_set_state_f32(nb, 0, last, frac, st->started ? grown_f.data() : nullptr)
+          : spxb_batch_set_state(nb, 0, last, frac, st->started ? grown_i.data() : nullptr);
   if (e) {
     spxb_batch_destroy(nb);
     return e;

@@ -734,9 +734,66 @@ def test_c_api_filter_changes_before_the_first_sample_match_the_reference():
             res.append((n_in.value, n_out.value, out[: n_out.value * ch].copy()))
         assert res[0][:2] == res[1][:2]
         assert np.array_equal(res[0][2], res[1][2])
-    # mid-stream: refused, and the stream carries on as if nothing had been asked
+    # mid-stream, shorter filter (magic samples): refused, and the stream carries on untouched
     assert L.speex_resampler_set_quality(ours, 5) == 2            # RESAMPLER_ERR_BAD_STATE
     assert "magic samples" in _lib.last_error()
     assert L.speex_resampler_set_rate_frac(ours, 640, 294, 96000, 44100) == 0   # same reduced ratio: no filter change
+    L.speex_resampler_destroy(ours)
+    R.speex_resampler_destroy(ref)
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("ch", [1, 2])
+def test_c_api_mid_stream_rate_and_quality_changes_match_the_reference(ch):
+    """Mid-stream filter changes that do not shorten the filter, call for call against the
+    reference build: clock-drift correction while up-sampling (same filter length, samp_frac_num
+    rescaled, resample.c:1131-1140), a quality increase and a deeper down-sampling (longer filter:
+    history re-anchored behind zeros, last_sample advanced, resample.c:727-758)."""
+    L, R = lib(), O._load_ref()
+    R.speex_resampler_set_quality.restype = R.speex_resampler_set_rate.restype = C.c_int
+    R.speex_resampler_set_quality.argtypes = [C.c_void_p, C.c_int]
+    R.speex_resampler_set_rate.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    err = C.c_int(0)
+    ours = L.speex_resampler_init(ch, 44100, 48000, 5, C.byref(err))
+    ref = R.speex_resampler_init(ch, 44100, 48000, 5, C.byref(err))
+    assert L.spxb_batch_set_kernel(L.spxb_resampler_batch(ours), KERNEL_STRICT) == 0
+    x = synth_pcm(1, ch, 12000, 44100, seed=123)[0]
+    pos = [0]
+
+    def both(n, cap):
+        chunk = np.ascontiguousarray(x[pos[0] * ch:(pos[0] + n) * ch])
+        pos[0] += n
+        res = []
+        for lib_, st in ((L, ours), (R, ref)):
+            out = np.zeros(cap * ch, np.int16)
+            n_in, n_out = C.c_uint32(n), C.c_uint32(cap)
+            assert lib_.speex_resampler_process_interleaved_int(st, chunk.ctypes.data, C.byref(n_in), out.ctypes.data,
+                                                                C.byref(n_out)) == 0
+            res.append((n_in.value, n_out.value, out[: n_out.value * ch].copy()))
+        assert res[0][:2] == res[1][:2], (pos[0], res[0][:2], res[1][:2])
+        assert np.array_equal(res[0][2], res[1][2]), pos[0]
+
+    def change(fn, *args):
+        a, b = getattr(L, fn)(ours, *args), getattr(R, fn)(ref, *args)
+        assert a == b == 0, (fn, args, a, b, _lib.last_error())
+
+    both(441, 600)
+    both(333, 600)
+    change("speex_resampler_set_rate", 44100, 48010)     # drift correction: same filter length
+    both(441, 600)
+    change("speex_resampler_set_rate", 44100, 47990)
+    both(500, 300)                                        # capacity binds
+    both(441, 600)
+    change("speex_resampler_set_quality", 8)              # longer filter
+    both(441, 600)
+    both(7, 600)
+    change("speex_resampler_set_rate", 44100, 22050)      # now down-sampling 2:1: longer again
+    both(882, 600)
+    both(441, 600)
+    change("speex_resampler_set_quality", 10)
+    both(441, 600)
+    assert L.speex_resampler_set_rate(ours, 44100, 44100) == 2   # would shorten the filter: refused ...
+    assert "magic samples" in _lib.last_error()
+    both(441, 600)                                               # ... and the state is untouched
     L.speex_resampler_destroy(ours)
     R.speex_resampler_destroy(ref)
