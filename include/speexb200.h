@@ -91,9 +91,12 @@ SPXB_API int speex_resampler_process_interleaved_float(SpeexResamplerState *st, 
  * resampled sample the filter is rebuilt and its memory zeroed; mid-stream a change that keeps
  * the filter length (any ratio change while up-sampling, e.g. clock-drift correction) rescales
  * samp_frac_num, and one that lengthens it re-anchors the history behind zeros and advances
- * last_sample by half the growth (resample.c:727-758, :1131-1140). A mid-stream change that
- * SHORTENS the filter (the reference's "magic samples", resample.c:759-776, :904-922) is not
- * implemented: RESAMPLER_ERR_BAD_STATE, state untouched. */
+ * last_sample by half the growth (resample.c:727-758, :1131-1140); one that SHORTENS it leaves
+ * the surplus history behind as "magic samples" that the next calls resample before their own
+ * input, on either entry, with the reference's lengths even when the capacity binds (resample.c:
+ * 759-776, :904-922, :940-941, :993-1016; its memory never shrinks, so its input block grows).
+ * Only a second change of the filter LENGTH while magic samples are still pending is refused
+ * (RESAMPLER_ERR_BAD_STATE, state untouched). */
 SPXB_API SpeexResamplerState *speex_resampler_init_frac(uint32_t nb_channels, uint32_t ratio_num,
                                                         uint32_t ratio_den, uint32_t in_rate,
                                                         uint32_t out_rate, int quality, int *err);
@@ -299,6 +302,15 @@ SPXB_API int spxb_plan_call(uint32_t in_rate, uint32_t out_rate, int32_t last_sa
 SPXB_API int spxb_plan_call_f32(uint32_t in_rate, uint32_t out_rate, int32_t last_sample,
                                 uint32_t samp_frac_num, uint32_t n_in, uint32_t out_cap,
                                 spxb_call_plan *plan);
+
+/* the general form: `magic` pending samples in front of the input (what a filter change that
+ * shortened the filter leaves behind, resample.c:759-776, :904-922), either entry's block walk,
+ * and the input block of a state whose memory outgrew its filter (in_block = mem_alloc_size -
+ * (filt_len - 1), 160 for a fresh state). plan->consumed counts real input frames. */
+SPXB_API int spxb_plan_call_ex(uint32_t in_rate, uint32_t out_rate, int32_t last_sample,
+                               uint32_t samp_frac_num, uint32_t magic, uint32_t n_in,
+                               uint32_t out_cap, int float_entry, uint32_t in_block,
+                               spxb_call_plan *plan, uint32_t *magic_used);
 
 SPXB_API const char *spxb_version(void);
 

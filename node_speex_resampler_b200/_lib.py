@@ -29,7 +29,7 @@ DECLARED_SYMBOLS = (
     "speex_resampler_init_frac", "speex_resampler_set_rate", "speex_resampler_set_rate_frac",
     "speex_resampler_set_quality",
     "speex_resampler_process_interleaved_float", "spxb_batch_create_f32", "spxb_batch_is_f32",
-    "spxb_batch_process_f32", "spxb_batch_get_state_f32", "spxb_batch_set_state_f32", "spxb_plan_call_f32",
+    "spxb_batch_process_f32", "spxb_batch_get_state_f32", "spxb_batch_set_state_f32", "spxb_plan_call_f32", "spxb_plan_call_ex",
 )
 
 KERNEL_AUTO, KERNEL_STRICT, KERNEL_TILED, KERNEL_TENSOR = 0, 1, 2, 3
@@ -111,6 +111,7 @@ def _bind(L):
     L.spxb_tensor_tap_tile.argtypes = [u32, u32, C.c_int, u32, u32, u32, vp, sz]
     L.spxb_plan_call.argtypes = [u32, u32, i32, u32, u32, u32, C.POINTER(CallPlan)]
     L.spxb_plan_call_f32.argtypes = [u32, u32, i32, u32, u32, u32, C.POINTER(CallPlan)]
+    L.spxb_plan_call_ex.argtypes = [u32, u32, i32, u32, u32, u32, u32, C.c_int, u32, C.POINTER(CallPlan), pu32]
     L.speex_resampler_init_frac.restype = vp
     L.speex_resampler_init_frac.argtypes = [u32, u32, u32, u32, u32, C.c_int, pint]
     L.speex_resampler_set_rate.argtypes = [vp, u32, u32]

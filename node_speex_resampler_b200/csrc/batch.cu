@@ -93,6 +93,8 @@ struct spxb_batch {
   // float sample occupies two of them.
   bool f32 = false;
   uint32_t hist_words = 1;  // int16 units per history sample
+  uint32_t in_block = kInBlock;           // input frames per block of the reference walk (call_plan.h)
+  const CallPlan *forced_plan = nullptr;  // set by the C API around a call that has magic samples pending
   uint32_t io_words = 1;    // int16 units per in/out sample of the call being issued
   // filter bank in HBM
   float *d_table = nullptr, *d_taps = nullptr, *d_blend = nullptr, *d_band = nullptr;
@@ -158,7 +160,7 @@ static CallPlan plan_memo(spxb_batch *b, StreamPos p, uint32_t n_in, uint32_t ca
       b->memo_pos.samp_frac_num == p.samp_frac_num && b->memo_n_in == n_in &&
       b->memo_cap == cap && b->memo_out_block == out_block)
     return b->memo_plan;
-  CallPlan pl = plan_call(b->spec.num, b->spec.den, p, n_in, cap, out_block);
+  CallPlan pl = plan_call(b->spec.num, b->spec.den, p, n_in, cap, out_block, b->in_block);
   b->memo_out_block = out_block;
   b->memo_valid = true;
   b->memo_pos = p;
@@ -437,7 +439,7 @@ struct Decided {
 static Decided decide_uniform(spxb_batch *b, uint32_t n_in, uint32_t cap) {
   Decided d;
   const StreamPos p = b->pos[0];
-  const CallPlan pl = plan_memo(b, p, n_in, cap);
+  const CallPlan pl = b->forced_plan ? *b->forced_plan : plan_memo(b, p, n_in, cap);
   d.uni = to_stream_call(p, n_in, pl);
   d.max_n_in = n_in;
   d.max_n_out = pl.n_out;
@@ -1333,6 +1335,25 @@ int spxb_plan_call(uint32_t in_rate, uint32_t out_rate, int32_t last_sample, uin
   return plan_call_any(in_rate, out_rate, last_sample, samp_frac_num, n_in, out_cap, kOutBlock, plan);
 }
 
+int spxb_plan_call_ex(uint32_t in_rate, uint32_t out_rate, int32_t last_sample, uint32_t samp_frac_num,
+                      uint32_t magic, uint32_t n_in, uint32_t out_cap, int float_entry, uint32_t in_block,
+                      spxb_call_plan *plan, uint32_t *magic_used) {
+  if (!plan || in_rate == 0 || out_rate == 0 || last_sample < 0 || in_block == 0) return RESAMPLER_ERR_INVALID_ARG;
+  FilterSpec s;
+  if (int e = derive_filter_spec(in_rate, out_rate, 0, &s)) return e;
+  if (samp_frac_num >= s.den) return RESAMPLER_ERR_INVALID_ARG;
+  StreamPos p;
+  p.last_sample = last_sample;
+  p.samp_frac_num = samp_frac_num;
+  const MagicPlan mp = plan_call_magic(s.num, s.den, p, magic, n_in, out_cap, float_entry != 0, in_block);
+  plan->n_out = mp.plan.n_out;
+  plan->consumed = mp.plan.consumed;
+  plan->last_sample = mp.plan.next.last_sample;
+  plan->samp_frac_num = mp.plan.next.samp_frac_num;
+  if (magic_used) *magic_used = mp.magic_used;
+  return 0;
+}
+
 int spxb_plan_call_f32(uint32_t in_rate, uint32_t out_rate, int32_t last_sample, uint32_t samp_frac_num,
                        uint32_t n_in, uint32_t out_cap, spxb_call_plan *plan) {
   return plan_call_any(in_rate, out_rate, last_sample, samp_frac_num, n_in, out_cap, kOutBlockUnbounded, plan);
@@ -1361,4 +1382,9 @@ static int plan_call_any(uint32_t in_rate, uint32_t out_rate, int32_t last_sampl
 namespace spxb {
 const FilterSpec &batch_spec(const spxb_batch *b) { return b->spec; }
 int batch_kernel_pref(const spxb_batch *b) { return b->kernel_pref; }
+void batch_set_in_block(spxb_batch *b, uint32_t in_block) {
+  b->in_block = in_block ? in_block : kInBlock;
+  b->memo_valid = false;
+}
+void batch_force_plan(spxb_batch *b, const CallPlan *plan) { b->forced_plan = plan; }
 }

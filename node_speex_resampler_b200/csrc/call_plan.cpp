@@ -19,7 +19,7 @@ inline uint64_t outputs_before(int64_t ls, uint64_t frac, uint64_t limit, uint64
 }  // namespace
 
 CallPlan plan_call(uint32_t num, uint32_t den, StreamPos pos, uint32_t n_in, uint32_t out_cap,
-                   uint32_t out_block) {
+                   uint32_t out_block, uint32_t in_block) {
   CallPlan plan;
   int64_t ls = pos.last_sample;
   uint64_t frac = pos.samp_frac_num;
@@ -39,7 +39,7 @@ CallPlan plan_call(uint32_t num, uint32_t den, StreamPos pos, uint32_t n_in, uin
 
   // resample.c:988 `while (ilen && olen)`
   while (left_in != 0 && left_out != 0) {
-    const uint64_t take = std::min<uint64_t>(left_in, kInBlock);
+    const uint64_t take = std::min<uint64_t>(left_in, in_block);
     const uint64_t room = std::min<uint64_t>(left_out, out_block);
     const uint64_t made = std::min(room, outputs_before(ls, frac, take, num, den));
     const uint64_t adv = frac + made * num;
@@ -56,6 +56,60 @@ CallPlan plan_call(uint32_t num, uint32_t den, StreamPos pos, uint32_t n_in, uin
   plan.next.last_sample = static_cast<int32_t>(ls);
   plan.next.samp_frac_num = static_cast<uint32_t>(frac);
   return plan;
+}
+
+MagicPlan plan_call_magic(uint32_t num, uint32_t den, StreamPos pos, uint32_t magic, uint32_t n_in,
+                          uint32_t out_cap, bool float_entry, uint32_t in_block) {
+  int64_t ls = pos.last_sample;
+  uint64_t frac = pos.samp_frac_num;
+  uint64_t left_in = n_in, left_out = out_cap, m = magic;
+  // one block of `len` input frames with room for `room` outputs (process_native, resample.c:878-902)
+  auto block = [&](uint64_t len, uint64_t room, uint64_t *made_out) {
+    const uint64_t made = std::min(room, outputs_before(ls, frac, len, num, den));
+    const uint64_t adv = frac + made * num;
+    ls += static_cast<int64_t>(adv / den);
+    frac = adv % den;
+    const uint64_t used = (ls < static_cast<int64_t>(len)) ? static_cast<uint64_t>(ls) : len;
+    ls -= static_cast<int64_t>(used);
+    *made_out = made;
+    return used;
+  };
+  if (float_entry) {  // resample.c:940-962
+    if (m) {
+      uint64_t made = 0;
+      m -= block(m, left_out, &made);
+      left_out -= made;
+    }
+    if (!m) {
+      while (left_in != 0 && left_out != 0) {
+        uint64_t made = 0;
+        left_in -= block(std::min<uint64_t>(left_in, in_block), left_out, &made);
+        left_out -= made;
+      }
+    }
+  } else {  // resample.c:988-1029
+    while (left_in != 0 && left_out != 0) {
+      uint64_t room = std::min<uint64_t>(left_out, kOutBlock);
+      if (m) {
+        uint64_t made = 0;
+        m -= block(m, room, &made);
+        room -= made;
+        left_out -= made;
+      }
+      if (!m) {
+        uint64_t made = 0;
+        left_in -= block(std::min<uint64_t>(left_in, in_block), room, &made);
+        left_out -= made;
+      }
+    }
+  }
+  MagicPlan r;
+  r.plan.n_out = static_cast<uint32_t>(out_cap - left_out);
+  r.plan.consumed = static_cast<uint32_t>(n_in - left_in);
+  r.plan.next.last_sample = static_cast<int32_t>(ls);
+  r.plan.next.samp_frac_num = static_cast<uint32_t>(frac);
+  r.magic_used = static_cast<uint32_t>(magic - m);
+  return r;
 }
 
 }  // namespace spxb

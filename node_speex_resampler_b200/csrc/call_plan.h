@@ -36,7 +36,22 @@ struct CallPlan {
 // stack buffer), unbounded on the float entry, which writes straight into the caller's buffer
 // (resample.c:944 `ochunk = olen`).
 constexpr uint32_t kOutBlockUnbounded = 0xffffffffu;
+// in_block: input frames one block may take -- mem_alloc_size - (filt_len - 1) of the reference
+// state: kInBlock for a fresh state, larger once a filter change has shortened the filter (the
+// reference never shrinks its memory, resample.c:709-719).
 CallPlan plan_call(uint32_t num, uint32_t den, StreamPos pos, uint32_t n_in, uint32_t out_cap,
-                   uint32_t out_block = kOutBlock);
+                   uint32_t out_block = kOutBlock, uint32_t in_block = kInBlock);
+
+// A call on a state that holds `magic` pending samples (left in its memory by a filter change
+// that shortened the filter, resample.c:759-776): they are resampled first, as one block of their
+// own (speex_resampler_magic, :904-922), sharing the first iteration's output block with the first
+// input block on the int16 entry (:993-1016) and taking all the capacity left on the float entry
+// (:940-941). plan.consumed counts REAL input frames; magic_used the pending samples consumed.
+struct MagicPlan {
+  CallPlan plan;
+  uint32_t magic_used = 0;
+};
+MagicPlan plan_call_magic(uint32_t num, uint32_t den, StreamPos pos, uint32_t magic, uint32_t n_in,
+                          uint32_t out_cap, bool float_entry, uint32_t in_block);
 
 }  // namespace spxb

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/speexb200.h"
+#include "call_plan.h"
 #include "filter_bank.h"
 
 #include <string>
@@ -15,6 +16,8 @@
 namespace spxb {
 const FilterSpec &batch_spec(const spxb_batch *b);
 int batch_kernel_pref(const spxb_batch *b);
+void batch_set_in_block(spxb_batch *b, uint32_t in_block);
+void batch_force_plan(spxb_batch *b, const CallPlan *plan);
 void set_error(const std::string &msg);
 }
 
@@ -24,6 +27,16 @@ struct SpeexResamplerState_ {
   uint32_t ratio_num = 0, ratio_den = 0;  // as given (the filter depends on their reduced ratio only)
   int quality = 0;
   bool started = false;  // a call has reached the resampling loop (resample.c:881 `st->started = 1`)
+  // the reference's memory only grows (resample.c:709-719): samples per channel it has room for.
+  // mem_alloc - (filt_len - 1) is the input block of its walk (160 unless a filter got shorter).
+  uint32_t mem_alloc = 0;
+  // "magic samples" (resample.c:759-776): frames a filter shortening left over, resampled before
+  // the next input; interleaved, in the batch's sample format (one of the two vectors is used)
+  uint32_t magic = 0;
+  std::vector<int16_t> magic_i;
+  std::vector<float> magic_f;
+  std::vector<int16_t> joined_i;  // magic ++ input of the call being issued
+  std::vector<float> joined_f;
   std::vector<int16_t> silence;  // stands in for in == NULL (resample.c:1007-1010)
   std::vector<float> fsilence;   // the same for the float entry (resample.c:950-952)
 };
@@ -61,6 +74,7 @@ SpeexResamplerState *speex_resampler_init_frac(uint32_t nb_channels, uint32_t ra
   st->ratio_den = ratio_den;
   st->channels = nb_channels;
   st->quality = quality;
+  st->mem_alloc = spxb::batch_spec(st->batch).taps - 1 + spxb::kInBlock;  // resample.c:835, :709
   if (err) *err = RESAMPLER_ERR_SUCCESS;
   return st;
 }
@@ -108,10 +122,12 @@ static int refilter(SpeexResamplerState *st, uint32_t ratio_num, uint32_t ratio_
   spxb::FilterSpec next;
   if (int e = spxb::derive_filter_spec(ratio_num, ratio_den, quality, &next)) return e;
   const spxb::FilterSpec old = spxb::batch_spec(st->batch);
-  if (st->started && next.taps < old.taps) {
-    spxb::set_error("shortening the filter after samples have been resampled (magic samples) is not supported");
+  if (st->magic != 0 && next.taps != old.taps) {
+    spxb::set_error("changing the filter length again while magic samples are pending is not supported");
     return RESAMPLER_ERR_BAD_STATE;
   }
+  const bool shrink = st->started && next.taps < old.taps;
+  const uint32_t new_magic = shrink ? (old.taps - next.taps) / 2 : 0;  // resample.c:767
   const bool f32 = spxb_batch_is_f32(st->batch) != 0;
   int32_t last = 0;
   uint32_t frac = 0, magic = 0;
@@ -128,10 +144,23 @@ static int refilter(SpeexResamplerState *st, uint32_t ratio_num, uint32_t ratio_
     if (frac != 0 && frac > 0xffffffffu / next.den) return RESAMPLER_ERR_OVERFLOW;  // multiply_frac's check
     if (scaled >= next.den) scaled = next.den - 1;
     frac = static_cast<uint32_t>(scaled);
-    const size_t pad = new_live - old_live;  // >= 0: growth or same length
-    if (f32) std::copy(hist_f.begin(), hist_f.begin() + old_live, grown_f.begin() + pad);
-    else std::copy(hist_i.begin(), hist_i.begin() + old_live, grown_i.begin() + pad);
-    last += static_cast<int32_t>((next.taps - old.taps) / 2);  // :748
+    if (!shrink) {
+      const size_t pad = new_live - old_live;  // >= 0: growth or same length
+      if (f32) std::copy(hist_f.begin(), hist_f.begin() + old_live, grown_f.begin() + pad);
+      else std::copy(hist_i.begin(), hist_i.begin() + old_live, grown_i.begin() + pad);
+      last += static_cast<int32_t>((next.taps - old.taps) / 2);  // :748
+    } else {
+      // :770-771 mem[j] = mem[j + magic] for j < filt_len - 1 + magic: the first filt_len - 1 are the
+      // new history, the next `magic` frames wait to be resampled before the next input
+      const size_t ch = st->channels, skip = static_cast<size_t>(new_magic) * ch;
+      if (f32) {
+        std::copy(hist_f.begin() + skip, hist_f.begin() + skip + new_live, grown_f.begin());
+        st->magic_f.assign(hist_f.begin() + skip + new_live, hist_f.begin() + skip + new_live + skip);
+      } else {
+        std::copy(hist_i.begin() + skip, hist_i.begin() + skip + new_live, grown_i.begin());
+        st->magic_i.assign(hist_i.begin() + skip + new_live, hist_i.begin() + skip + new_live + skip);
+      }
+    }
   } else {
     frac = 0;
   }
@@ -147,8 +176,49 @@ static int refilter(SpeexResamplerState *st, uint32_t ratio_num, uint32_t ratio_
   spxb_batch_set_kernel(nb, spxb::batch_kernel_pref(st->batch));
   spxb_batch_destroy(st->batch);
   st->batch = nb;
+  if (shrink) st->magic = new_magic;
+  st->mem_alloc = std::max(st->mem_alloc, next.taps - 1 + spxb::kInBlock);  // :709-719: never shrinks
+  spxb::batch_set_in_block(nb, st->mem_alloc - (next.taps - 1));
   return RESAMPLER_ERR_SUCCESS;
 }
+
+// A call while magic samples are pending (resample.c:993-1016 int16 entry, :940-962 float entry):
+// the pending frames go in front of the caller's input, the lengths follow the reference's walk
+// (call_plan.h: plan_call_magic) and the kernels see one call over the joined input.
+extern "C++" {
+template <typename T>
+static int process_with_magic(SpeexResamplerState *st, const T *in, uint32_t *in_len, T *out, uint32_t *out_len,
+                              std::vector<T> &magic, std::vector<T> &joined, bool float_entry) {
+  const spxb::FilterSpec &s = spxb::batch_spec(st->batch);
+  const size_t ch = st->channels;
+  int32_t last = 0;
+  uint32_t frac = 0, mg = 0;
+  if (int e = spxb_batch_get_state(st->batch, 0, &last, &frac, &mg, nullptr)) return e;
+  spxb::StreamPos pos;
+  pos.last_sample = last;
+  pos.samp_frac_num = frac;
+  const uint32_t in_block = st->mem_alloc - (s.taps - 1);
+  const spxb::MagicPlan mp = spxb::plan_call_magic(s.num, s.den, pos, st->magic, *in_len, *out_len, float_entry, in_block);
+  joined.assign(magic.begin(), magic.begin() + static_cast<size_t>(st->magic) * ch);
+  joined.insert(joined.end(), in, in + static_cast<size_t>(*in_len) * ch);
+  spxb::CallPlan forced = mp.plan;
+  forced.consumed = mp.magic_used + mp.plan.consumed;  // what the history slides by
+  uint32_t n_total = st->magic + *in_len, n_cap = *out_len;
+  spxb::batch_force_plan(st->batch, &forced);
+  const int e = float_entry
+                    ? spxb_batch_process_f32(st->batch, reinterpret_cast<const float *>(joined.data()), n_total, &n_total,
+                                             reinterpret_cast<float *>(out), n_cap, &n_cap)
+                    : spxb_batch_process(st->batch, reinterpret_cast<const int16_t *>(joined.data()), n_total, &n_total,
+                                         reinterpret_cast<int16_t *>(out), n_cap, &n_cap);
+  spxb::batch_force_plan(st->batch, nullptr);
+  if (e) return e;
+  magic.erase(magic.begin(), magic.begin() + static_cast<size_t>(mp.magic_used) * ch);
+  st->magic -= mp.magic_used;
+  *in_len = mp.plan.consumed;
+  *out_len = mp.plan.n_out;
+  return RESAMPLER_ERR_SUCCESS;
+}
+}  // extern "C++"
 
 int speex_resampler_set_rate_frac(SpeexResamplerState *st, uint32_t ratio_num, uint32_t ratio_den, uint32_t in_rate,
                                   uint32_t out_rate) {
@@ -182,7 +252,12 @@ int speex_resampler_set_quality(SpeexResamplerState *st, int quality) {
 
 int speex_resampler_skip_zeros(SpeexResamplerState *st) { return spxb_batch_skip_zeros(st->batch); }
 
-int speex_resampler_reset_mem(SpeexResamplerState *st) { return spxb_batch_reset(st->batch); }
+int speex_resampler_reset_mem(SpeexResamplerState *st) {
+  st->magic = 0;  // resample.c:1213
+  st->magic_i.clear();
+  st->magic_f.clear();
+  return spxb_batch_reset(st->batch);
+}
 
 int speex_resampler_process_interleaved_int(SpeexResamplerState *st, const int16_t *in, uint32_t *in_len,
                                             int16_t *out, uint32_t *out_len) {
@@ -192,6 +267,18 @@ int speex_resampler_process_interleaved_int(SpeexResamplerState *st, const int16
     in = st->silence.data();
   }
   if (*in_len != 0 && *out_len != 0) st->started = true;
+  if (st->magic != 0) {
+    if (spxb_batch_is_f32(st->batch)) {
+      spxb::set_error("int16 call on a float-history state with magic samples pending is not supported");
+      return RESAMPLER_ERR_BAD_STATE;
+    }
+    if (*in_len == 0 || *out_len == 0) {  // resample.c:988: the loop does not run, nothing moves
+      *in_len = 0;
+      *out_len = 0;
+      return RESAMPLER_ERR_SUCCESS;
+    }
+    return process_with_magic<int16_t>(st, in, in_len, out, out_len, st->magic_i, st->joined_i, false);
+  }
   // one stream: the strides are irrelevant, the lengths are the in-out cells
   return spxb_batch_process(st->batch, in, *in_len, in_len, out, *out_len, out_len);
 }
@@ -223,6 +310,13 @@ int speex_resampler_process_interleaved_float(SpeexResamplerState *st, const flo
     in = st->fsilence.data();
   }
   if (*in_len != 0 && *out_len != 0) st->started = true;
+  if (st->magic != 0) {
+    if (st->magic_f.empty()) {  // the state turned float after the filter change
+      st->magic_f.assign(st->magic_i.begin(), st->magic_i.end());
+      st->magic_i.clear();
+    }
+    return process_with_magic<float>(st, in, in_len, out, out_len, st->magic_f, st->joined_f, true);
+  }
   return spxb_batch_process_f32(st->batch, in, *in_len, in_len, out, *out_len, out_len);
 }
 

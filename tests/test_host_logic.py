@@ -195,3 +195,43 @@ def test_init_frac_argument_checks_precede_any_allocation():
     else:
         assert st and err.value == 0
         L.speex_resampler_destroy(st)
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built on this machine")
+@pytest.mark.parametrize("float_entry", [False, True], ids=["int16_entry", "float_entry"])
+def test_call_plan_with_magic_samples_matches_the_reference_walk(float_entry):
+    """The reference build driven through filter changes that shorten the filter mid-stream
+    (magic samples pending, memory larger than the filter needs -> input block > 160), then
+    through calls of random sizes and capacities: spxb_plan_call_ex must predict consumed /
+    written and the next position of every call from the state before it."""
+    L, R = lib(), O._load_ref()
+    R.speex_resampler_set_quality.restype = R.speex_resampler_set_rate.restype = C.c_int
+    R.speex_resampler_set_quality.argtypes = [C.c_void_p, C.c_int]
+    R.speex_resampler_set_rate.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    rng = np.random.default_rng(17 + float_entry)
+    for (i, o, q0, changes) in ((44100, 48000, 10, [("q", 3)]), (48000, 16000, 8, [("r", 48000, 32000)]),
+                               (96000, 44100, 10, [("q", 5), ("q", 5)]), (8000, 96000, 9, [("q", 0)])):
+        r = O.RefResampler(1, i, o, q0)
+        st = r._st()
+        r.process(rng.integers(-9000, 9000, 700).astype(np.int16), 4000)       # started
+        for chg in changes:
+            if chg[0] == "q":
+                assert R.speex_resampler_set_quality(r.h, chg[1]) == 0
+            else:
+                assert R.speex_resampler_set_rate(r.h, chg[1], chg[2]) == 0
+                i, o = chg[1], chg[2]
+        assert st.magic_samples[0] > 0
+        for k in range(25):
+            n = int(rng.choice([0, 1, 50, 160, 161, 400, 1000]))
+            cap = int(rng.choice([0, 1, 7, 60, 300, 1023, 1024, 1025, 3000]))
+            ls, fr, mg = st.last_sample[0], st.samp_frac_num[0], st.magic_samples[0]
+            in_block = st.mem_alloc_size - (st.filt_len - 1)
+            plan, used = _lib.CallPlan(), C.c_uint32(0)
+            assert L.spxb_plan_call_ex(i, o, ls, fr, mg, n, cap, int(float_entry), in_block, C.byref(plan),
+                                       C.byref(used)) == 0
+            if float_entry:
+                _, u, m = r.process_float(np.zeros(n, np.float32), cap)
+            else:
+                _, u, m = r.process(np.zeros(n, np.int16), cap)
+            assert (plan.consumed, plan.n_out, plan.last_sample, plan.samp_frac_num, mg - used.value) == \
+                (u, m, st.last_sample[0], st.samp_frac_num[0], st.magic_samples[0]), (i, o, k, n, cap, mg)

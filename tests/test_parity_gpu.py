@@ -692,8 +692,8 @@ def test_one_shot_long_chunk_on_the_tensor_kernel():
 def test_c_api_filter_changes_before_the_first_sample_match_the_reference():
     """init_frac / set_quality / set_rate / set_rate_frac / skip_zeros before any sample has been
     resampled (resample.c:1107-1163 with update_filter's !started branch): same lengths and bytes
-    as the reference's own build given the same call sequence; the mid-stream change (magic
-    samples) is refused without touching the state."""
+    as the reference's own build given the same call sequence (mid-stream changes have their own
+    tests below)."""
     L, R = lib(), O._load_ref()
     R.speex_resampler_init_frac.restype = C.c_void_p
     R.speex_resampler_init_frac.argtypes = [C.c_uint32] * 5 + [C.c_int, C.POINTER(C.c_int)]
@@ -734,10 +734,9 @@ def test_c_api_filter_changes_before_the_first_sample_match_the_reference():
             res.append((n_in.value, n_out.value, out[: n_out.value * ch].copy()))
         assert res[0][:2] == res[1][:2]
         assert np.array_equal(res[0][2], res[1][2])
-    # mid-stream, shorter filter (magic samples): refused, and the stream carries on untouched
-    assert L.speex_resampler_set_quality(ours, 5) == 2            # RESAMPLER_ERR_BAD_STATE
-    assert "magic samples" in _lib.last_error()
-    assert L.speex_resampler_set_rate_frac(ours, 640, 294, 96000, 44100) == 0   # same reduced ratio: no filter change
+    # the same reduced ratio under other numbers: no filter change on either side
+    assert L.speex_resampler_set_rate_frac(ours, 640, 294, 96000, 44100) == 0
+    assert R.speex_resampler_set_rate_frac(ref, 640, 294, 96000, 44100) == 0
     L.speex_resampler_destroy(ours)
     R.speex_resampler_destroy(ref)
 
@@ -792,8 +791,60 @@ def test_c_api_mid_stream_rate_and_quality_changes_match_the_reference(ch):
     both(441, 600)
     change("speex_resampler_set_quality", 10)
     both(441, 600)
-    assert L.speex_resampler_set_rate(ours, 44100, 44100) == 2   # would shorten the filter: refused ...
+    # shorter filters: the surplus history becomes "magic samples", resampled before the next input
+    # (resample.c:759-776, :904-922); the reference's memory does not shrink, so its input block grows
+    change("speex_resampler_set_rate", 44100, 44100)
+    both(100, 7)                                          # capacity binds inside the magic block
+    both(0, 50)                                           # nothing moves without input (resample.c:988)
+    both(441, 30)
+    both(441, 600)
+    both(1000, 600)                                       # input block > 160 shows in a capacity-bound call
+    change("speex_resampler_set_quality", 1)
+    both(300, 600)
+    both(441, 600)
+    assert L.speex_resampler_set_quality(ours, 0) == 0 and R.speex_resampler_set_quality(ref, 0) == 0
+    assert L.speex_resampler_set_quality(ours, 4) == 2   # a second length change with magic pending: refused
     assert "magic samples" in _lib.last_error()
-    both(441, 600)                                               # ... and the state is untouched
+    L.speex_resampler_destroy(ours)
+    R.speex_resampler_destroy(ref)
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not present")
+def test_c_api_magic_samples_on_the_float_entry_match_the_reference():
+    """float entry after a filter shortening (resample.c:940-941: the pending samples take all the
+    capacity that is left, then the input follows): every f32 bit and length against the
+    reference build"""
+    L, R = lib(), O._load_ref()
+    R.speex_resampler_set_quality.restype = C.c_int
+    R.speex_resampler_set_quality.argtypes = [C.c_void_p, C.c_int]
+    ch = 2
+    err = C.c_int(0)
+    ours = L.speex_resampler_init(ch, 48000, 32000, 9, C.byref(err))
+    ref = R.speex_resampler_init(ch, 48000, 32000, 9, C.byref(err))
+    x = (synth_pcm(1, ch, 6000, 48000, seed=321)[0].astype(np.float32) * np.float32(0.61)).astype(np.float32)
+    pos = [0]
+
+    def both(n, cap):
+        chunk = np.ascontiguousarray(x[pos[0] * ch:(pos[0] + n) * ch])
+        pos[0] += n
+        res = []
+        for lib_, st in ((L, ours), (R, ref)):
+            out = np.zeros(max(cap * ch, 1), np.float32)
+            n_in, n_out = C.c_uint32(n), C.c_uint32(cap)
+            buf = chunk if chunk.size else np.zeros(1, np.float32)
+            assert lib_.speex_resampler_process_interleaved_float(st, buf.ctypes.data, C.byref(n_in), out.ctypes.data,
+                                                                  C.byref(n_out)) == 0, _lib.last_error()
+            res.append((n_in.value, n_out.value, out[: n_out.value * ch].copy()))
+        assert res[0][:2] == res[1][:2], (pos[0], res[0][:2], res[1][:2])
+        assert np.array_equal(res[0][2].view(np.uint32), res[1][2].view(np.uint32)), pos[0]
+
+    both(480, 400)
+    both(333, 400)
+    assert L.speex_resampler_set_quality(ours, 2) == 0 and R.speex_resampler_set_quality(ref, 2) == 0
+    both(200, 5)      # capacity binds inside the magic block: no input is taken
+    both(200, 400)
+    both(7, 400)
+    both(1000, 100)
+    both(480, 400)
     L.speex_resampler_destroy(ours)
     R.speex_resampler_destroy(ref)
