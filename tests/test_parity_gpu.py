@@ -848,3 +848,52 @@ def test_c_api_magic_samples_on_the_float_entry_match_the_reference():
     both(480, 400)
     L.speex_resampler_destroy(ours)
     R.speex_resampler_destroy(ref)
+
+
+def test_batches_release_their_device_memory():
+    """create / use / destroy in a loop (uniform calls, a ragged call with cohorts, a captured hop
+    sequence, a float batch, a C-API state that changes filter): free device memory returns to
+    where it started"""
+    torch = pytest.importorskip("torch")
+    L = lib()
+    ch, i, o, q, S, n, cap = 2, 44100, 48000, 7, 96, 882, 962
+
+    def one_round():
+        b = StreamBatch(S, ch, i, o, q)
+        pcm = synth_pcm(S, ch, n, i, seed=3)
+        b.process(pcm, n, cap)
+        b.process(pcm, np.where(np.arange(S) < 48, n, 500).astype(np.uint32), cap)     # two cohorts
+        ts = torch.cuda.Stream()
+        assert L.spxb_batch_set_stream(b._h, C.c_void_p(ts.cuda_stream)) == 0
+        d_in = torch.zeros((2, S, n * ch), dtype=torch.int16, device="cuda")
+        d_out = torch.zeros((2, S, cap * ch), dtype=torch.int16, device="cuda")
+        c = StreamBatch(S, ch, i, o, q)
+        assert L.spxb_batch_set_stream(c._h, C.c_void_p(ts.cuda_stream)) == 0
+        for r in range(4):
+            assert L.spxb_batch_process_device_ring(c._h, d_in.data_ptr(), n, S * n * ch, d_out.data_ptr(), cap,
+                                                    S * cap * ch, 2, n, cap, r * 4, 4) == 0
+        torch.cuda.synchronize()
+        f = StreamBatch(4, ch, i, o, q, sample_format="f32")
+        f.process_f32(np.zeros((4, n * ch), np.float32), n, cap)
+        err = C.c_int(0)
+        st = L.speex_resampler_init(ch, i, o, 10, C.byref(err))
+        x = np.zeros(n * ch, np.int16)
+        out = np.zeros(cap * ch, np.int16)
+        a, bb = C.c_uint32(n), C.c_uint32(cap)
+        L.speex_resampler_process_interleaved_int(st, x.ctypes.data, C.byref(a), out.ctypes.data, C.byref(bb))
+        assert L.speex_resampler_set_quality(st, 3) == 0
+        a, bb = C.c_uint32(n), C.c_uint32(cap)
+        L.speex_resampler_process_interleaved_int(st, x.ctypes.data, C.byref(a), out.ctypes.data, C.byref(bb))
+        L.speex_resampler_destroy(st)
+        for h in (b, c, f):
+            h.close()
+        del d_in, d_out
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
+    one_round()                       # first round pays one-time costs (module load, pools)
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(12):
+        one_round()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < (8 << 20), (free0, free1)
