@@ -443,7 +443,8 @@ static Decided decide_uniform(spxb_batch *b, uint32_t n_in, uint32_t cap) {
   d.uni = to_stream_call(p, n_in, pl);
   d.max_n_in = n_in;
   d.max_n_out = pl.n_out;
-  d.any_work = n_in != 0 && cap != 0;
+  // (a forced plan -- magic samples pending -- may consume without producing: resample.c:904-922)
+  d.any_work = b->forced_plan ? (pl.consumed != 0 || pl.n_out != 0) : (n_in != 0 && cap != 0);
   if (d.any_work) {
     // all shadows advance together; inside a hop sequence only pos[0] is kept exact and the
     // rest are mirrored once at its end (ring_hops)

@@ -115,9 +115,9 @@ int speex_resampler_get_output_latency(SpeexResamplerState *st) {
 //    denominator (:1131-1140, multiply_frac :593-603);
 //  * mid-stream, longer filter (:727-758 with no magic samples pending): the old history moves to
 //    the end of the new one behind zeros and last_sample advances by half the growth;
-//  * mid-stream, shorter filter: the reference keeps the surplus history as "magic samples" that
-//    are resampled before the next input (:759-776, :904-922) -- not implemented:
-//    RESAMPLER_ERR_BAD_STATE, state untouched.
+//  * mid-stream, shorter filter: the surplus history stays behind as "magic samples" that the next
+//    calls resample before their own input (:759-776, :904-922; process_with_magic below). Only a
+//    further change of the filter LENGTH while such samples are pending is refused.
 static int refilter(SpeexResamplerState *st, uint32_t ratio_num, uint32_t ratio_den, int quality) {
   spxb::FilterSpec next;
   if (int e = spxb::derive_filter_spec(ratio_num, ratio_den, quality, &next)) return e;

@@ -842,6 +842,7 @@ def test_c_api_magic_samples_on_the_float_entry_match_the_reference():
     both(333, 400)
     assert L.speex_resampler_set_quality(ours, 2) == 0 and R.speex_resampler_set_quality(ref, 2) == 0
     both(200, 5)      # capacity binds inside the magic block: no input is taken
+    both(50, 0)       # no room at all: the pending samples the read position has passed are still consumed
     both(200, 400)
     both(7, 400)
     both(1000, 100)
