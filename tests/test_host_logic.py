@@ -235,3 +235,33 @@ def test_call_plan_with_magic_samples_matches_the_reference_walk(float_entry):
                 _, u, m = r.process(np.zeros(n, np.int16), cap)
             assert (plan.consumed, plan.n_out, plan.last_sample, plan.samp_frac_num, mg - used.value) == \
                 (u, m, st.last_sample[0], st.samp_frac_num[0], st.magic_samples[0]), (i, o, k, n, cap, mg)
+
+
+def test_wav_pcm_finds_the_payload(tmp_path):
+    """the reference's fixtures are WAV files; the helper returns format + PCM bytes"""
+    import io
+    import wave
+
+    from node_speex_resampler_b200 import wav_pcm
+    frames = (np.arange(1000 * 2, dtype=np.int32) * 37 % 65536 - 32768).astype(np.int16)
+    buf = io.BytesIO()
+    with wave.open(buf, "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(2)
+        w.setframerate(44100)
+        w.writeframes(frames.tobytes())
+    blob = buf.getvalue()
+    info = wav_pcm(blob)
+    assert (info.channels, info.sample_rate, info.bits_per_sample, info.format_tag) == (2, 44100, 16, 1)
+    assert bytes(info.data) == frames.tobytes()
+    # an extra odd-sized chunk in front of `data`, and a truncated data chunk
+    riff = bytearray(blob[:36]) + b"LIST" + (3).to_bytes(4, "little") + b"abc\0" + blob[36:]
+    riff[4:8] = (len(riff) - 8).to_bytes(4, "little")
+    assert bytes(wav_pcm(bytes(riff)).data) == frames.tobytes()
+    assert len(wav_pcm(blob[:-3]).data) == frames.nbytes - 4       # whole frames only
+    with pytest.raises(ValueError):
+        wav_pcm(b"RIFX" + blob[4:])
+    res = "/root/reference/resources/44100hz_test.pcm"
+    if os.path.exists(res):                                        # the reference's own fixture
+        info = wav_pcm(open(res, "rb").read())
+        assert (info.channels, info.sample_rate, info.bits_per_sample) == (2, 44100, 16)
