@@ -265,3 +265,34 @@ def test_wav_pcm_finds_the_payload(tmp_path):
     if os.path.exists(res):                                        # the reference's own fixture
         info = wav_pcm(open(res, "rb").read())
         assert (info.channels, info.sample_rate, info.bits_per_sample) == (2, 44100, 16)
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built on this machine")
+def test_call_plan_input_block_after_a_filter_got_shorter_before_the_first_sample():
+    """The reference's memory never shrinks (resample.c:709-719): a state initialised with a long
+    filter and switched to a short one BEFORE any sample keeps the long filter's room, so its walk
+    takes input blocks longer than 160 frames. spxb_plan_call_ex with that input block must track
+    the reference call for call, capacity-bound calls included."""
+    L, R = lib(), O._load_ref()
+    R.speex_resampler_set_quality.restype = C.c_int
+    R.speex_resampler_set_quality.argtypes = [C.c_void_p, C.c_int]
+    rng = np.random.default_rng(23)
+    r = O.RefResampler(1, 8000, 96000, 10)
+    assert R.speex_resampler_set_quality(r.h, 1) == 0
+    st = r._st()
+    in_block = st.mem_alloc_size - (st.filt_len - 1)
+    assert in_block > 160 and st.magic_samples[0] == 0
+    differs = 0
+    for k in range(60):
+        n = int(rng.choice([100, 161, 400, 1000]))
+        cap = int(rng.choice([7, 300, 1023, 1500, 3000]))
+        ls, fr = st.last_sample[0], st.samp_frac_num[0]
+        plan, used, plain = _lib.CallPlan(), C.c_uint32(0), _lib.CallPlan()
+        assert L.spxb_plan_call_ex(8000, 96000, ls, fr, 0, n, cap, 0, in_block, C.byref(plan), C.byref(used)) == 0
+        assert L.spxb_plan_call(8000, 96000, ls, fr, n, cap, C.byref(plain)) == 0
+        _, u, m = r.process(np.zeros(n, np.int16), cap)
+        assert (plan.consumed, plan.n_out, plan.last_sample, plan.samp_frac_num) == \
+            (u, m, st.last_sample[0], st.samp_frac_num[0]), (k, n, cap)
+        differs += (plain.consumed, plain.n_out) != (u, m)
+    # (whether the plain 160-frame walk would have differed depends on the ratio; the point is that
+    # the walk with the state's real block size is exact)
