@@ -15,6 +15,8 @@
  *   batchProcess(batch, chunks: Buffer[], capFrames: Uint32Array): Buffer[]
  *   batchAdopt(batch, streamIndex, handle): void            migrate a single stream's state
  *   batchDestroy(batch): void
+ *   setKernel(handle, kernel): void / batchSetKernel(batch, kernel): void
+ *                                                   0 auto, 1 strict (bit-exact), 2 tiled, 3 tensor
  *
  * Built by binding.gyp (node-gyp) against include/speexb200.h; no Node toolchain exists in the
  * image this repository is developed in, so tests/test_node_binding.py compiles this file
@@ -43,6 +45,8 @@ typedef struct {
   size_t in_cap, out_cap; /* int16 elements */
   uint32_t *in_frames, *out_frames;
 } spx_batch;
+
+static int16_t empty_frame; /* stands in for the data pointer of a zero-length Buffer */
 
 static napi_value throw_text(napi_env env, const char *msg) {
   napi_throw_error(env, NULL, msg);
@@ -159,6 +163,10 @@ static napi_value js_process(napi_env env, napi_callback_info info) {
   out_len = cap;
   if (napi_create_buffer(env, (size_t)cap * h->channels * 2, &out, &r) != napi_ok)
     return throw_code(env, RESAMPLER_ERR_ALLOC_FAILED);
+  /* N-API may hand out NULL for the data of a zero-length Buffer; the reference returns an empty
+   * Buffer for an empty chunk (its loop does not run), so never pass NULL down */
+  if (!in) in = &empty_frame;
+  if (!out) out = &empty_frame;
   err = speex_resampler_process_interleaved_int(h->st, (const int16_t *)in, &in_len, (int16_t *)out, &out_len);
   if (err) return throw_code(env, err);
   if (out_len != cap) {
@@ -317,6 +325,36 @@ static napi_value js_batch_destroy(napi_env env, napi_callback_info info) {
   return NULL;
 }
 
+/* setKernel(handle, kernel) / batchSetKernel(batch, kernel): kernel family of include/speexb200.h
+ * (SPXB_KERNEL_*). A single stream defaults to the bit-exact kernel, a batch to AUTO. */
+static napi_value js_set_kernel(napi_env env, napi_callback_info info) {
+  napi_value argv[SPX_MAX_ARGS];
+  spx_handle *h = NULL;
+  uint32_t k = 0;
+  int err;
+  if (!get_args(env, info, 2, argv)) return NULL;
+  if (napi_get_value_external(env, argv[0], (void **)&h) != napi_ok || !h || !h->st)
+    return throw_code(env, RESAMPLER_ERR_BAD_STATE);
+  if (!get_u32(env, argv[1], &k)) return NULL;
+  err = spxb_batch_set_kernel(spxb_resampler_batch(h->st), (int)k);
+  if (err) return throw_code(env, err);
+  return NULL;
+}
+
+static napi_value js_batch_set_kernel(napi_env env, napi_callback_info info) {
+  napi_value argv[SPX_MAX_ARGS];
+  spx_batch *bt = NULL;
+  uint32_t k = 0;
+  int err;
+  if (!get_args(env, info, 2, argv)) return NULL;
+  if (napi_get_value_external(env, argv[0], (void **)&bt) != napi_ok || !bt || !bt->b)
+    return throw_code(env, RESAMPLER_ERR_BAD_STATE);
+  if (!get_u32(env, argv[1], &k)) return NULL;
+  err = spxb_batch_set_kernel(bt->b, (int)k);
+  if (err) return throw_code(env, err);
+  return NULL;
+}
+
 #define SPX_METHOD(name, fn) \
   { name, NULL, fn, NULL, NULL, NULL, napi_default, NULL }
 
@@ -326,7 +364,8 @@ NAPI_MODULE_INIT() {
       SPX_METHOD("init", js_init),                  SPX_METHOD("process", js_process),
       SPX_METHOD("destroy", js_destroy),            SPX_METHOD("batchCreate", js_batch_create),
       SPX_METHOD("batchProcess", js_batch_process), SPX_METHOD("batchAdopt", js_batch_adopt),
-      SPX_METHOD("batchDestroy", js_batch_destroy),
+      SPX_METHOD("batchDestroy", js_batch_destroy), SPX_METHOD("setKernel", js_set_kernel),
+      SPX_METHOD("batchSetKernel", js_batch_set_kernel),
   };
   napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
   return exports;

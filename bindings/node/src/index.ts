@@ -25,7 +25,12 @@ interface Addon {
   batchProcess(batch: object, chunks: Buffer[], capFrames: Uint32Array): Buffer[];
   batchAdopt(batch: object, streamIndex: number, handle: object): void;
   batchDestroy(batch: object): void;
+  setKernel(handle: object, kernel: number): void;
+  batchSetKernel(batch: object, kernel: number): void;
 }
+
+/** kernel families of include/speexb200.h (SPXB_KERNEL_*) */
+export const KERNEL_AUTO = 0, KERNEL_STRICT = 1, KERNEL_TILED = 2, KERNEL_TENSOR = 3;
 
 let addon: Addon | undefined;
 // The reference resolves this promise when the WASM module has compiled (src/index.ts:19);
@@ -51,6 +56,12 @@ class SpeexResampler {
   _batchIndex = -1;
 
   static initPromise = globalModulePromise as Promise<any>;
+
+  /** Kernel family (not in the reference). processChunk / the Transform default to the bit-exact
+    * kernel -- the reference's bytes --, the tensor-core kernel (+-1 LSB, >= 90 dB) is opt-in there;
+    * processChunks, whose purpose is throughput, defaults to AUTO (tensor when the call qualifies). */
+  kernel = KERNEL_STRICT;
+  static batchKernel = KERNEL_AUTO;
 
   /**
     * channels: interleaved channel count (>= 1); inRate / outRate: sample rates in Hz;
@@ -94,6 +105,7 @@ class SpeexResampler {
       // lazy init; a failed init throws strerror(err) and leaves _handle unset so that the next
       // call retries (src/index.ts:59-65)
       this._handle = addon!.init(this.channels, this.inRate, this.outRate, this.quality);
+      addon!.setKernel(this._handle, this.kernel);
     }
     return addon!.process(this._handle, chunk, this._capacityFrames(chunk.length));
   }
@@ -147,6 +159,7 @@ class StreamGroup {
     this.members = members;
     this.batch = addon!.batchCreate(members.length, r.channels, r.inRate, r.outRate, r.quality, 0);
     this.caps = new Uint32Array(members.length);
+    addon!.batchSetKernel(this.batch, SpeexResampler.batchKernel);
     members.forEach((m, i) => {
       if (m._handle) {
         // the stream already ran through processChunk: carry last_sample / samp_frac_num / history over

@@ -2,7 +2,8 @@
  * addon_selftest.c -- executes bindings/node/src/addon.c through the in-process N-API stand-in
  * (fake_napi.c) against the real libspeexb200.so: the calls index.ts makes, in the order it
  * makes them. Prints one line per result ("label frames fnv1a64"); tests/test_parity_gpu.py
- * recomputes every line through the Python mirror (same C ABI underneath) and compares.
+ * recomputes every line with the CPU oracle (the single stream runs the bit-exact kernel by default,
+ * the batches are switched to it with batchSetKernel) and compares.
  * Needs a B200; test infrastructure only.
  */
 #include <stdint.h>
@@ -94,6 +95,13 @@ int main(void) {
       report("single", k, out);
       pos += hops[k];
     }
+    /* an empty chunk: the reference returns an empty Buffer (N-API gives NULL data for it) */
+    {
+      napi_value chunk = fake_buffer("", 0);
+      argv[0] = h; argv[1] = chunk; argv[2] = fake_number(capacity_frames(&cap_state, 0));
+      out = must(env, fake_call(env, exports, "process", 3, argv), "process(empty)");
+      printf("empty %zu\n", out->length);
+    }
   }
 
   /* a batch of 8 streams, ragged chunk lengths, two calls */
@@ -105,6 +113,8 @@ int main(void) {
     argv[0] = fake_number(S); argv[1] = fake_number(CH); argv[2] = fake_number(IN_RATE); argv[3] = fake_number(OUT_RATE);
     argv[4] = fake_number(QUALITY); argv[5] = fake_number(0);
     batch = must(env, fake_call(env, exports, "batchCreate", 6, argv), "batchCreate");
+    argv[0] = batch; argv[1] = fake_number(1); /* SPXB_KERNEL_STRICT */
+    must(env, fake_call(env, exports, "batchSetKernel", 2, argv), "batchSetKernel");
     for (s = 0; s < S; ++s) cap_states[s] = -1;
     for (k = 0; k < 2; ++k) {
       chunks = fake_array(S);
@@ -130,6 +140,8 @@ int main(void) {
     argv[0] = fake_number(2); argv[1] = fake_number(CH); argv[2] = fake_number(IN_RATE); argv[3] = fake_number(OUT_RATE);
     argv[4] = fake_number(QUALITY); argv[5] = fake_number(0);
     batch = must(env, fake_call(env, exports, "batchCreate", 6, argv), "batchCreate");
+    argv[0] = batch; argv[1] = fake_number(1); /* SPXB_KERNEL_STRICT */
+    must(env, fake_call(env, exports, "batchSetKernel", 2, argv), "batchSetKernel");
     argv[0] = batch; argv[1] = fake_number(1); argv[2] = h;
     must(env, fake_call(env, exports, "batchAdopt", 3, argv), "batchAdopt");
     chunks = fake_array(2);

@@ -44,7 +44,8 @@ napi_value fake_number(double d) {
 
 napi_value fake_buffer(const void *data, size_t len) {
   napi_value v = new_value(FAKE_BUFFER);
-  v->data = (uint8_t *)malloc(len ? len : 1);
+  /* like N-API, a zero-length Buffer has no storage: its data pointer is NULL */
+  v->data = len ? (uint8_t *)malloc(len) : NULL;
   if (len) memcpy(v->data, data, len);
   v->length = len;
   return v;
@@ -153,7 +154,7 @@ napi_status napi_get_buffer_info(napi_env env, napi_value value, void **data, si
 napi_status napi_create_buffer(napi_env env, size_t length, void **data, napi_value *result) {
   napi_value v = new_value(FAKE_BUFFER);
   (void)env;
-  v->data = (uint8_t *)calloc(length ? length : 1, 1);
+  v->data = length ? (uint8_t *)calloc(length, 1) : NULL; /* NULL data for an empty Buffer, like N-API */
   v->length = length;
   if (data) *data = v->data;
   *result = v;

@@ -245,6 +245,11 @@ SPXB_API int spxb_batch_counters(const spxb_batch *b, spxb_counters *c);
 SPXB_API void *spxb_host_alloc(size_t bytes);
 SPXB_API void spxb_host_free(void *p);
 
+/* Measurement aid (bench.py): achieved FP32 rate, in FLOP/s (2 per FMA), of a register-resident
+ * FFMA loop on the current device -- the measured denominator of the FP32-FMA roofline SURVEY 8d
+ * asks for (MEASURED_PEAKS.json has no fp32 entry). `iters` <= 0 picks a default. */
+SPXB_API double spxb_measure_fp32_peak(int iters);
+
 /* ------------------------------------------------------------------ */
 /* Part 3: host-only introspection (no GPU needed)                     */
 /* ------------------------------------------------------------------ */

@@ -30,6 +30,7 @@ DECLARED_SYMBOLS = (
     "speex_resampler_set_quality",
     "speex_resampler_process_interleaved_float", "spxb_batch_create_f32", "spxb_batch_is_f32",
     "spxb_batch_process_f32", "spxb_batch_get_state_f32", "spxb_batch_set_state_f32", "spxb_plan_call_f32", "spxb_plan_call_ex",
+    "spxb_measure_fp32_peak",
 )
 
 KERNEL_AUTO, KERNEL_STRICT, KERNEL_TILED, KERNEL_TENSOR = 0, 1, 2, 3

@@ -434,7 +434,13 @@ struct Decided {
   StreamCall uni{};
   uint32_t max_n_in = 0, max_n_out = 0;
   bool any_work = false;
+  StreamPos next_uniform{};  // uniform call: where every stream stands afterwards
 };
+
+// decide() / decide_uniform() only PLAN: the host shadow of the positions moves in
+// commit_positions(), after the call's kernels have been launched successfully -- a call that
+// fails (a forced kernel family that does not cover it, a CUDA launch error) leaves the shadow,
+// the ping-pong half and the device state where they were.
 
 static Decided decide_uniform(spxb_batch *b, uint32_t n_in, uint32_t cap) {
   Decided d;
@@ -445,13 +451,29 @@ static Decided decide_uniform(spxb_batch *b, uint32_t n_in, uint32_t cap) {
   d.max_n_out = pl.n_out;
   // (a forced plan -- magic samples pending -- may consume without producing: resample.c:904-922)
   d.any_work = b->forced_plan ? (pl.consumed != 0 || pl.n_out != 0) : (n_in != 0 && cap != 0);
-  if (d.any_work) {
+  d.next_uniform = pl.next;
+  return d;
+}
+
+static void commit_positions(spxb_batch *b, const Decided &d, const StreamCall *calls) {
+  if (!d.any_work) return;
+  if (d.uniform) {
     // all shadows advance together; inside a hop sequence only pos[0] is kept exact and the
     // rest are mirrored once at its end (ring_hops)
-    if (b->defer_pos_mirror) b->pos[0] = pl.next;
-    else for (auto &q : b->pos) q = pl.next;
+    if (b->defer_pos_mirror) b->pos[0] = d.next_uniform;
+    else for (auto &q : b->pos) q = d.next_uniform;
+    return;
   }
-  return d;
+  const uint32_t S = b->n_streams;
+  for (uint32_t s = 0; s < S; ++s) {  // (a stream that sits the call out has ls1 == ls0, frac1 == frac0)
+    b->pos[s].last_sample = calls[s].ls1;
+    b->pos[s].samp_frac_num = calls[s].frac1;
+  }
+  // positions may have diverged
+  b->uniform_pos = true;
+  for (uint32_t s = 1; s < S && b->uniform_pos; ++s)
+    b->uniform_pos = b->pos[s].last_sample == b->pos[0].last_sample &&
+                     b->pos[s].samp_frac_num == b->pos[0].samp_frac_num;
 }
 
 static Decided decide(spxb_batch *b, uint32_t *in_frames, uint32_t *out_frames, StreamCall *calls) {
@@ -476,18 +498,10 @@ static Decided decide(spxb_batch *b, uint32_t *in_frames, uint32_t *out_frames, 
     calls[s] = to_stream_call(p, n_in, pl);
     d.max_n_in = std::max(d.max_n_in, n_in);
     d.max_n_out = std::max(d.max_n_out, pl.n_out);
-    if (n_in != 0 && cap != 0) {
-      d.any_work = true;
-      b->pos[s] = pl.next;
-    }
+    if (n_in != 0 && cap != 0) d.any_work = true;
     in_frames[s] = pl.consumed;
     out_frames[s] = pl.n_out;
   }
-  // positions may have diverged
-  b->uniform_pos = true;
-  for (uint32_t s = 1; s < S && b->uniform_pos; ++s)
-    b->uniform_pos = b->pos[s].last_sample == b->pos[0].last_sample &&
-                     b->pos[s].samp_frac_num == b->pos[0].samp_frac_num;
   return d;
 }
 
@@ -696,8 +710,12 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
   SPXB_CUDA(cudaStreamWaitEvent(b->s_compute, sl.ev_h2d, 0));
   if (int e = launch_call(b, sl.d_in, dev_in_stride, sl.d_out, dev_out_stride,
                           d.uniform ? nullptr : sl.d_calls, d.uni, d.max_n_out,
-                          d.uniform ? RaggedHost() : RaggedHost{sl.h_calls, sl.h_ids, sl.d_ids}))
+                          d.uniform ? RaggedHost() : RaggedHost{sl.h_calls, sl.h_ids, sl.d_ids})) {
+    // nothing was launched: the slot goes back (its H2D is harmless), the positions were never moved
+    cudaEventRecord(sl.ev_done, b->s_in);
     return e;
+  }
+  commit_positions(b, d, sl.h_calls);
   SPXB_CUDA(cudaEventRecord(sl.ev_kernel, b->s_compute));
 
   // ---- D2H ----
@@ -901,7 +919,11 @@ int spxb_batch_process_device(spxb_batch *b, const int16_t *d_in, size_t in_stri
                       out_stride_frames * b->channels * b->io_words,
                       d.uniform ? nullptr : sl.d_calls, d.uni, d.max_n_out,
                       d.uniform ? RaggedHost() : RaggedHost{sl.h_calls, sl.h_ids, sl.d_ids});
-  if (e) return e;
+  if (e) {
+    if (!d.uniform) cudaEventRecord(sl.ev_done, b->s_compute);  // the slot's plan upload is in flight
+    return e;
+  }
+  commit_positions(b, d, sl.h_calls);
   if (!d.uniform) SPXB_CUDA(cudaEventRecord(sl.ev_done, b->s_compute));
   b->counters.calls += 1;
   return 0;
@@ -924,6 +946,7 @@ int spxb_batch_process_device_uniform(spxb_batch *b, const int16_t *d_in, size_t
                       out_stride_frames * b->channels * b->io_words,
                       nullptr, d.uni, d.max_n_out);
   if (e) return e;
+  commit_positions(b, d, nullptr);
   b->counters.calls += 1;
   return 0;
 }
@@ -1005,7 +1028,13 @@ int spxb_batch_process_device_ring(spxb_batch *b, const int16_t *d_in, size_t in
   if (hit != b->ring_graphs.end()) {
     // the GPU starts at once; the host-side bookkeeping of the hops runs beside it
     hit->second.last_use = ++b->ring_clock;
-    SPXB_CUDA(cudaGraphLaunch(hit->second.exec, b->s_compute));
+    if (cudaGraphLaunch(hit->second.exec, b->s_compute) != cudaSuccess) {
+      // nothing ran and nothing moved yet: drop the graph and run the hops launch by launch
+      cudaGetLastError();
+      cudaGraphExecDestroy(hit->second.exec);
+      b->ring_graphs.erase(hit);
+      return plain();
+    }
     b->dry_run = true;
     const int e = plain();
     b->dry_run = false;
@@ -1023,7 +1052,23 @@ int spxb_batch_process_device_ring(spxb_batch *b, const int16_t *d_in, size_t in
     return e;
   }
 
-  // second unchanged sighting: capture the launches (they still execute: the graph is launched below)
+  // second unchanged sighting: capture the launches (they still execute: the graph is launched below).
+  // Capturing runs the host-side planning of every hop, which moves the position shadow, the
+  // ping-pong half and the counters although no kernel executes yet: if the capture or the
+  // instantiation fails, all of that is put back and the sequence runs launch by launch instead.
+  const StreamPos pos_before = b->pos[0];
+  const int hist_before = b->hist_cur;
+  const spxb_counters counters_before = b->counters;
+  auto fall_back = [&](const char *what, cudaError_t ce) {
+    for (auto &q : b->pos) q = pos_before;
+    b->hist_cur = hist_before;
+    b->counters = counters_before;
+    b->memo_valid = false;
+    b->ring_seen.erase(k);  // do not try to capture this sequence again right away
+    cudaGetLastError();
+    set_error(std::string("ring graph ") + what + ": " + cudaGetErrorString(ce) + " (ran launch by launch)");
+    return plain();
+  };
   cudaGraph_t graph = nullptr;
   SPXB_CUDA(cudaStreamBeginCapture(b->s_compute, cudaStreamCaptureModeThreadLocal));
   umma_set_frozen(b->umma, true);
@@ -1032,17 +1077,12 @@ int spxb_batch_process_device_ring(spxb_batch *b, const int16_t *d_in, size_t in
   const cudaError_t ce = cudaStreamEndCapture(b->s_compute, &graph);
   if (e || ce != cudaSuccess || !graph) {
     if (graph) cudaGraphDestroy(graph);
-    cudaGetLastError();
-    if (!e) set_error(std::string("ring graph capture: ") + cudaGetErrorString(ce));
-    return e ? e : RESAMPLER_ERR_BAD_STATE;
+    return fall_back("capture", ce != cudaSuccess ? ce : cudaErrorUnknown);
   }
   cudaGraphExec_t exec = nullptr;
   const cudaError_t ci = cudaGraphInstantiate(&exec, graph, 0);
   cudaGraphDestroy(graph);
-  if (ci != cudaSuccess || !exec) {
-    set_error(std::string("ring graph instantiate: ") + cudaGetErrorString(ci));
-    return RESAMPLER_ERR_BAD_STATE;
-  }
+  if (ci != cudaSuccess || !exec) return fall_back("instantiate", ci != cudaSuccess ? ci : cudaErrorUnknown);
   if (b->ring_graphs.size() >= 64) {  // evict the least recently used
     auto victim = b->ring_graphs.begin();
     for (auto it = b->ring_graphs.begin(); it != b->ring_graphs.end(); ++it)
@@ -1054,7 +1094,12 @@ int spxb_batch_process_device_ring(spxb_batch *b, const int16_t *d_in, size_t in
   rg.exec = exec;
   rg.last_use = ++b->ring_clock;
   b->ring_graphs.emplace(k, rg);
-  SPXB_CUDA(cudaGraphLaunch(exec, b->s_compute));
+  const cudaError_t cl = cudaGraphLaunch(exec, b->s_compute);
+  if (cl != cudaSuccess) {
+    cudaGraphExecDestroy(exec);
+    b->ring_graphs.erase(k);
+    return fall_back("launch", cl);
+  }
   return 0;
 }
 

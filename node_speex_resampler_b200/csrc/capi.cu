@@ -75,6 +75,10 @@ SpeexResamplerState *speex_resampler_init_frac(uint32_t nb_channels, uint32_t ra
   st->channels = nb_channels;
   st->quality = quality;
   st->mem_alloc = spxb::batch_spec(st->batch).taps - 1 + spxb::kInBlock;  // resample.c:835, :709
+  // The reference's own entry points return the reference's bytes: a single-stream state runs the
+  // bit-exact kernel unless the caller opts into the tensor kernel
+  // (spxb_batch_set_kernel(spxb_resampler_batch(st), SPXB_KERNEL_AUTO / _TENSOR): +-1 LSB).
+  spxb_batch_set_kernel(st->batch, SPXB_KERNEL_STRICT);
   if (err) *err = RESAMPLER_ERR_SUCCESS;
   return st;
 }
@@ -261,21 +265,24 @@ int speex_resampler_reset_mem(SpeexResamplerState *st) {
 
 int speex_resampler_process_interleaved_int(SpeexResamplerState *st, const int16_t *in, uint32_t *in_len,
                                             int16_t *out, uint32_t *out_len) {
-  if (!st || !in_len || !out_len || !out) return RESAMPLER_ERR_INVALID_ARG;
+  if (!st || !in_len || !out_len) return RESAMPLER_ERR_INVALID_ARG;
+  if (*in_len == 0 || *out_len == 0) {
+    // resample.c:988: the block loop does not run -- nothing is read, written or consumed, so the
+    // buffers may be NULL (N-API hands out NULL for a zero-length Buffer)
+    *in_len = 0;
+    *out_len = 0;
+    return RESAMPLER_ERR_SUCCESS;
+  }
+  if (!out) return RESAMPLER_ERR_INVALID_ARG;
   if (!in) {
     st->silence.assign(static_cast<size_t>(*in_len) * st->channels, 0);
     in = st->silence.data();
   }
-  if (*in_len != 0 && *out_len != 0) st->started = true;
+  st->started = true;
   if (st->magic != 0) {
     if (spxb_batch_is_f32(st->batch)) {
       spxb::set_error("int16 call on a float-history state with magic samples pending is not supported");
       return RESAMPLER_ERR_BAD_STATE;
-    }
-    if (*in_len == 0 || *out_len == 0) {  // resample.c:988: the loop does not run, nothing moves
-      *in_len = 0;
-      *out_len = 0;
-      return RESAMPLER_ERR_SUCCESS;
     }
     return process_with_magic<int16_t>(st, in, in_len, out, out_len, st->magic_i, st->joined_i, false);
   }
@@ -285,7 +292,15 @@ int speex_resampler_process_interleaved_int(SpeexResamplerState *st, const int16
 
 int speex_resampler_process_interleaved_float(SpeexResamplerState *st, const float *in, uint32_t *in_len,
                                               float *out, uint32_t *out_len) {
-  if (!st || !in_len || !out_len || !out) return RESAMPLER_ERR_INVALID_ARG;
+  if (!st || !in_len || !out_len) return RESAMPLER_ERR_INVALID_ARG;
+  if (*out_len == 0 || (*in_len == 0 && st->magic == 0)) {
+    // resample.c:939-943: the loop does not run (pending magic samples are drained even without
+    // input, :937-938, hence the second condition); buffers may be NULL
+    *in_len = 0;
+    *out_len = 0;
+    return RESAMPLER_ERR_SUCCESS;
+  }
+  if (!out) return RESAMPLER_ERR_INVALID_ARG;
   if (!spxb_batch_is_f32(st->batch)) {
     // first float call: the state moves to a float-history batch (int16 history converts exactly)
     int e = 0;
@@ -302,6 +317,9 @@ int speex_resampler_process_interleaved_float(SpeexResamplerState *st, const flo
       return e;
     }
     if (spxb::batch_kernel_pref(st->batch) == SPXB_KERNEL_STRICT) spxb_batch_set_kernel(fb, SPXB_KERNEL_STRICT);
+    // the reference's memory never shrinks (resample.c:709-719): a state whose filter got shorter
+    // keeps its enlarged input block on the float side too
+    spxb::batch_set_in_block(fb, st->mem_alloc - (s.taps - 1));
     spxb_batch_destroy(st->batch);
     st->batch = fb;
   }

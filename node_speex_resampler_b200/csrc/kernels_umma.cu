@@ -761,7 +761,10 @@ struct UmmaContext {
   size_t trace_ctas = 0;
   // memo of the planned geometry
   bool memo = false;
-  bool fresh_plan = false;  // the last umma_prepare re-planned (tile table / pool just rewritten)
+  // the tile table / tap pool were (re)written on the stream since the last tensor-kernel launch:
+  // that launch goes without the programmatic edge. Sticky until a launch succeeds, so a failed
+  // launch cannot make the next one read a pool that is still being built.
+  bool fresh_plan = false;
   int32_t m_ls0 = 0;
   uint32_t m_frac0 = 0, m_n_out = 0, m_hist_frames = 0, m_groups = 0;
 };
@@ -901,7 +904,6 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
   const StreamCall &sc = a.uniform;
   if (c->memo && c->m_ls0 == sc.ls0 && c->m_frac0 == sc.frac0 && c->m_n_out == sc.n_out &&
       c->m_hist_frames == a.hist_frames && c->m_groups == n_groups) {
-    c->fresh_plan = false;
     return true;  // steady state: same tiles as the previous call
   }
   const uint64_t ops_before = c->stream_ops;
@@ -1018,7 +1020,7 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
   }
   // a re-plan that uploaded or built something launches without the programmatic edge (the next
   // kernel's prologue reads the tile table / tap pool before its grid dependency resolves)
-  c->fresh_plan = c->stream_ops != ops_before;
+  if (c->stream_ops != ops_before) c->fresh_plan = true;
   c->n_tiles = static_cast<uint32_t>(tiles.size());
   c->h_tiles = tiles;
   c->memo = true;
@@ -1143,6 +1145,7 @@ cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, 
              : by_pace(umma_fir_kernel<1, false, false, false>, umma_fir_kernel<1, false, false, true>);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess) c->fresh_plan = false;
   if (e == cudaSuccess && launches) *launches += 1;
   return e;
 }

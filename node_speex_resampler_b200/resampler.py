@@ -60,9 +60,14 @@ class SpeexResampler:
     """Drop-in for the reference class of the same name (src/index.ts:21-117)."""
 
     initPromise = _Resolved(_load_module)
-    # kernel family for streams created from this class / instance (KERNEL_AUTO: tiled when
-    # the call qualifies, strict otherwise). Not in the reference; tests pin it.
-    kernel = KERNEL_AUTO
+    # Kernel family (not in the reference). The drop-in surface -- processChunk and the Transform
+    # built on it -- defaults to the STRICT kernel, which reproduces the reference's bytes exactly;
+    # the tensor-core kernel (+-1 LSB, >= 90 dB, the north star's tolerance) is opt-in there
+    # (``r.kernel = KERNEL_TENSOR`` or KERNEL_AUTO). The batched entry the north star adds,
+    # processChunks, defaults to AUTO (tensor kernel whenever the call qualifies) because
+    # throughput is its purpose; set ``batch_kernel = KERNEL_STRICT`` for reference bytes there too.
+    kernel = KERNEL_STRICT
+    batch_kernel = KERNEL_AUTO
 
     def __init__(self, channels, inRate, outRate, quality=7):
         # like the reference constructor: no validation, no side effects (index.ts:40-44)
@@ -89,8 +94,7 @@ class SpeexResampler:
             msg = _lib.strerror(err.value)
             raise RuntimeError(msg + (f" ({detail})" if detail and err.value == 1 else ""))
         self._resamplerPtr = ptr
-        if self.kernel != KERNEL_AUTO:
-            L.spxb_batch_set_kernel(L.spxb_resampler_batch(ptr), int(self.kernel))
+        L.spxb_batch_set_kernel(L.spxb_resampler_batch(ptr), int(self.kernel))
 
     def destroy(self):
         """Not in the reference (its instances leak); frees the device state."""
@@ -159,7 +163,10 @@ class SpeexResampler:
         for idx in idx_lists:
             members = resamplers if idx is None else [resamplers[k] for k in idx]
             group = members[0]._group
-            if group is None or (group.members is not members and list(group.members) != list(members)):
+            # same resamplers, same order -- compared element by element, by identity (a caller may
+            # reorder its own list in place between calls)
+            if group is None or len(group.members) != len(members) or \
+                    any(a is not b for a, b in zip(group.members, members)):
                 group = StreamBatch._adopt(members)
             res = group.processChunks(chunks if idx is None else [chunks[k] for k in idx])
             if idx is None:
@@ -200,10 +207,14 @@ class StreamBatch:
             if (r.channels, r.inRate, r.outRate, r.quality) != key:
                 raise ValueError("processChunks needs resamplers of one (channels, rates, quality)")
             if r._group is not None:
-                raise RuntimeError("resampler already belongs to another batch")
+                raise RuntimeError("processChunks needs the same resamplers in the same order on every call "
+                                   "(a resampler already belongs to another batch)")
         g = cls(len(resamplers), *key)
-        if r0.kernel != KERNEL_AUTO:
-            g.set_kernel(r0.kernel)
+        # an instance whose `kernel` was set explicitly (e.g. pinned to STRICT by a test) keeps it
+        # in the batch; otherwise the class-level batch default applies
+        wanted = r0.__dict__.get("kernel", r0.batch_kernel)
+        if wanted != KERNEL_AUTO:
+            g.set_kernel(wanted)
         info = g.filter_info()
         hist = np.zeros(max((info.filt_len - 1) * g.channels, 1), dtype=np.int16)
         L = _lib.lib()
@@ -215,7 +226,7 @@ class StreamBatch:
                 r.destroy()
             g._out_buffer_size[i] = r._outBufferSize
             r._group, r._group_index = g, i
-        g.members = resamplers
+        g.members = tuple(resamplers)
         return g
 
     def close(self):

@@ -26,6 +26,18 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libspeex_ref.so")
+# the reference's own test inputs: oracle/Makefile copies resources/*.pcm beside the built reference
+# objects (git-ignored, travels to the GPU box); in the build container the originals are there too
+FIXTURE_DIRS = (os.path.join(HERE, "_ref", "resources"), "/root/reference/resources")
+
+
+def fixture_path(name: str):
+    """Path of one of the reference's resources/*.pcm files, or None where neither copy exists."""
+    for d in FIXTURE_DIRS:
+        p = os.path.join(d, name)
+        if os.path.isfile(p):
+            return p
+    return None
 
 
 def build(quiet: bool = True) -> None:

@@ -92,8 +92,8 @@ def test_golden_fast_kernels_within_one_lsb(c, kernel):
 SHAPES = [
     # name, n_streams, ch, in, out, q, frames per 20 ms call, calls
     ("C3", 70, 2, 44100, 48000, 7, 882, 50),
-    ("C4", 40, 1, 48000, 16000, 10, 960, 50),
-    ("C5", 33, 2, 96000, 44100, 10, 1920, 12),
+    ("C4", 66, 1, 48000, 16000, 10, 960, 30),
+    ("C5", 65, 2, 96000, 44100, 10, 1920, 10),
     ("up2_direct", 37, 1, 24000, 48000, 5, 480, 20),
     ("sweep_q9", 16, 1, 24000, 44100, 9, 480, 20),
 ]
@@ -109,6 +109,7 @@ def test_batch_state_carry(shape, kernel):
     refs = [O.OracleResampler(ch, i, o, q) for _ in range(S)]
     cap = int(np.ceil(n * o / i)) + 2
     kernels_used = set()
+    saturated = 0
     for k in range(calls):
         pcm = synth_pcm(S, ch, n, i, seed=0xC0DE, start_frame=k * n)
         out, used, made = b.process(pcm, n, cap)
@@ -117,6 +118,16 @@ def test_batch_state_carry(shape, kernel):
             y, u, m = refs[s].process(pcm[s], cap)
             assert (u, m) == (int(used[s]), int(made[s])), (name, k, s)
             check_close(y, out[s, : m * ch], exact=kernel == KERNEL_STRICT, what=(name, k, s))
+            if s % 64 == 63:  # the stream with full-scale square bursts: WORD2INT's clamp is live
+                hit = (y == 32767) | (y == -32768)
+                saturated += int(np.count_nonzero(hit))
+                got_hit = (out[s, : m * ch] == 32767) | (out[s, : m * ch] == -32768)
+                if kernel == KERNEL_STRICT:
+                    assert np.array_equal(hit, got_hit), (name, k, s)
+                else:  # a value that rounds to exactly +-32767/8 unclamped may sit 1 LSB inside
+                    assert abs(int(np.count_nonzero(got_hit)) - int(np.count_nonzero(hit))) <= 2 + hit.size // 200
+    if S > 63:
+        assert saturated > 0, "stream 63 should drive the output into saturation"
     if kernel == KERNEL_AUTO:
         assert kernels_used == {KERNEL_TENSOR}, "auto should pick the tensor kernel for uniform mono/stereo batches"
     else:
@@ -569,10 +580,12 @@ def test_process_chunks_groups_mixed_configurations():
             assert got[s] == refs[s].processChunk(chunks[s]), (k, s)
 
 
-def test_node_addon_executes_like_the_mirror():
+def test_node_addon_executes_like_the_oracle():
     """bindings/node/src/addon.c EXECUTED (through the in-process N-API stand-in, no Node in this
     image) with the calls index.ts makes -- init, process, batchCreate/Process/Adopt, the two error
-    paths -- must return byte for byte what the Python mirror returns for the same inputs."""
+    paths, an empty chunk -- must return byte for byte what the CPU ORACLE returns for the same
+    inputs through the wrapper's capacity rule (the single stream runs the bit-exact kernel by
+    default, the batches are switched to it with batchSetKernel)."""
     import subprocess
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bindings", "node", "test",
                        "addon_selftest")
@@ -583,6 +596,7 @@ def test_node_addon_executes_like_the_mirror():
     lines = dict((ln.split()[0], ln.split(None, 1)[1]) for ln in r.stdout.strip().split("\n") if " " in ln)
     assert lines["init_error"] == "1 Invalid argument."
     assert lines["align_error"] == "1 Chunk length should be a multiple of channels * 2 bytes"
+    assert lines["empty"] == "0"
 
     ch, i, o, q = 2, 44100, 48000, 7
 
@@ -595,23 +609,21 @@ def test_node_addon_executes_like_the_mirror():
     def line(y):
         return f"{len(y) // (ch * 2)} {O.fnv1a64(y)}"
 
-    single = SpeexResampler(ch, i, o, q)
+    single = O.OracleResampler(ch, i, o, q)
     pos = 0
     for k, n in enumerate((882, 441, 7, 882)):
         assert lines[f"single{k}"] == line(single.processChunk(pcm(0, pos, n))), k
         pos += n
-    rs = [SpeexResampler(ch, i, o, q) for _ in range(8)]
+    assert single.processChunk(b"") == b""
+    rs = [O.OracleResampler(ch, i, o, q) for _ in range(8)]
     posb = [0] * 8
     for tag, frames in (("batchA", lambda s: 882), ("batchB", lambda s: 300 + 41 * s)):
-        chunks = [pcm(10 + s, posb[s], frames(s)) for s in range(8)]
         for s in range(8):
+            assert lines[f"{tag}{s}"] == line(rs[s].processChunk(pcm(10 + s, posb[s], frames(s)))), (tag, s)
             posb[s] += frames(s)
-        got = SpeexResampler.processChunks(rs, chunks)
-        for s in range(8):
-            assert lines[f"{tag}{s}"] == line(got[s]), (tag, s)
-    pair = [SpeexResampler(ch, i, o, q), single]
-    got = SpeexResampler.processChunks(pair, [pcm(30, 0, 882), pcm(0, pos, 882)])
-    assert lines["adopt0"] == line(got[0]) and lines["adopt1"] == line(got[1])
+    # a fresh stream and the single stream (4 hops + an empty chunk in) continued inside a batch
+    assert lines["adopt0"] == line(O.OracleResampler(ch, i, o, q).processChunk(pcm(30, 0, 882)))
+    assert lines["adopt1"] == line(single.processChunk(pcm(0, pos, 882)))
 
 
 def test_ragged_batch_cohorts_take_the_tensor_kernel():
@@ -898,3 +910,85 @@ def test_batches_release_their_device_memory():
         one_round()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < (8 << 20), (free0, free1)
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("kernel", [KERNEL_STRICT, KERNEL_TENSOR], ids=["strict", "tensor"])
+def test_c_api_reset_mem_matches_the_reference(kernel):
+    """speex_resampler_reset_mem (resample.c:1208-1220): last_sample, samp_frac_num, magic_samples and
+    the whole filter memory go back to zero mid-stream -- the next calls must match the reference's
+    own build doing the same, and a fresh state fed the same samples."""
+    L, R = lib(), O._load_ref()
+    R.speex_resampler_reset_mem.restype = C.c_int
+    R.speex_resampler_reset_mem.argtypes = [C.c_void_p]
+    ch, i, o, q = 2, 44100, 48000, 7
+    err = C.c_int(0)
+    ours = L.speex_resampler_init(ch, i, o, q, C.byref(err))
+    ref = R.speex_resampler_init(ch, i, o, q, C.byref(err))
+    fresh = O.OracleResampler(ch, i, o, q)
+    assert L.spxb_batch_set_kernel(L.spxb_resampler_batch(ours), kernel) == 0
+    x = synth_pcm(1, ch, 6000, i, seed=515)[0]
+    pos = 0
+    for k, (n, cap) in enumerate(((882, 962), (441, 482), (300, 100), ("reset", 0), (882, 962), (7, 9), (882, 962))):
+        if n == "reset":
+            assert L.speex_resampler_reset_mem(ours) == 0 and R.speex_resampler_reset_mem(ref) == 0
+            ls, fr, mg = C.c_int32(1), C.c_uint32(1), C.c_uint32(1)
+            hist = np.ones((127) * ch, np.int16)
+            assert L.spxb_batch_get_state(L.spxb_resampler_batch(ours), 0, C.byref(ls), C.byref(fr), C.byref(mg),
+                                          hist.ctypes.data) == 0
+            assert (ls.value, fr.value, mg.value) == (0, 0, 0) and not hist.any()
+            after_reset = pos
+            continue
+        chunk = np.ascontiguousarray(x[pos * ch:(pos + n) * ch])
+        pos += n
+        res = []
+        for lib_, st in ((L, ours), (R, ref)):
+            out = np.zeros(cap * ch, np.int16)
+            n_in, n_out = C.c_uint32(n), C.c_uint32(cap)
+            assert lib_.speex_resampler_process_interleaved_int(st, chunk.ctypes.data, C.byref(n_in), out.ctypes.data,
+                                                                C.byref(n_out)) == 0
+            res.append((n_in.value, n_out.value, out[: n_out.value * ch].copy()))
+        assert res[0][:2] == res[1][:2], k
+        check_close(res[1][2], res[0][2], exact=kernel == KERNEL_STRICT, what=("reset_mem", k))
+        if k > 3:  # after the reset the stream is indistinguishable from a new one
+            y, u, m = fresh.process(chunk, cap)
+            assert (u, m) == res[1][:2] and np.array_equal(y, res[1][2])
+    assert after_reset == 882 + 441 + 300
+    L.speex_resampler_destroy(ours)
+    R.speex_resampler_destroy(ref)
+
+
+def test_batch_reset_restarts_every_stream():
+    """spxb_batch_reset: all streams of a batch back to the state of a new resampler"""
+    S, ch, i, o, q, n, cap = 40, 1, 48000, 16000, 10, 960, 322
+    b = StreamBatch(S, ch, i, o, q)
+    first = None
+    for rnd in range(2):
+        for k in range(3):
+            out, used, made = b.process(synth_pcm(S, ch, n, i, seed=31, start_frame=k * n), n, cap)
+            if rnd == 0 and k == 0:
+                first = (out.copy(), used.copy(), made.copy())
+        b.reset()
+        assert b.get_state(S - 1)[:3] == (0, 0, 0) and not b.get_state(S - 1)[3].any()
+    out, used, made = b.process(synth_pcm(S, ch, n, i, seed=31, start_frame=0), n, cap)
+    assert np.array_equal(out, first[0]) and np.array_equal(used, first[1]) and np.array_equal(made, first[2])
+    b.close()
+
+
+def test_empty_chunks_return_empty_buffers():
+    """src/index.ts:50-116 with an empty Buffer: the reference's loop does not run and an empty Buffer
+    comes back; state untouched (used to be 'Invalid argument.' through N-API's NULL data)"""
+    r = SpeexResampler(2, 44100, 48000, 7)
+    ref = O.OracleResampler(2, 44100, 48000, 7)
+    x = synth_pcm(1, 2, 882 * 2, 44100, seed=3)[0]
+    assert r.processChunk(b"") == b"" == ref.processChunk(b"")
+    assert r.processChunk(x[: 882 * 2]) == ref.processChunk(x[: 882 * 2])
+    assert r.processChunk(b"") == b""
+    assert r.processChunk(x[882 * 2:]) == ref.processChunk(x[882 * 2:])
+    L = lib()
+    n_in, n_out = C.c_uint32(0), C.c_uint32(10)
+    assert L.speex_resampler_process_interleaved_int(r._resamplerPtr, None, C.byref(n_in), None, C.byref(n_out)) == 0
+    assert (n_in.value, n_out.value) == (0, 0)
+    t = SpeexResamplerTransform(2, 44100, 48000, 7)
+    assert t.transform(b"\x01") == b""  # shorter than one frame: carried, nothing to resample yet
+    r.destroy()
