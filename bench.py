@@ -198,6 +198,8 @@ def ours(args):
     L = pkg.lib()
     wl = args.workload
     S, ch, i, o, q, n = WORKLOADS[wl]
+    if args.streams:
+        S = args.streams
     # weak scaling: the job is world * S independent streams, rank r owns one contiguous block
     from node_speex_resampler_b200.sharding import shard_range
     lo, hi = shard_range(S * world, world, rank)
@@ -222,10 +224,12 @@ def ours(args):
     out_slot = S * cap_pad * ch
     ring = max(4, int(math.ceil(1.25 * L2_BYTES / (in_slot * 2))))
     ring = min(ring, 96)
+    if args.ring:
+        ring = args.ring
     # a ring that divides the step count makes every timed region walk the same slots, so the
     # library's CUDA graph of the hop sequence (spxb_batch_process_device_ring) is captured once
     for cand in range(ring, min(2 * ring, 96) + 1):
-        if args.steps % cand == 0:
+        if args.steps % cand == 0 and not args.ring:
             ring = cand
             break
     hop = pkg.synth_pcm(min(S, 256), ch, n * 4, i, seed=0xB200 + rank)
@@ -490,6 +494,8 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "strict", "tiled", "tensor"])
     ap.add_argument("--min-seconds", type=float, default=1.0, help="clock-sampling window for the timed regions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=0, help="experiments: streams per GPU instead of the workload's")
+    ap.add_argument("--ring", type=int, default=0, help="experiments: number of distinct hops resident in HBM")
     ap.add_argument("--lean", action="store_true", help="skip the auxiliary probes (FFMA peak, device-copy floor)")
     args = ap.parse_args()
     if args.impl == "reference":

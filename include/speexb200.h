@@ -290,6 +290,16 @@ SPXB_API long spxb_tensor_plan(uint32_t in_rate, uint32_t out_rate, int quality,
  * [chunk < 2*ksteps][row < 3*nt][16 B], rows = digit d2 | d1 | d0 of each of the nt outputs */
 SPXB_API long spxb_tensor_tap_tile(uint32_t in_rate, uint32_t out_rate, int quality, uint32_t nt,
                                    uint32_t phase0, uint32_t delta, int8_t *dst, size_t cap);
+/* The packed ("resident") tap-tile layout of the persistent tensor kernel: per K step only the
+ * 16-column blocks of each tap digit that can be non-zero are stored (csrc/umma_plan.h). Per K
+ * step 18 words: byte offset / 16, rows per chunk, MMA entries, 3 x (first row, columns, first
+ * accumulator column of the hi plane), first block of d2/d1/d0, end block of d2/d1/d0.
+ * Returns the number of K steps (or -error); *tile_bytes receives the packed tile size. */
+SPXB_API long spxb_tensor_packed_plan(uint32_t in_rate, uint32_t out_rate, int quality, uint32_t nt,
+                                      uint32_t *dst, size_t cap_words, uint32_t *tile_bytes);
+SPXB_API long spxb_tensor_tap_tile_packed(uint32_t in_rate, uint32_t out_rate, int quality,
+                                          uint32_t nt, uint32_t phase0, uint32_t delta, int8_t *dst,
+                                          size_t cap);
 
 /* lengths and next state of one speex_resampler_process_int call (resample.c:968-1036
  * with :878-902), without touching samples: a pure function of the stream position. */

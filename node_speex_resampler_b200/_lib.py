@@ -30,7 +30,7 @@ DECLARED_SYMBOLS = (
     "speex_resampler_set_quality",
     "speex_resampler_process_interleaved_float", "spxb_batch_create_f32", "spxb_batch_is_f32",
     "spxb_batch_process_f32", "spxb_batch_get_state_f32", "spxb_batch_set_state_f32", "spxb_plan_call_f32", "spxb_plan_call_ex",
-    "spxb_measure_fp32_peak",
+    "spxb_measure_fp32_peak", "spxb_tensor_packed_plan", "spxb_tensor_tap_tile_packed",
 )
 
 KERNEL_AUTO, KERNEL_STRICT, KERNEL_TILED, KERNEL_TENSOR = 0, 1, 2, 3
@@ -110,6 +110,10 @@ def _bind(L):
     L.spxb_tensor_plan.argtypes = [u32, u32, C.c_int, i32, u32, u32, u32, vp, sz, pu32]
     L.spxb_tensor_tap_tile.restype = C.c_long
     L.spxb_tensor_tap_tile.argtypes = [u32, u32, C.c_int, u32, u32, u32, vp, sz]
+    L.spxb_tensor_packed_plan.restype = C.c_long
+    L.spxb_tensor_packed_plan.argtypes = [u32, u32, C.c_int, u32, vp, sz, pu32]
+    L.spxb_tensor_tap_tile_packed.restype = C.c_long
+    L.spxb_tensor_tap_tile_packed.argtypes = [u32, u32, C.c_int, u32, u32, u32, vp, sz]
     L.spxb_plan_call.argtypes = [u32, u32, i32, u32, u32, u32, C.POINTER(CallPlan)]
     L.spxb_plan_call_f32.argtypes = [u32, u32, i32, u32, u32, u32, C.POINTER(CallPlan)]
     L.spxb_plan_call_ex.argtypes = [u32, u32, i32, u32, u32, u32, u32, C.c_int, u32, C.POINTER(CallPlan), pu32]

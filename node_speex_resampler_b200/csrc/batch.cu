@@ -751,6 +751,27 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
 
 }  // namespace spxb
 
+// speex_resampler_reset_mem (resample.c:1208-1220) for every stream. The reference zeroes the FIRST
+// nb_channels * (filt_len - 1) floats of `mem`, whose channels are mem_alloc_size apart -- so only
+// channel 0's history is certainly cleared; element j of channel c's history goes to zero iff
+// c * mem_alloc_size + j < nb_channels * (filt_len - 1). Reproduced as it is (a stereo stream keeps
+// its right-channel history across a reset in the reference, and so it does here).
+__global__ void reset_hist_kernel(int16_t *hist, uint32_t n_streams, uint32_t hist_stride, uint32_t hist_frames,
+                                  uint32_t channels, uint32_t words, uint32_t live, uint32_t mem_alloc) {
+  const size_t per_stream = static_cast<size_t>(hist_frames) * channels;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= per_stream * n_streams) return;
+  const uint32_t s = static_cast<uint32_t>(idx / per_stream), e = static_cast<uint32_t>(idx % per_stream);
+  const uint32_t frame = e / channels, c = e % channels, lead = hist_frames - live;
+  bool zero = frame < lead;  // padding in front of the live history is always zero
+  if (!zero) {
+    const uint64_t j = frame - lead;
+    zero = static_cast<uint64_t>(c) * mem_alloc + j < static_cast<uint64_t>(channels) * live;
+  }
+  if (zero)
+    for (uint32_t w = 0; w < words; ++w) hist[static_cast<size_t>(s) * hist_stride + static_cast<size_t>(e) * words + w] = 0;
+}
+
 // ---------------------------------------------------------------------------
 // C ABI, part 2 (batched streams)
 // ---------------------------------------------------------------------------
@@ -1240,14 +1261,21 @@ int spxb_batch_reset(spxb_batch *b) {
   if (!b) return RESAMPLER_ERR_INVALID_ARG;
   if (int e = spxb_batch_synchronize(b)) return e;
   DeviceGuard g(b->device);
-  const size_t hist_bytes = static_cast<size_t>(b->n_streams) * b->hist_stride * sizeof(int16_t);
-  SPXB_CUDA(cudaMemset(b->d_hist[b->hist_cur], 0, hist_bytes));
-  SPXB_CUDA(cudaMemset(b->d_last_sample, 0, b->n_streams * sizeof(int32_t)));
-  SPXB_CUDA(cudaMemset(b->d_samp_frac, 0, b->n_streams * sizeof(uint32_t)));
-  SPXB_CUDA(cudaMemset(b->d_magic, 0, b->n_streams * sizeof(uint32_t)));
-  SPXB_CUDA(cudaDeviceSynchronize());
+  const uint32_t live = b->spec.taps - 1, mem_alloc = live + b->in_block;  // resample.c:709, :835
+  const size_t elems = static_cast<size_t>(b->n_streams) * b->hist_frames * b->channels;
+  if (elems) {
+    reset_hist_kernel<<<static_cast<unsigned>((elems + 255) / 256), 256, 0, b->s_compute>>>(
+        b->d_hist[b->hist_cur], b->n_streams, b->hist_stride, b->hist_frames, b->channels, b->hist_words, live,
+        mem_alloc);
+    SPXB_CUDA(cudaGetLastError());
+  }
+  SPXB_CUDA(cudaMemsetAsync(b->d_last_sample, 0, b->n_streams * sizeof(int32_t), b->s_compute));
+  SPXB_CUDA(cudaMemsetAsync(b->d_samp_frac, 0, b->n_streams * sizeof(uint32_t), b->s_compute));
+  SPXB_CUDA(cudaMemsetAsync(b->d_magic, 0, b->n_streams * sizeof(uint32_t), b->s_compute));
+  SPXB_CUDA(cudaStreamSynchronize(b->s_compute));
   b->pos.assign(b->n_streams, StreamPos{});
   b->uniform_pos = true;
+  b->memo_valid = false;
   return 0;
 }
 
@@ -1371,6 +1399,53 @@ long spxb_tensor_tap_tile(uint32_t in_rate, uint32_t out_rate, int quality, uint
   key.delta = delta;
   fill_tap_tile_host(ft, s.num, s.den, s.taps, nt, ks, key, dst);
   return static_cast<long>(bytes);
+}
+
+long spxb_tensor_packed_plan(uint32_t in_rate, uint32_t out_rate, int quality, uint32_t nt, uint32_t *dst,
+                             size_t cap_words, uint32_t *tile_bytes) {
+  FilterSpec s;
+  if (int e = derive_filter_spec(in_rate, out_rate, quality, &s)) return -e;
+  if (!dst || !tile_bytes) return -RESAMPLER_ERR_INVALID_ARG;
+  FixedTaps ft;
+  if (!build_fixed_taps(s, build_reference_table(s), &ft)) return -RESAMPLER_ERR_BAD_STATE;
+  UmmaPackedPlan plan;
+  if (!build_packed_plan(s, ft, nt, &plan)) return -RESAMPLER_ERR_INVALID_ARG;
+  if (cap_words < static_cast<size_t>(plan.ksteps) * 18) return -RESAMPLER_ERR_INVALID_ARG;
+  for (uint32_t k = 0; k < plan.ksteps; ++k) {
+    const UmmaKStep &ks = plan.k[k];
+    uint32_t *w = dst + static_cast<size_t>(k) * 18;
+    w[0] = ks.off16;
+    w[1] = ks.rows;
+    w[2] = ks.n_ent;
+    for (uint32_t e = 0; e < 3; ++e) {
+      w[3 + 3 * e] = e < ks.n_ent ? ks.ent[e].row : 0;
+      w[4 + 3 * e] = e < ks.n_ent ? ks.ent[e].n : 0;
+      w[5 + 3 * e] = e < ks.n_ent ? ks.ent[e].dcol : 0;
+    }
+    for (int i = 0; i < 3; ++i) {
+      w[12 + i] = ks.b0[i];
+      w[15 + i] = ks.b1[i];
+    }
+  }
+  *tile_bytes = plan.tile_bytes;
+  return static_cast<long>(plan.ksteps);
+}
+
+long spxb_tensor_tap_tile_packed(uint32_t in_rate, uint32_t out_rate, int quality, uint32_t nt, uint32_t phase0,
+                                 uint32_t delta, int8_t *dst, size_t cap) {
+  FilterSpec s;
+  if (int e = derive_filter_spec(in_rate, out_rate, quality, &s)) return -e;
+  if (!dst || phase0 >= s.den || delta >= 16) return -RESAMPLER_ERR_INVALID_ARG;
+  FixedTaps ft;
+  if (!build_fixed_taps(s, build_reference_table(s), &ft)) return -RESAMPLER_ERR_BAD_STATE;
+  UmmaPackedPlan plan;
+  if (!build_packed_plan(s, ft, nt, &plan)) return -RESAMPLER_ERR_INVALID_ARG;
+  if (cap < plan.tile_bytes) return -RESAMPLER_ERR_INVALID_ARG;
+  UmmaTileKey key;
+  key.phase0 = phase0;
+  key.delta = delta;
+  fill_tap_tile_packed_host(ft, s.num, s.den, s.taps, plan, key, dst);
+  return static_cast<long>(plan.tile_bytes);
 }
 
 static int plan_call_any(uint32_t in_rate, uint32_t out_rate, int32_t last_sample, uint32_t samp_frac_num,

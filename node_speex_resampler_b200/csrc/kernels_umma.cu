@@ -47,6 +47,8 @@
 #include "kernels_common.cuh"
 #include "launch.h"
 #include "umma_plan.h"
+#include "umma_common.cuh"
+#include "umma_context.h"
 #include "umma_ptx.cuh"
 
 namespace spxb {
@@ -54,24 +56,9 @@ namespace spxb {
 namespace {
 
 using namespace ptx;
+using namespace ummac;
 
-constexpr int kConvWarps = 8;
-constexpr int kConvThreads = kConvWarps * 32;
-constexpr int kTmaWarp = 8, kMmaWarp = 9;  // warp 10 slides the history
-constexpr int kThreads = 352;
-constexpr int kStageChunks = 4;                                  // 64 frames, 2 K steps
-// One byte plane of a stage = four K chunks of 128 rows x 16 B. Chunk c sits at
-// (c >> 1) * x_kstep + (c & 1) * x_lbo: the pair of chunks of one MMA is LBO apart (a free multiple
-// of 16 B), and the paddings are chosen so that one converter store instruction hits 32 distinct
-// banks -- mono: a warp stores 4 rows x 8 positions (8 B each), chunks must start 8 banks apart;
-// stereo: a warp stores 2 streams x 16 positions into rows 2s (left) or 2s+1 (right), chunk
-// starts must be {0, 16, 4, 20} banks (checked exhaustively in tests/test_tensor_plan.py).
-__host__ __device__ constexpr uint32_t x_lbo(int ch) { return kUmmaRows * 16 + (ch == 2 ? 64 : 32); }
-__host__ __device__ constexpr uint32_t x_kstep(int ch) { return 2 * x_lbo(ch) + (ch == 2 ? 16 : 0); }
-__host__ __device__ constexpr uint32_t x_plane(int ch) { return 2 * x_kstep(ch); }
-__host__ __device__ constexpr uint32_t x_stage(int ch) { return 2 * x_plane(ch); }  // hi + lo planes
 constexpr int kMaxStages = 6;
-constexpr uint32_t kMaxSmem = 227u * 1024u - 2048u;              // dynamic part; barriers are static
 
 constexpr uint32_t kInlineTiles = 64;  // tile table carried in the kernel parameters up to this many tiles
 struct InlineTile {
@@ -117,65 +104,6 @@ __device__ __forceinline__ void trace_mark_t(const UmmaArgs &u, int slot) {
     SPXB_TRACE_PTR(u)[static_cast<size_t>(blockIdx.x) * kTraceSlots + slot] = static_cast<unsigned long long>(clock64());
 }
 #define trace_mark(u, slot) trace_mark_t<PACED>(u, slot)
-
-// 16 bytes of one stream's input, sample by sample: the first `n` int16 samples at p, zeros after
-// (kept out of line: only the item holding the end of a row, or 2-byte aligned rows, come here)
-__device__ __noinline__ uint4 fetch_item_slow(const int16_t *p, int n) {
-  uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i < n) w[i >> 1] |= static_cast<uint32_t>(static_cast<uint16_t>(p[i])) << (16 * (i & 1));
-  return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// exactly one lane of a converged warp (elect.sync): the lane that issues tcgen05 / bulk copies
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-// two int32 -> saturated int16 pair: (hi << 16) | lo  (the saturation of WORD2INT, arch.h:208-209)
-__device__ __forceinline__ uint32_t pack_sat_s16x2(int hi, int lo) {
-  uint32_t d;
-  asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
-  return d;
-}
-
-// the 16 accumulator columns of one output group -> rounded (not yet saturated) integers
-// y = (p0*2^24 + p1*2^16 + p2*2^8 + p3) * 2^-shift, result floor(y + 1/2) (arch.h:208-209)
-__device__ __forceinline__ void combine16(const uint32_t (&p0)[16], const uint32_t (&p1)[16],
-                                          const uint32_t (&p2)[16], const uint32_t (&p3)[16], int shift,
-                                          int (&r16)[16]) {
-  if (shift >= 16 && shift <= 30) {
-    // nested floor division by 256 is exact: floor((a*256 + b) / 256) = a + floor(b / 256). The
-    // running value after two steps is floor((v + half) / 2^16); it fits int32 (|y| < 2^18 for any
-    // windowed-sinc filter, so |v| * 2^-16 < 2^(shift+2)), hence wrapping arithmetic is exact.
-    const int half = 1 << (shift - 1), s2 = shift - 16;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      int w = static_cast<int>(p3[i]) + half;
-      w = (w >> 8) + static_cast<int>(p2[i]);
-      w = (w >> 8) + static_cast<int>(p1[i]) + static_cast<int>(p0[i] << 8);
-      r16[i] = w >> s2;
-    }
-  } else {
-    const long long half = 1ll << (shift - 1);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      long long v = static_cast<long long>(static_cast<int>(p3[i]));
-      v += static_cast<long long>(static_cast<int>(p2[i])) << 8;
-      v += static_cast<long long>(static_cast<int>(p1[i])) << 16;
-      v += static_cast<long long>(static_cast<int>(p0[i])) << 24;
-      const long long r = (v + half) >> shift;
-      r16[i] = static_cast<int>(max(-40000ll, min(40000ll, r)));
-    }
-  }
-}
 
 // History slide of the streams first, first + step, ... (n_total of them) by whichever warps are
 // free, claiming from one packed counter (low half: streams taken from the front, high half:
@@ -732,43 +660,6 @@ uint32_t pow2_cols(uint32_t cols) {
 
 }  // namespace
 
-// Per-batch state of the tensor kernel: fixed-point taps in HBM, the pool of tap tiles keyed
-// by (first phase, K-origin offset), and the tile list of the last planned call geometry.
-struct UmmaContext {
-  FilterSpec spec;
-  uint32_t channels = 0;
-  int sm_count = 148;
-  FixedTaps ft;
-  int32_t *d_h = nullptr;
-  // geometry (changes only when the tile width changes)
-  uint32_t nt = 0, ksteps = 0, tile_bytes = 0, stages = 0, tmem_cols = 0, smem_bytes = 0;
-  uint32_t cluster = 1, grid_groups = 0;  // CTAs per cluster; series groups padded to a multiple of it
-  int8_t *d_pool = nullptr;
-  size_t pool_cap = 0;  // tiles
-  std::unordered_map<uint64_t, uint32_t> slot_of;
-  UmmaTile *d_tiles = nullptr;
-  size_t tiles_cap = 0;
-  uint32_t n_tiles = 0;
-  std::vector<UmmaTile> h_tiles;  // host copy of the planned tile table (kernel parameters)
-  // CUDA-graph support (batch.cu: ring graphs): while `frozen`, planning must not touch the
-  // stream or allocate (the stream is being captured); stream_ops counts every such operation,
-  // pool_generation changes whenever cached launches would point at stale tap tiles
-  bool frozen = false;
-  uint64_t stream_ops = 0, pool_generation = 0;
-  uint32_t *d_jobs = nullptr;
-  size_t jobs_cap = 0;
-  unsigned long long *d_trace = nullptr;  // SPXB_UMMA_TRACE=1: timeline of the last launch
-  size_t trace_ctas = 0;
-  // memo of the planned geometry
-  bool memo = false;
-  // the tile table / tap pool were (re)written on the stream since the last tensor-kernel launch:
-  // that launch goes without the programmatic edge. Sticky until a launch succeeds, so a failed
-  // launch cannot make the next one read a pool that is still being built.
-  bool fresh_plan = false;
-  int32_t m_ls0 = 0;
-  uint32_t m_frac0 = 0, m_n_out = 0, m_hist_frames = 0, m_groups = 0;
-};
-
 namespace {
 
 constexpr size_t kMaxPoolBytes = 256ull << 20;
@@ -803,7 +694,7 @@ uint32_t pick_nt(const UmmaContext &c, uint32_t n_groups, uint32_t n_out) {
     const double ctas = static_cast<double>(tiles) * n_groups;
     const double waves = std::ceil(ctas / c.sm_count);
     const uint32_t ks = umma_ksteps(c.spec.taps, c.spec.num, c.spec.den, nt);
-    const double stage_cycles = std::max(6.0 * nt, (1.0 * x_stage(2) + 4.0 * 48.0 * nt) / 30.0);
+    const double stage_cycles = std::max(6.0 * nt, (1.0 * x_stage(static_cast<int>(c.channels)) + 4.0 * 48.0 * nt) / 30.0);
     const double tile_cycles = 5500.0 + stage_cycles * ((ks + 1) / 2) + 10.0 * nt;
     const double cost = waves * tile_cycles;
     if (cost < best_cost) {
@@ -864,6 +755,7 @@ UmmaContext *umma_create(const FilterSpec &spec, const std::vector<float> &ref_t
     big_smem(umma_fir_kernel<1, false, true, true>);
     big_smem(umma_fir_kernel<2, false, true, false>);
     big_smem(umma_fir_kernel<2, false, true, true>);
+    umma2_configure_device();
     configured_dev = dev;
   }
   return c;
@@ -875,6 +767,8 @@ void umma_destroy(UmmaContext *c) {
   if (c->d_pool) cudaFree(c->d_pool);
   if (c->d_tiles) cudaFree(c->d_tiles);
   if (c->d_jobs) cudaFree(c->d_jobs);
+  if (c->d_kplan) cudaFree(c->d_kplan);
+  if (c->d_kdev) cudaFree(c->d_kdev);
   if (c->d_trace) cudaFree(c->d_trace);
   delete c;
 }
@@ -917,15 +811,50 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
     drop_pool(c);
     c->nt = nt;
     c->ksteps = umma_ksteps(c->spec.taps, c->spec.num, c->spec.den, nt);
-    c->tile_bytes = 2 * c->ksteps * 3 * nt * 16;
     c->tmem_cols = pow2_cols(4 * nt);
-    const uint32_t stage_bytes = x_stage(static_cast<int>(a.channels)) + kStageChunks * 3 * nt * 16;
-    const uint32_t n_iters = (2 * c->ksteps + kStageChunks - 1) / kStageChunks;
-    uint32_t stages = std::min<uint32_t>(kMaxStages, kMaxSmem / stage_bytes);
-    stages = std::max(1u, std::min(stages, n_iters));
-    c->stages = stages;
-    c->smem_bytes = stages * stage_bytes;
-    if (c->smem_bytes > kMaxSmem) return false;
+    // the persistent kernel with a packed, shared-memory-resident tap tile when that tile fits
+    c->resident = false;
+    // opt-in (SPXB_UMMA_RESIDENT=1): measured slower than the one-tile-per-CTA kernel on every
+    // BASELINE shape
+    static const bool allow_resident = [] {
+      const char *e = getenv("SPXB_UMMA_RESIDENT");
+      return e && atoi(e) != 0;
+    }();
+    uint32_t x_stages = 0;
+    if (allow_resident && build_packed_plan(c->spec, c->ft, nt, &c->packed))
+      x_stages = umma2_x_stages(a.channels, c->packed.tile_bytes, c->ksteps);
+    if (x_stages >= 2) {
+      c->stream_ops += 1;
+      if (c->d_kplan) {
+        cudaStreamSynchronize(stream);
+        cudaFree(c->d_kplan);
+        c->d_kplan = nullptr;
+      }
+      if ((*err = cudaMalloc(reinterpret_cast<void **>(&c->d_kplan), c->ksteps * sizeof(UmmaKStep))) != cudaSuccess ||
+          (*err = cudaMemcpyAsync(c->d_kplan, c->packed.k.data(), c->ksteps * sizeof(UmmaKStep), cudaMemcpyHostToDevice,
+                                  stream)) != cudaSuccess) {
+        c->nt = 0;
+        return false;
+      }
+      cudaStreamSynchronize(stream);  // pageable source; geometry changes are rare
+      if ((*err = umma2_upload_plan(c, stream)) != cudaSuccess) {
+        c->nt = 0;
+        return false;
+      }
+      c->resident = true;
+      c->tile_bytes = c->packed.tile_bytes;
+      c->stages = x_stages;
+      c->smem_bytes = x_stages * x_stage(static_cast<int>(a.channels)) + c->tile_bytes;
+    } else {
+      c->tile_bytes = 2 * c->ksteps * 3 * nt * 16;
+      const uint32_t stage_bytes = x_stage(static_cast<int>(a.channels)) + kStageChunks * 3 * nt * 16;
+      const uint32_t n_iters = (2 * c->ksteps + kStageChunks - 1) / kStageChunks;
+      uint32_t stages = std::min<uint32_t>(kMaxStages, kMaxSmem / stage_bytes);
+      stages = std::max(1u, std::min(stages, n_iters));
+      c->stages = stages;
+      c->smem_bytes = stages * stage_bytes;
+      if (c->smem_bytes > kMaxSmem) return false;
+    }
   }
   std::vector<UmmaTile> tiles;
   std::vector<UmmaTileKey> keys;
@@ -955,7 +884,7 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
     jobs.push_back(keys[i].delta);
   }
   if (next_slot * static_cast<size_t>(c->tile_bytes) > kMaxPoolBytes) return false;
-  const bool table_in_params = inline_tiles_enabled() && tiles.size() <= kInlineTiles;
+  const bool table_in_params = c->resident ? tiles.size() <= 32 : inline_tiles_enabled() && tiles.size() <= kInlineTiles;
   if (c->frozen && (!jobs.empty() || next_slot > c->pool_cap || !table_in_params)) {
     *err = cudaErrorNotSupported;  // would need the stream / an allocation while it is being captured
     return false;
@@ -995,11 +924,15 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
     if ((*err = cudaMemcpyAsync(c->d_jobs, jobs.data(), jobs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
                                 stream)) != cudaSuccess)
       return false;
-    const uint32_t cells = 2 * c->ksteps * 3 * nt;
-    const dim3 grid((cells + 255) / 256, static_cast<unsigned>(n_jobs));
-    build_tap_tiles_kernel<<<grid, 256, 0, stream>>>(c->d_h, c->spec.num, c->spec.den, c->spec.taps, nt, c->ksteps,
-                                                     c->d_jobs, c->d_pool, c->tile_bytes);
-    if ((*err = cudaGetLastError()) != cudaSuccess) return false;
+    if (c->resident) {
+      if ((*err = umma2_build_tiles(c, c->d_jobs, n_jobs, stream)) != cudaSuccess) return false;
+    } else {
+      const uint32_t cells = 2 * c->ksteps * 3 * nt;
+      const dim3 grid((cells + 255) / 256, static_cast<unsigned>(n_jobs));
+      build_tap_tiles_kernel<<<grid, 256, 0, stream>>>(c->d_h, c->spec.num, c->spec.den, c->spec.taps, nt, c->ksteps,
+                                                       c->d_jobs, c->d_pool, c->tile_bytes);
+      if ((*err = cudaGetLastError()) != cudaSuccess) return false;
+    }
     for (auto &kv : fresh) c->slot_of.emplace(kv.first, kv.second);
   }
   // the tile table travels in the kernel parameters when it fits; only longer tables go to HBM
@@ -1056,6 +989,7 @@ uint64_t umma_stream_ops(const UmmaContext *c) { return c ? c->stream_ops : 0; }
 uint64_t umma_pool_generation(const UmmaContext *c) { return c ? c->pool_generation : 0; }
 
 cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, uint32_t *launches) {
+  if (c->resident) return launch_umma2(c, a, stream, launches);
   UmmaArgs u;
   u.tiles = c->d_tiles;
   u.n_tiles = c->n_tiles;
@@ -1100,6 +1034,11 @@ cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, 
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = c->smem_bytes;
+  static const uint32_t pad_smem = [] {  // experiment: what a smaller L1 carve-out costs this kernel
+    const char *e = getenv("SPXB_UMMA_PAD_SMEM");
+    return e ? static_cast<uint32_t>(atoi(e)) : 0u;
+  }();
+  if (pad_smem) cfg.dynamicSmemBytes = std::min<uint32_t>(kMaxSmem, c->smem_bytes + pad_smem);
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   unsigned n_attr = 0;
@@ -1153,6 +1092,12 @@ cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, 
 // debug timeline of the last traced launch: kTraceSlots words per CTA; returns CTAs copied
 long umma_read_trace(const UmmaContext *c, unsigned long long *dst, size_t cap_words) {
   if (!c || !c->d_trace || !c->memo) return 0;
+  if (c->resident) {  // persistent kernel: 128 words per CTA, one CTA per SM at most
+    const size_t n = std::min<size_t>(std::min<size_t>(static_cast<size_t>(c->n_tiles) * c->m_groups, c->sm_count),
+                                      cap_words / 128);
+    if (cudaMemcpy(dst, c->d_trace, n * 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return static_cast<long>(n);
+  }
   const size_t ctas = std::min<size_t>(static_cast<size_t>(c->n_tiles) * c->grid_groups, cap_words / kTraceSlots);
   if (cudaMemcpy(dst, c->d_trace, ctas * kTraceSlots * sizeof(unsigned long long), cudaMemcpyDeviceToHost) !=
       cudaSuccess)

@@ -49,6 +49,13 @@ cudaError_t launch_umma(UmmaContext *c, const CallArgs &a, cudaStream_t stream, 
 void umma_set_frozen(UmmaContext *c, bool frozen);
 uint64_t umma_stream_ops(const UmmaContext *c);
 uint64_t umma_pool_generation(const UmmaContext *c);
+// persistent kernel with resident packed tap tiles (kernels_umma2.cu), chosen by umma_prepare when
+// the packed tile of the geometry fits shared memory
+void umma2_configure_device();
+cudaError_t umma2_upload_plan(UmmaContext *c, cudaStream_t stream);
+uint32_t umma2_x_stages(uint32_t channels, uint32_t tile_bytes, uint32_t ksteps);
+cudaError_t umma2_build_tiles(UmmaContext *c, const uint32_t *d_jobs, size_t n_jobs, cudaStream_t stream);
+cudaError_t launch_umma2(UmmaContext *c, const CallArgs &a, cudaStream_t stream, uint32_t *launches);
 // SPXB_UMMA_TRACE=1: clock64 timeline of the last launch, 32 words per CTA (debug only)
 long umma_read_trace(const UmmaContext *c, unsigned long long *dst, size_t cap_words);
 

@@ -1,6 +1,7 @@
 // umma_plan.cpp -- see umma_plan.h.
 #include "umma_plan.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -98,6 +99,113 @@ void fill_tap_tile_host(const FixedTaps &ft, uint32_t num, uint32_t den, uint32_
         dst[(static_cast<size_t>(c) * rows + r) * 16 + e] = static_cast<int8_t>(d[digit]);
       }
     }
+}
+
+bool build_packed_plan(const FilterSpec &s, const FixedTaps &ft, uint32_t nt, UmmaPackedPlan *out) {
+  const uint32_t ksteps = umma_ksteps(s.taps, s.num, s.den, nt);
+  if (ksteps == 0 || ksteps > kUmmaMaxKsteps || nt % 16 != 0 || nt == 0 || nt > 128) return false;
+  const uint32_t N = s.taps, nb = nt / 16;
+  // tap indices at which each digit is non-zero for some phase
+  int64_t jlo[3] = {N, N, N}, jhi[3] = {-1, -1, -1};
+  for (uint32_t phase = 0; phase < s.den; ++phase)
+    for (uint32_t j = 0; j < N; ++j) {
+      int d[3];
+      split_digits(ft.h[static_cast<size_t>(phase) * N + j], &d[0], &d[1], &d[2]);  // d2, d1, d0
+      for (int i = 0; i < 3; ++i)
+        if (d[i] != 0) {
+          jlo[i] = std::min<int64_t>(jlo[i], j);
+          jhi[i] = std::max<int64_t>(jhi[i], j);
+        }
+    }
+  out->nt = nt;
+  out->ksteps = ksteps;
+  out->k.assign(ksteps, UmmaKStep{});
+  uint32_t off16 = 0;
+  for (uint32_t k = 0; k < ksteps; ++k) {
+    UmmaKStep &ks = out->k[k];
+    for (int i = 0; i < 3; ++i) {
+      uint32_t b0 = nb, b1 = 0;
+      static const bool dense = [] {  // experiment: store every block (one fused MMA per plane when 3nt <= 256)
+        const char *e = getenv("SPXB_UMMA_DENSE");
+        return e && atoi(e) != 0;
+      }();
+      if (k == 0 || dense) {
+        b0 = 0;
+        b1 = nb;
+      } else if (jhi[i] >= 0) {
+        // column n of a tile with key (phase0, delta) starts its window at frame
+        // first(n) = delta + floor((phase0 + n*num)/den) of the tile's K axis, between
+        // floor(n*num/den) and 15 + floor((den-1 + n*num)/den); digit i of column n touches
+        // frames first(n) + [jlo, jhi]; K step k covers frames [32k, 32k+32)
+        for (uint32_t n = 0; n < nt; ++n) {
+          const int64_t fmin = static_cast<int64_t>(static_cast<uint64_t>(n) * s.num / s.den);
+          const int64_t fmax = 15 + static_cast<int64_t>((static_cast<uint64_t>(s.den) - 1 + static_cast<uint64_t>(n) * s.num) / s.den);
+          const bool hit = fmin + jlo[i] <= static_cast<int64_t>(32 * k + 31) && fmax + jhi[i] >= static_cast<int64_t>(32 * k);
+          if (hit) {
+            b0 = std::min(b0, n / 16);
+            b1 = std::max(b1, n / 16 + 1);
+          }
+        }
+      }
+      if (b1 <= b0) b0 = b1 = 0;
+      ks.b0[i] = static_cast<uint8_t>(b0);
+      ks.b1[i] = static_cast<uint8_t>(b1);
+    }
+    // rows of a chunk: d2 blocks, d1 blocks, d0 blocks; entries fuse neighbouring digits whose runs
+    // are contiguous in both the B rows (always) and the D columns (digit i ends at nt and digit
+    // i+1 starts at 0), up to 256 columns
+    uint32_t row = 0;
+    ks.n_ent = 0;
+    bool open = false;
+    for (int i = 0; i < 3; ++i) {
+      const uint32_t n = 16u * (ks.b1[i] - ks.b0[i]);
+      if (n == 0) {
+        open = false;
+        continue;
+      }
+      const uint32_t dcol = static_cast<uint32_t>(i) * nt + 16u * ks.b0[i];
+      UmmaKStep::Entry *last = ks.n_ent ? &ks.ent[ks.n_ent - 1] : nullptr;
+      if (open && last && ks.b0[i] == 0 && last->dcol + last->n == dcol && last->n + n <= 256) {
+        last->n = static_cast<uint16_t>(last->n + n);
+      } else {
+        ks.ent[ks.n_ent].row = static_cast<uint16_t>(row);
+        ks.ent[ks.n_ent].n = static_cast<uint16_t>(n);
+        ks.ent[ks.n_ent].dcol = static_cast<uint16_t>(dcol);
+        ks.n_ent += 1;
+      }
+      open = ks.b1[i] == nb;
+      row += n;
+    }
+    ks.rows = static_cast<uint16_t>(row);
+    ks.off16 = off16;
+    off16 += 2 * row;
+  }
+  out->tile_bytes = off16 * 16;
+  return true;
+}
+
+void fill_tap_tile_packed_host(const FixedTaps &ft, uint32_t num, uint32_t den, uint32_t taps,
+                               const UmmaPackedPlan &plan, UmmaTileKey key, int8_t *dst) {
+  for (uint32_t k = 0; k < plan.ksteps; ++k) {
+    const UmmaKStep &ks = plan.k[k];
+    for (uint32_t half = 0; half < 2; ++half) {
+      uint32_t row = 0;
+      for (int i = 0; i < 3; ++i)
+        for (uint32_t n = 16u * ks.b0[i]; n < 16u * ks.b1[i]; ++n, ++row) {
+          const uint64_t t = static_cast<uint64_t>(key.phase0) + static_cast<uint64_t>(n) * num;
+          const uint32_t phase = static_cast<uint32_t>(t % den);
+          const int64_t first = static_cast<int64_t>(key.delta) + static_cast<int64_t>(t / den);
+          int8_t *cell = dst + (static_cast<size_t>(ks.off16) + static_cast<size_t>(half) * ks.rows + row) * 16;
+          for (uint32_t e = 0; e < 16; ++e) {
+            const int64_t j = static_cast<int64_t>(32 * k + 16 * half + e) - first;
+            int d[3] = {0, 0, 0};
+            if (j >= 0 && j < static_cast<int64_t>(taps))
+              split_digits(ft.h[static_cast<size_t>(phase) * taps + static_cast<size_t>(j)], &d[0], &d[1], &d[2]);
+            cell[e] = static_cast<int8_t>(d[i]);
+          }
+        }
+    }
+  }
 }
 
 }  // namespace spxb

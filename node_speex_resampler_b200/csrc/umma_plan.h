@@ -73,4 +73,44 @@ void plan_umma_tiles(uint32_t num, uint32_t den, uint32_t taps, uint32_t hist_fr
 void fill_tap_tile_host(const FixedTaps &ft, uint32_t num, uint32_t den, uint32_t taps, uint32_t nt,
                         uint32_t ksteps, UmmaTileKey key, int8_t *dst);
 
+// ---------------------------------------------------------------------------------------------
+// Packed ("resident") tap tiles: the banded tap matrix of a tile is mostly zeros -- the corners
+// outside the band, and, because a windowed sinc decays, the high digit d2 is zero outside the
+// main lobe and the middle digit d1 near the filter's ends. A packed tile stores, per K step, only
+// the 16-column blocks of each digit that can hold a non-zero for SOME tile key (phase0, delta), so
+// that one layout -- one table of MMA segments -- serves every tile of the geometry:
+//   K step k:  chunk 0 rows [d2 blocks | d1 blocks | d0 blocks], then chunk 1 rows alike
+//              (rows_k rows of 16 bytes per chunk; the two K halves of one MMA are rows_k*16 apart)
+// K step 0 is stored whole: its MMAs initialise every accumulator column.
+// Each K step runs at most three MMAs per byte plane ("entries": a run of B rows and the D columns
+// it accumulates into; neighbouring digits whose block ranges are whole fuse into one entry).
+constexpr uint32_t kUmmaMaxKsteps = 64;
+constexpr uint32_t kUmmaMaxEntries = 3;
+
+struct UmmaKStep {
+  uint32_t off16;    // byte offset of the K step inside the packed tile, / 16
+  uint16_t rows;     // rows per chunk (= LBO / 16)
+  uint16_t n_ent;
+  struct Entry {
+    uint16_t row;    // first B row inside the chunk
+    uint16_t n;      // columns (multiple of 16, <= 256)
+    uint16_t dcol;   // first accumulator column for the hi plane (the lo plane adds nt)
+  } ent[kUmmaMaxEntries];
+  // block ranges per digit, index 0 = d2, 1 = d1, 2 = d0 (16-column blocks [b0, b1))
+  uint8_t b0[3], b1[3];
+};
+
+struct UmmaPackedPlan {
+  uint32_t nt = 0, ksteps = 0;
+  uint32_t tile_bytes = 0;
+  std::vector<UmmaKStep> k;  // [ksteps]
+};
+
+// false when the geometry is not covered (too many K steps)
+bool build_packed_plan(const FilterSpec &spec, const FixedTaps &ft, uint32_t nt, UmmaPackedPlan *out);
+
+// host fill of one packed tile (tests; the device builder in kernels_umma2.cu must agree)
+void fill_tap_tile_packed_host(const FixedTaps &ft, uint32_t num, uint32_t den, uint32_t taps,
+                               const UmmaPackedPlan &plan, UmmaTileKey key, int8_t *dst);
+
 }  // namespace spxb

@@ -913,15 +913,20 @@ def test_batches_release_their_device_memory():
 
 
 @pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("ch", [1, 2, 3])
 @pytest.mark.parametrize("kernel", [KERNEL_STRICT, KERNEL_TENSOR], ids=["strict", "tensor"])
-def test_c_api_reset_mem_matches_the_reference(kernel):
-    """speex_resampler_reset_mem (resample.c:1208-1220): last_sample, samp_frac_num, magic_samples and
-    the whole filter memory go back to zero mid-stream -- the next calls must match the reference's
-    own build doing the same, and a fresh state fed the same samples."""
+def test_c_api_reset_mem_matches_the_reference(kernel, ch):
+    """speex_resampler_reset_mem (resample.c:1208-1220) mid-stream, call for call against the
+    reference's own build. The reference zeroes last_sample / samp_frac_num / magic_samples and the
+    FIRST nb_channels * (filt_len - 1) floats of `mem`, whose channels lie mem_alloc_size apart: only
+    channel 0's history is certainly cleared (a stereo stream keeps its right-channel history). That
+    is reproduced, not corrected; a mono stream is indistinguishable from a new one afterwards."""
+    if ch == 3 and kernel == KERNEL_TENSOR:
+        pytest.skip("the tensor kernel serves mono and stereo")
     L, R = lib(), O._load_ref()
     R.speex_resampler_reset_mem.restype = C.c_int
     R.speex_resampler_reset_mem.argtypes = [C.c_void_p]
-    ch, i, o, q = 2, 44100, 48000, 7
+    i, o, q = 44100, 48000, 7
     err = C.c_int(0)
     ours = L.speex_resampler_init(ch, i, o, q, C.byref(err))
     ref = R.speex_resampler_init(ch, i, o, q, C.byref(err))
@@ -936,7 +941,9 @@ def test_c_api_reset_mem_matches_the_reference(kernel):
             hist = np.ones((127) * ch, np.int16)
             assert L.spxb_batch_get_state(L.spxb_resampler_batch(ours), 0, C.byref(ls), C.byref(fr), C.byref(mg),
                                           hist.ctypes.data) == 0
-            assert (ls.value, fr.value, mg.value) == (0, 0, 0) and not hist.any()
+            assert (ls.value, fr.value, mg.value) == (0, 0, 0) and not hist.reshape(-1, ch)[:, 0].any()
+            if ch == 2:  # mem_alloc_size 287 > 2 * 127: the right channel's history survives
+                assert hist.reshape(-1, ch)[:, 1].any()
             after_reset = pos
             continue
         chunk = np.ascontiguousarray(x[pos * ch:(pos + n) * ch])
@@ -950,7 +957,7 @@ def test_c_api_reset_mem_matches_the_reference(kernel):
             res.append((n_in.value, n_out.value, out[: n_out.value * ch].copy()))
         assert res[0][:2] == res[1][:2], k
         check_close(res[1][2], res[0][2], exact=kernel == KERNEL_STRICT, what=("reset_mem", k))
-        if k > 3:  # after the reset the stream is indistinguishable from a new one
+        if k > 3 and ch == 1:  # after the reset a mono stream is indistinguishable from a new one
             y, u, m = fresh.process(chunk, cap)
             assert (u, m) == res[1][:2] and np.array_equal(y, res[1][2])
     assert after_reset == 882 + 441 + 300
@@ -992,3 +999,22 @@ def test_empty_chunks_return_empty_buffers():
     t = SpeexResamplerTransform(2, 44100, 48000, 7)
     assert t.transform(b"\x01") == b""  # shorter than one frame: carried, nothing to resample yet
     r.destroy()
+
+
+@pytest.mark.parametrize("shape", [
+    ("C3x", 1300, 2, 44100, 48000, 7, 882, 3),    # 21 groups x 9 tiles on <= 148 CTAs: CTAs walk two tiles
+    ("C5x", 700, 2, 96000, 44100, 10, 1920, 2),   # packed tile of 172 KB, 3 PCM stages, tap tile changes mid-CTA
+    ("C4x", 600, 1, 48000, 16000, 10, 960, 2),    # mono, direct filter N = 768
+    ("q0", 200, 2, 44100, 48000, 0, 441, 2),      # shortest filter: a single stage per tile
+], ids=lambda s: s[0])
+def test_persistent_kernel_parity(shape):
+    """The persistent tensor kernel with packed, resident tap tiles (csrc/kernels_umma2.cu) is opt-in
+    (SPXB_UMMA_RESIDENT=1; measured slower than the one-tile-per-CTA kernel): it must
+    still meet the bar -- <= 1 LSB, >= 90 dB, lengths and device state equal to the oracle's."""
+    import subprocess
+    import sys
+    env = dict(os.environ, SPXB_UMMA_RESIDENT="1", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "resident_check.py")] + [str(v) for v in shape],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "resident ok" in r.stdout and "'stages'" in r.stdout

@@ -122,3 +122,107 @@ def test_emulated_integer_pipeline_matches_oracle(c):
     assert O.snr_db(want, got.astype(np.int16)) >= 90.0
     # the integer pipeline is closer to the reference than +-1 LSB suggests: mismatches are rare
     assert (d != 0).mean() < 0.02
+
+
+# ---------------------------------------------------------------------------------------------
+# packed ("resident") tap tiles of the persistent tensor kernel (csrc/umma_plan.h, kernels_umma2.cu)
+# ---------------------------------------------------------------------------------------------
+def packed_plan(i, o, q, nt):
+    L = lib()
+    words = np.zeros(64 * 18, np.uint32)
+    tb = C.c_uint32(0)
+    ks = L.spxb_tensor_packed_plan(i, o, q, nt, words.ctypes.data, words.size, C.byref(tb))
+    assert ks > 0, ks
+    return words[: ks * 18].reshape(ks, 18).astype(np.int64), tb.value
+
+
+@pytest.mark.parametrize("c", CASES, ids=lambda c: f"{c[0]}ch_{c[1]}to{c[2]}_q{c[3]}_nt{c[5]}")
+def test_packed_tiles_hold_every_nonzero_of_the_dense_tiles(c):
+    """For a spread of tile keys the packed tile, unpacked through its own block table, must equal
+    the dense tile exactly: nothing non-zero falls outside the stored blocks, the stored cells are
+    the dense cells, K step 0 is whole, offsets are the running sum of the rows."""
+    L = lib()
+    ch, i, o, q, n, nt = c
+    info, h, sh, _ = fixed_taps(i, o, q)
+    plan, tile_bytes = packed_plan(i, o, q, nt)
+    ks = plan.shape[0]
+    off = 0
+    for k in range(ks):
+        assert plan[k, 0] == off
+        rows = sum(16 * (plan[k, 15 + d] - plan[k, 12 + d]) for d in range(3))
+        assert plan[k, 1] == rows
+        off += 2 * rows
+    assert off * 16 == tile_bytes
+    assert all(plan[0, 12 + d] == 0 and plan[0, 15 + d] == nt // 16 for d in range(3))
+    dense_bytes = 2 * ks * 3 * nt * 16
+    assert tile_bytes <= dense_bytes
+    rng = np.random.default_rng(nt)
+    keys = [(0, 0), (info.den - 1, 15), (info.den // 2, 7)] + [(int(rng.integers(info.den)), int(rng.integers(16))) for _ in range(5)]
+    for phase0, delta in keys:
+        dense = np.zeros(dense_bytes, np.int8)
+        assert L.spxb_tensor_tap_tile(i, o, q, nt, phase0, delta, dense.ctypes.data, dense.size) == dense.size
+        dense = dense.reshape(2 * ks, 3 * nt, 16)
+        packed = np.zeros(tile_bytes, np.int8)
+        assert L.spxb_tensor_tap_tile_packed(i, o, q, nt, phase0, delta, packed.ctypes.data, packed.size) == tile_bytes
+        rebuilt = np.zeros_like(dense)
+        for k in range(ks):
+            rows = plan[k, 1]
+            for half in range(2):
+                cells = packed[(plan[k, 0] + half * rows) * 16: (plan[k, 0] + (half + 1) * rows) * 16].reshape(rows, 16)
+                r = 0
+                for d in range(3):
+                    n0, n1 = 16 * plan[k, 12 + d], 16 * plan[k, 15 + d]
+                    rebuilt[2 * k + half, d * nt + n0: d * nt + n1] = cells[r: r + (n1 - n0)]
+                    r += n1 - n0
+                assert r == rows
+        assert np.array_equal(rebuilt, dense), (phase0, delta, np.argwhere(rebuilt != dense)[:4])
+
+
+@pytest.mark.parametrize("c", CASES[:5], ids=lambda c: f"{c[0]}ch_{c[1]}to{c[2]}_q{c[3]}_nt{c[5]}")
+def test_packed_mma_schedule_reproduces_the_dense_gemm(c):
+    """The kernel's MMA schedule over the packed tile -- K step 0 whole, then per K step the table's
+    entries (first B row, columns, first accumulator column; lo plane one digit block to the right) --
+    must leave in the four accumulator blocks exactly what the dense banded GEMM leaves."""
+    L = lib()
+    ch, i, o, q, n, nt = c
+    info, h, sh, _ = fixed_taps(i, o, q)
+    plan, tile_bytes = packed_plan(i, o, q, nt)
+    ks = plan.shape[0]
+    rng = np.random.default_rng(7)
+    phase0, delta = int(rng.integers(info.den)), int(rng.integers(16))
+    dense = np.zeros(2 * ks * 3 * nt * 16, np.int8)
+    L.spxb_tensor_tap_tile(i, o, q, nt, phase0, delta, dense.ctypes.data, dense.size)
+    B = dense.reshape(2 * ks, 3 * nt, 16).transpose(1, 0, 2).reshape(3 * nt, 32 * ks).astype(np.int64)
+    packed = np.zeros(tile_bytes, np.int8)
+    L.spxb_tensor_tap_tile_packed(i, o, q, nt, phase0, delta, packed.ctypes.data, packed.size)
+    x = rng.integers(-32768, 32768, size=32 * ks).astype(np.int64)
+    hi, lo = x >> 8, x & 255
+    want = np.zeros(4 * nt, np.int64)
+    want[: 3 * nt] += B @ hi
+    want[nt:] += B @ lo
+    acc = np.full(4 * nt, 10 ** 12, np.int64)  # garbage until initialised
+    for k in range(ks):
+        rows = plan[k, 1]
+        chunk = [packed[(plan[k, 0] + half * rows) * 16: (plan[k, 0] + (half + 1) * rows) * 16].reshape(rows, 16).astype(np.int64)
+                 for half in range(2)]
+        xs = [x[32 * k + 16 * half: 32 * k + 16 * half + 16] for half in range(2)]
+        if k == 0:
+            assert rows == 3 * nt
+            full = sum(chunk[half] @ (xs[half] >> 8) for half in range(2))
+            full_lo = sum(chunk[half] @ (xs[half] & 255) for half in range(2))
+            acc[: 3 * nt] = full                    # hi plane, accumulate = 0
+            acc[nt: 3 * nt] += full_lo[: 2 * nt]    # lo plane onto P1, P2
+            acc[3 * nt:] = full_lo[2 * nt:]         # lo plane, P3 fresh
+            continue
+        assert 0 <= plan[k, 2] <= 3
+        covered = 0
+        for e in range(plan[k, 2]):
+            row, ncol, dcol = plan[k, 3 + 3 * e], plan[k, 4 + 3 * e], plan[k, 5 + 3 * e]
+            assert ncol % 16 == 0 and 16 <= ncol <= 256 and row + ncol <= rows and dcol + ncol <= 3 * nt
+            for plane, shift in ((0, 0), (1, nt)):
+                v = sum(chunk[half][row: row + ncol] @ ((xs[half] >> 8) if plane == 0 else (xs[half] & 255))
+                        for half in range(2))
+                acc[dcol + shift: dcol + shift + ncol] += v
+            covered += ncol
+        assert covered == rows
+    assert np.array_equal(acc, want)
