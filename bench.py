@@ -113,6 +113,11 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # CPU implementation of the path (reference arm / cpu_baseline)
 # ---------------------------------------------------------------------------
+CPU_WHAT = ("the reference's own deps/speex/resample.c compiled natively by oracle/Makefile "
+            "(-O2 -ffp-contract=off -DFLOATING_POINT -DOUTSIDE_SPEEX): the native-C proxy for the shipped "
+            "WASM module (no Node / WASM runtime in this image; the translated module itself runs at 0.9x of it)")
+
+
 def cpu_run(wl: str, steps: int, warmup: int, threads: int | None = None):
     """The reference's CPU path on this box's cores: every step resamples one 20 ms chunk of
     every stream of the workload, streams spread over `threads` OS threads (ctypes releases
@@ -157,15 +162,17 @@ def reference_arm(args):
         return
     wl = args.workload
     S, ch, i, o, q, n = WORKLOADS[wl]
-    # bound the run: ~0.75 core-seconds per C3 step
-    steps = args.steps
-    rate, sec_per_step, kind, threads = cpu_run(wl, steps, min(args.warmup, 2))
+    steps, W = args.steps, max(args.warmup, 3)
+    # bound the run: ~0.75 core-seconds per C3 step; the warm-up is capped in TIME, not in the count
+    # it reports (the CPU path has no clocks to ramp: two steps warm its caches and page in the streams)
+    rate, sec_per_step, kind, threads = cpu_run(wl, steps, min(W, 2))
     sample = f"{steps} steps x {S} streams x 20 ms ({kind} C, one stream per thread, {threads} threads)"
     line = {"impl": "reference", "metric": "output_msamples_per_sec", "value": rate / 1e6, "unit": "Msamples/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": sec_per_step * 1e3,
+            "n_gpus": args.gpus, "steps": steps, "warmup": W, "ms_per_step": sec_per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": describe(wl),
-            "cpu_baseline": {"value": rate / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": rate / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind,
+                             "what": CPU_WHAT, "sample": sample, "warmup_steps_run": min(W, 2)},
             "e2e": {"value": rate / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -173,44 +180,24 @@ def reference_arm(args):
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
-def ours(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    pass
 
-    import node_speex_resampler_b200 as pkg
-    from node_speex_resampler_b200 import _lib
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path "
-                         "(use --impl reference for the CPU implementation)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    L = pkg.lib()
-    wl = args.workload
-    S, ch, i, o, q, n = WORKLOADS[wl]
-    if args.streams:
-        S = args.streams
-    # weak scaling: the job is world * S independent streams, rank r owns one contiguous block
-    from node_speex_resampler_b200.sharding import shard_range
-    lo, hi = shard_range(S * world, world, rank)
-    assert hi - lo == S
+def measure(cx, wl, S, K, W, min_seconds, lean, kernel):
+    """One workload on this rank's GPU: device-resident throughput (CUDA events), the roofline of
+    its FIR kernel, and the same metric end to end through the C ABI with pinned host buffers.
+    Returns a dict; the multi-rank reductions (max over ranks) happen inside."""
+    torch, dist, pkg, _lib, L = cx.torch, cx.dist, cx.pkg, cx._lib, cx.L
+    world, rank, local = cx.world, cx.rank, cx.local
+    _, ch, i, o, q, n = WORKLOADS[wl]
     info = _lib.FilterInfo()
     L.spxb_filter_describe(i, o, q, C.byref(info))
     N = info.filt_len
     cap = int(math.ceil(n * o / i))
     batch = pkg.StreamBatch(S, ch, i, o, q, device=local)
     batch.set_kernel({"auto": pkg.KERNEL_AUTO, "strict": pkg.KERNEL_STRICT, "tiled": pkg.KERNEL_TILED,
-                      "tensor": pkg.KERNEL_TENSOR}[args.kernel])
+                      "tensor": pkg.KERNEL_TENSOR}[kernel])
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)  # events below and the batch's kernels share this stream
     assert L.spxb_batch_set_stream(batch._h, C.c_void_p(stream.cuda_stream)) == 0
@@ -224,12 +211,12 @@ def ours(args):
     out_slot = S * cap_pad * ch
     ring = max(4, int(math.ceil(1.25 * L2_BYTES / (in_slot * 2))))
     ring = min(ring, 96)
-    if args.ring:
-        ring = args.ring
+    if cx.ring:
+        ring = cx.ring
     # a ring that divides the step count makes every timed region walk the same slots, so the
     # library's CUDA graph of the hop sequence (spxb_batch_process_device_ring) is captured once
     for cand in range(ring, min(2 * ring, 96) + 1):
-        if args.steps % cand == 0 and not args.ring:
+        if K % cand == 0 and not cx.ring:
             ring = cand
             break
     hop = pkg.synth_pcm(min(S, 256), ch, n * 4, i, seed=0xB200 + rank)
@@ -246,9 +233,8 @@ def ours(args):
         if e:
             raise RuntimeError(_lib.strerror(e) + ": " + _lib.last_error())
 
-    K, W = args.steps, max(args.warmup, 3)
     run_hops(0, W)
-    barrier()
+    cx.barrier()
     # probe one step to size the repetitions (each timed region is EXACTLY K steps)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -256,7 +242,7 @@ def ours(args):
     e1.record()
     torch.cuda.synchronize()
     est = max(e0.elapsed_time(e1) * 1e-3, 1e-6)
-    reps = int(min(400, max(3, math.ceil(args.min_seconds / est))))
+    reps = int(min(400, max(3, math.ceil(min_seconds / est))))
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -264,15 +250,15 @@ def ours(args):
         time.sleep(0.15)
     c0 = batch.counters().kernel_launches
     times = []
-    barrier()
+    cx.barrier()
     t_start = time.perf_counter()
     step_no = W + K
     for r in range(reps):
-        barrier()
+        cx.barrier()
         e0.record()
         run_hops(step_no, K)
         e1.record()
-        barrier()
+        cx.barrier()
         times.append(e0.elapsed_time(e1) * 1e-3)
         step_no += K
     t_end = time.perf_counter()
@@ -290,22 +276,19 @@ def ours(args):
     # ---- roofline of the FIR kernel ----
     # --lean: no auxiliary kernels (FFMA peak probe, device-copy floor), so that an ncu launch list
     # of the command holds the step's own kernels only
-    fp32_peak = 148 * 128 * 2 * 1.965e9 if args.lean else L.spxb_measure_fp32_peak(8192)
+    fp32_peak = 148 * 128 * 2 * 1.965e9 if lean else cx.fp32_peak()
     flops_per_launch = out_samples_step * 2.0 * N
     t_launch = sec / K
     bytes_per_launch = (out_samples_step * 2.0 + S * n * ch * 2.0 + 2.0 * S * ch * (N - 1) * 2.0)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = cx.peaks
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     # DRAM bytes per launch of this kernel from the committed ncu --set full capture (never measured
-    # under the profiler here); null when no capture exists for the workload
+    # under the profiler here; profiles/traffic.json is written by scripts/ncu_traffic.py from the
+    # .ncu-rep files); null when no capture exists for the workload at this batch size
     traffic, traffic_src = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{wl}:{kernel_used}")
-        if tr:
+        if tr and int(tr.get("streams", WORKLOADS[wl][0])) == S:
             traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
             traffic_src = tr["source"]
     except Exception:
@@ -324,7 +307,7 @@ def ours(args):
     # is dominated by per-launch latency, not by HBM -- a practical floor for one step.
     copy_floor = None
     try:
-        if args.lean:
+        if lean:
             raise RuntimeError("skipped (--lean)")
         half = int(bytes_per_launch // 2) // 16 * 16
         c_src = torch.empty((8, half), dtype=torch.uint8, device="cuda")
@@ -372,6 +355,7 @@ def ours(args):
     src = np.ascontiguousarray(d_in[:hr, :, : n * ch].cpu().numpy())
     for k in range(hr):
         C.memmove(hin[k], src[k].ctypes.data, in_bytes)
+    del src
     nin = np.empty(S, np.uint32)
     nout = np.empty(S, np.uint32)
     depth = L.spxb_batch_pipeline_depth(batch._h)
@@ -403,13 +387,13 @@ def ours(args):
     e2e_steps(max(W, 3))
     batch.synchronize()
     host_t["submit"] = host_t["wait"] = 0.0
-    barrier()
+    cx.barrier()
     e0.record()
     tw0 = time.perf_counter()
     e2e_steps(Ke)
     batch.synchronize()
     e1.record()
-    barrier()
+    cx.barrier()
     tw1 = time.perf_counter()
     e2e_sec = max(e0.elapsed_time(e1) * 1e-3, tw1 - tw0)
     if world > 1:
@@ -418,7 +402,8 @@ def ours(args):
         e2e_sec = float(t.item())
     e2e_value = out_samples_step * world * Ke / e2e_sec
     # the ceiling of that number: this step's H2D and D2H bytes copied concurrently from/to pinned
-    # memory with nothing else running (PCIe Gen5 x16 on this box), no kernel in between
+    # memory with nothing else running on this GPU (every rank does it at the same time, so at N > 1
+    # it is the ceiling UNDER the contention for the host's memory and PCIe switches), no kernel
     pcie = None
     try:
         # same number of distinct pinned host buffers as the e2e loop rotates over (a single
@@ -431,6 +416,7 @@ def ours(args):
         nrep = max(10, int(0.2 / max(e2e_sec / Ke, 1e-6)))
         for timed in (False, True):
             torch.cuda.synchronize()
+            cx.barrier()
             tp0 = time.perf_counter()
             for k in range(nrep):
                 with torch.cuda.stream(s_a):
@@ -440,15 +426,212 @@ def ours(args):
             torch.cuda.synchronize()
             tp1 = time.perf_counter()
         per_step = (tp1 - tp0) / nrep
+        if world > 1:
+            t = torch.tensor([per_step], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            per_step = float(t.item())
         pcie = {"copy_only_us_per_step": per_step * 1e6, "h2d_GBs": in_bytes / per_step / 1e9,
                 "d2h_GBs": out_bytes / per_step / 1e9, "host_buffers": hr,
                 "ceiling_msamples_per_sec": out_samples_step * world / per_step / 1e6,
-                "e2e_frac_of_ceiling": (e2e_value / (out_samples_step * world / per_step))}
+                "e2e_frac_of_ceiling": (e2e_value / (out_samples_step * world / per_step)),
+                "how": "this rank's H2D and D2H of one step's bytes, concurrently, all ranks at once, max over ranks"}
         del h_i, h_o, d_i, d_o
     except Exception as ex:  # noqa: BLE001
         pcie = {"error": str(ex)}
     for p in hin + hout:
         L.spxb_host_free(p)
+    batch.close()
+    del d_in, d_out
+    torch.cuda.empty_cache()
+    return {"config": dict(describe(wl), streams_per_gpu=S,
+                           workload=describe(wl)["workload"].replace(f"{WORKLOADS[wl][0]} streams/GPU", f"{S} streams/GPU")),
+            "value": value / 1e6, "unit": "Msamples/s", "ms_per_step": sec / K * 1e3,
+            "measurement": {"timing": f"median of {reps} regions of exactly {K} steps, CUDA events; inputs: ring of "
+                                      f"{ring} distinct hops in HBM ({ring * in_slot * 2 >> 20} MiB > L2), no L2 flush needed",
+                            "kernel": kernel_used, "filt_len": N},
+            "dtype": "s8 x s8 -> s32 (exact integer FIR)" if kernel_used == "tensor" else "f32",
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": out_bytes, "steps": Ke, "pipeline_depth": depth,
+                    "how": "spxb_batch_submit/wait (C ABI), pinned host buffers, H2D+kernel+D2H per step",
+                    "host_us_per_step": {"submit": host_t["submit"] / Ke * 1e6, "wait": host_t["wait"] / Ke * 1e6},
+                    "pcie": pcie},
+            "roofline": roof}
+
+
+def single_stream_latency(cx):
+    """The reference's real call pattern (src/index.ts:96-102): ONE stereo stream, one 20 ms chunk per
+    synchronous call through speex_resampler_process_interleaved_int with pageable host buffers.
+    Wall time per call, median of 300, per kernel family, beside the reference's C on one core."""
+    pkg, _lib, L = cx.pkg, cx._lib, cx.L
+    from oracle import oracle as O
+    ch, i, o, q, n = 2, 44100, 48000, 7, 882
+    cap = 960
+    x = pkg.synth_pcm(1, ch, n * 8, i, seed=77)[0]
+    out = np.zeros(cap * ch, np.int16)
+    res = {}
+    for name, k in (("strict", pkg.KERNEL_STRICT), ("tensor", pkg.KERNEL_TENSOR), ("auto", pkg.KERNEL_AUTO)):
+        err = C.c_int(0)
+        st = L.speex_resampler_init(ch, i, o, q, C.byref(err))
+        L.spxb_batch_set_kernel(L.spxb_resampler_batch(st), k)
+        ts = []
+        for it in range(340):
+            chunk = x[(it % 8) * n * ch:((it % 8) + 1) * n * ch]
+            n_in, n_out = C.c_uint32(n), C.c_uint32(cap)
+            t0 = time.perf_counter()
+            e = L.speex_resampler_process_interleaved_int(st, chunk.ctypes.data, C.byref(n_in), out.ctypes.data, C.byref(n_out))
+            ts.append(time.perf_counter() - t0)
+            assert e == 0 and n_out.value in (959, 960)
+        L.speex_resampler_destroy(st)
+        res[name] = statistics.median(ts[40:]) * 1e6
+    cls, kind = O.best_cpu_resampler()
+    r = cls(ch, i, o, q)
+    ts = []
+    for it in range(340):
+        chunk = x[(it % 8) * n * ch:((it % 8) + 1) * n * ch]
+        t0 = time.perf_counter()
+        r.process(chunk, cap)
+        ts.append(time.perf_counter() - t0)
+    res["cpu_" + kind] = statistics.median(ts[40:]) * 1e6
+    res["what"] = ("one stereo 44100->48000 q7 stream, 882 frames per call, speex_resampler_process_interleaved_int, "
+                   "pageable buffers, wall clock around the call (includes both copies and the synchronisation), "
+                   "median of 300 calls; strict is the default of the drop-in surface")
+    return res
+
+
+def file_configs(cx):
+    """BASELINE configs 1-2: the reference's own resources/*.pcm through processChunk -- the whole file
+    in one call (src/test.ts:24-44, what its test prints the time of) and in 20 ms chunks -- beside the
+    reference's C on one core, same file, same calls. Wall clock; the GPU arm includes the copies."""
+    pkg = cx.pkg
+    from oracle import oracle as O
+    cases = [("44100hz_test.pcm", 2, 44100, 48000, 7), ("24000hz_mono_test.pcm", 1, 24000, 44100, 1),
+             ("24000hz_mono_test.pcm", 1, 24000, 44100, 7), ("24000hz_mono_test.pcm", 1, 24000, 44100, 10)]
+    if O.fixture_path(cases[0][0]) is None:
+        return {"unavailable": "oracle/_ref/resources absent (make -C oracle where /root/reference exists)"}
+    cls, kind = O.best_cpu_resampler()
+    rows = []
+    for f, ch, i, o, q in cases:
+        data = open(O.fixture_path(f), "rb").read()
+        hop = i // 50 * ch * 2  # 20 ms of input, in bytes
+        row = {"file": f, "channels": ch, "in_rate": i, "out_rate": o, "quality": q, "bytes": len(data)}
+        for kname, kern in (("strict", pkg.KERNEL_STRICT), ("tensor", pkg.KERNEL_TENSOR)):
+            r = pkg.SpeexResampler(ch, i, o, q)
+            r.kernel = kern
+            r.processChunk(data[: hop * 4])  # init + first-call planning outside the timed region
+            r.destroy()
+            r = pkg.SpeexResampler(ch, i, o, q)
+            r.kernel = kern
+            r.processChunk(b"")
+            t0 = time.perf_counter()
+            y = r.processChunk(data)
+            t1 = time.perf_counter()
+            r.destroy()
+            r = pkg.SpeexResampler(ch, i, o, q)
+            r.kernel = kern
+            r.processChunk(b"")
+            t2 = time.perf_counter()
+            total = 0
+            for k in range(0, len(data) - len(data) % (ch * 2), hop):
+                total += len(r.processChunk(data[k:k + hop]))
+            t3 = time.perf_counter()
+            r.destroy()
+            row[kname] = {"one_shot_ms": (t1 - t0) * 1e3, "one_shot_msamples_per_sec": len(y) / 2 / (t1 - t0) / 1e6,
+                          "chunked_20ms_ms": (t3 - t2) * 1e3, "chunked_us_per_call": (t3 - t2) / max(1, -(-len(data) // hop)) * 1e6}
+        c = cls(ch, i, o, q)
+        t0 = time.perf_counter()
+        yc = c.processChunk(data)
+        t1 = time.perf_counter()
+        c = cls(ch, i, o, q)
+        t2 = time.perf_counter()
+        for k in range(0, len(data) - len(data) % (ch * 2), hop):
+            c.processChunk(data[k:k + hop])
+        t3 = time.perf_counter()
+        row["cpu_" + kind] = {"one_shot_ms": (t1 - t0) * 1e3, "one_shot_msamples_per_sec": len(yc) / 2 / (t1 - t0) / 1e6,
+                              "chunked_20ms_ms": (t3 - t2) * 1e3, "cores": 1}
+        row["out_frames"] = len(yc) // 2 // ch
+        rows.append(row)
+    return {"what": "whole file in one processChunk call and in 20 ms chunks, wall clock, one stream; "
+                    "cpu = " + CPU_WHAT, "cases": rows}
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import node_speex_resampler_b200 as pkg
+    from node_speex_resampler_b200 import _lib
+
+    cx = Ctx()
+    cx.torch, cx.dist, cx.pkg, cx._lib = torch, dist, pkg, _lib
+    cx.world = world = int(os.environ.get("WORLD_SIZE", "1"))
+    cx.rank = rank = int(os.environ.get("RANK", "0"))
+    cx.local = local = int(os.environ.get("LOCAL_RANK", "0"))
+    cx.ring = args.ring
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path "
+                         "(use --impl reference for the CPU implementation)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    cx.barrier = barrier
+    cx.L = L = pkg.lib()
+    try:
+        cx.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        cx.peaks = {}
+    _fp32 = []
+
+    def fp32_peak():
+        if not _fp32:
+            _fp32.append(L.spxb_measure_fp32_peak(8192))
+        return _fp32[0]
+    cx.fp32_peak = fp32_peak
+
+    wl = args.workload
+    S = args.streams or WORKLOADS[wl][0]
+    # weak scaling: the job is world * S independent streams, rank r owns one contiguous block
+    from node_speex_resampler_b200.sharding import shard_range
+    lo, hi = shard_range(S * world, world, rank)
+    assert hi - lo == S
+    K, W = args.steps, max(args.warmup, 3)
+    head = measure(cx, wl, S, K, W, args.min_seconds, args.lean, args.kernel)
+
+    # ---- the other BASELINE shapes, timed like the headline (BASELINE configs[3], configs[4]) ----
+    also = None
+    if wl == "C3" and not args.no_also and not args.streams:
+        also = {}
+        # config 5 as BASELINE states it: 65536 stereo streams sharded over the GPUs of the run
+        # (2/4/8); on one GPU the per-GPU share of the 8-GPU case
+        shapes = {"C4": WORKLOADS["C4"][0], "C5": 8192 if world == 1 else 65536 // world}
+        for name, s_gpu in shapes.items():
+            try:
+                m = measure(cx, name, s_gpu, K, W, min(args.min_seconds, 0.4), True, args.kernel)
+                m["scaling"] = "weak" if name == "C4" else ("strong (65536 streams over the run's GPUs)" if world > 1 else
+                                                            "weak (8192 streams: one GPU's share of the 8-GPU case)")
+                r = m["roofline"]
+                m["roofline"] = {k: r.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "traffic_source",
+                                                       "launch_us", "algorithmic_bytes_per_launch", "bytes_per_output_sample")}
+                also[name] = m
+            except Exception as ex:  # noqa: BLE001
+                also[name] = {"error": repr(ex)}
+
+    # ---- single stream: call latency and the reference's own files (rank 0, one GPU) ----
+    latency = files = None
+    if rank == 0 and world == 1 and not args.no_also and not args.streams:
+        try:
+            latency = single_stream_latency(cx)
+        except Exception as ex:  # noqa: BLE001
+            latency = {"error": repr(ex)}
+        try:
+            files = file_configs(cx)
+        except Exception as ex:  # noqa: BLE001
+            files = {"error": repr(ex)}
 
     # ---- CPU baseline beside it (rank 0, N == 1 only) ----
     cpu = None
@@ -459,27 +642,19 @@ def ours(args):
         cpu_steps = max(1, int(20.0 * cores / per_step_core_s / cores)) if wl != "C5" else 1
         cpu_steps = max(1, min(cpu_steps, int(15.0 * cores / per_step_core_s)))
         rate, sps, kind, threads = cpu_run(wl, cpu_steps, 0)
-        cpu = {"value": rate / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind,
+        cpu = {"value": rate / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind, "what": CPU_WHAT,
                "sample": f"{cpu_steps} steps x {S_} streams x 20 ms, one stream per thread, {threads} threads"}
 
     if rank == 0:
-        line = {"metric": "output_msamples_per_sec", "value": value / 1e6, "unit": "Msamples/s", "n_gpus": world,
-                "steps": K, "warmup": W, "ms_per_step": sec / K * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None,
-                "dtype": "s8 x s8 -> s32 (exact integer FIR)" if kernel_used == "tensor" else "f32",
-                "data": "synthetic",
-                "config": dict(describe(wl), timing=f"median of {reps} regions of exactly {K} steps, CUDA events; "
-                               f"inputs: ring of {ring} distinct hops in HBM ({ring * in_slot * 2 >> 20} MiB > L2), "
-                               "no L2 flush needed", kernel=kernel_used, filt_len=N),
-                "clocks": clocks, "gpu_launches": int(launches),
-                "e2e": {"value": e2e_value / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": in_bytes,
-                        "d2h_bytes_per_step": out_bytes, "steps": Ke, "pipeline_depth": depth,
-                        "how": "spxb_batch_submit/wait (C ABI), pinned host buffers, H2D+kernel+D2H per step",
-                        "host_us_per_step": {"submit": host_t["submit"] / Ke * 1e6, "wait": host_t["wait"] / Ke * 1e6},
-                        "pcie": pcie},
-                "roofline": roof, "cpu_baseline": cpu}
+        line = {"metric": "output_msamples_per_sec", "value": head["value"], "unit": "Msamples/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
+                "config": describe(wl) if not args.streams else head["config"],
+                "measurement": head["measurement"],
+                "clocks": head["clocks"], "gpu_launches": head["gpu_launches"],
+                "e2e": head["e2e"], "roofline": head["roofline"], "cpu_baseline": cpu,
+                "also": also, "latency_us": latency, "files": files}
         print(json.dumps(line), flush=True)
-    batch.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -494,6 +669,8 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "strict", "tiled", "tensor"])
     ap.add_argument("--min-seconds", type=float, default=1.0, help="clock-sampling window for the timed regions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true",
+                    help="headline workload only: skip the `also` (C4, C5), `latency_us` and `files` blocks")
     ap.add_argument("--streams", type=int, default=0, help="experiments: streams per GPU instead of the workload's")
     ap.add_argument("--ring", type=int, default=0, help="experiments: number of distinct hops resident in HBM")
     ap.add_argument("--lean", action="store_true", help="skip the auxiliary probes (FFMA peak, device-copy floor)")

@@ -681,15 +681,24 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
     return 0;
   }
 
-  // ---- H2D ----
+  // Small calls (a single stream's 20 ms chunk is 3.5 KB) are latency, not bandwidth: both copies and
+  // the kernel go down ONE stream with no event hand-overs between three (each costs several
+  // microseconds of a ~25 us call); large calls keep the three-stream pipeline that overlaps the
+  // copy of step k+1 with the kernel of step k and the read-back of step k-1.
   const size_t in_row_bytes = static_cast<size_t>(d.max_n_in) * ch * sizeof(int16_t);
+  const size_t out_bytes_est = static_cast<size_t>(d.max_n_out) * ch * sizeof(int16_t) * S;
+  const bool small_call = in_row_bytes * S + out_bytes_est <= (256u << 10);
+  const cudaStream_t s_in = small_call ? b->s_compute : b->s_in;
+  const cudaStream_t s_out = small_call ? b->s_compute : b->s_out;
+
+  // ---- H2D ----
   const bool direct_in = d.uniform && is_pinned_or_device(in);
   if (dense_in) {
-    SPXB_CUDA(cudaMemcpyAsync(sl.d_in, in, in_row_bytes * S, cudaMemcpyDefault, b->s_in));
+    SPXB_CUDA(cudaMemcpyAsync(sl.d_in, in, in_row_bytes * S, cudaMemcpyDefault, s_in));
   } else if (direct_in) {
     SPXB_CUDA(cudaMemcpy2DAsync(sl.d_in, dev_in_stride * sizeof(int16_t), in,
                                 in_stride_frames * ch * sizeof(int16_t), in_row_bytes, S,
-                                cudaMemcpyDefault, b->s_in));
+                                cudaMemcpyDefault, s_in));
   } else {
     if (int e = grow_pinned(&sl.h_in, &sl.h_in_cap, dev_in_stride * S)) return e;
     for (uint32_t s = 0; s < S; ++s) {
@@ -697,42 +706,42 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
       std::memcpy(sl.h_in + s * dev_in_stride, in + s * in_stride_frames * ch, n * ch * sizeof(int16_t));
     }
     SPXB_CUDA(cudaMemcpyAsync(sl.d_in, sl.h_in, dev_in_stride * S * sizeof(int16_t),
-                              cudaMemcpyHostToDevice, b->s_in));
+                              cudaMemcpyHostToDevice, s_in));
   }
   b->counters.h2d_bytes += in_row_bytes * S;
   if (!d.uniform) {
-    SPXB_CUDA(cudaMemcpyAsync(sl.d_calls, sl.h_calls, S * sizeof(StreamCall), cudaMemcpyHostToDevice, b->s_in));
+    SPXB_CUDA(cudaMemcpyAsync(sl.d_calls, sl.h_calls, S * sizeof(StreamCall), cudaMemcpyHostToDevice, s_in));
     b->counters.h2d_bytes += S * sizeof(StreamCall);
   }
-  SPXB_CUDA(cudaEventRecord(sl.ev_h2d, b->s_in));
+  if (!small_call) SPXB_CUDA(cudaEventRecord(sl.ev_h2d, s_in));
 
   // ---- kernel ----
-  SPXB_CUDA(cudaStreamWaitEvent(b->s_compute, sl.ev_h2d, 0));
+  if (!small_call) SPXB_CUDA(cudaStreamWaitEvent(b->s_compute, sl.ev_h2d, 0));
   if (int e = launch_call(b, sl.d_in, dev_in_stride, sl.d_out, dev_out_stride,
                           d.uniform ? nullptr : sl.d_calls, d.uni, d.max_n_out,
                           d.uniform ? RaggedHost() : RaggedHost{sl.h_calls, sl.h_ids, sl.d_ids})) {
     // nothing was launched: the slot goes back (its H2D is harmless), the positions were never moved
-    cudaEventRecord(sl.ev_done, b->s_in);
+    cudaEventRecord(sl.ev_done, s_in);
     return e;
   }
   commit_positions(b, d, sl.h_calls);
-  SPXB_CUDA(cudaEventRecord(sl.ev_kernel, b->s_compute));
+  if (!small_call) SPXB_CUDA(cudaEventRecord(sl.ev_kernel, b->s_compute));
 
   // ---- D2H ----
-  SPXB_CUDA(cudaStreamWaitEvent(b->s_out, sl.ev_kernel, 0));
+  if (!small_call) SPXB_CUDA(cudaStreamWaitEvent(s_out, sl.ev_kernel, 0));
   const size_t out_row_bytes = static_cast<size_t>(d.max_n_out) * ch * sizeof(int16_t);
   if (d.max_n_out != 0) {
     const bool direct_out = d.uniform && is_pinned_or_device(out);
     if (dense_out) {
-      SPXB_CUDA(cudaMemcpyAsync(out, sl.d_out, out_row_bytes * S, cudaMemcpyDefault, b->s_out));
+      SPXB_CUDA(cudaMemcpyAsync(out, sl.d_out, out_row_bytes * S, cudaMemcpyDefault, s_out));
     } else if (direct_out) {
       SPXB_CUDA(cudaMemcpy2DAsync(out, out_stride_frames * ch * sizeof(int16_t), sl.d_out,
                                   dev_out_stride * sizeof(int16_t), out_row_bytes, S,
-                                  cudaMemcpyDefault, b->s_out));
+                                  cudaMemcpyDefault, s_out));
     } else {
       if (int e = grow_pinned(&sl.h_out, &sl.h_out_cap, dev_out_stride * S)) return e;
       SPXB_CUDA(cudaMemcpyAsync(sl.h_out, sl.d_out, dev_out_stride * S * sizeof(int16_t),
-                                cudaMemcpyDeviceToHost, b->s_out));
+                                cudaMemcpyDeviceToHost, s_out));
       sl.bounce_out = true;
       sl.user_out = out;
       sl.user_out_stride = out_stride_frames * ch;
@@ -744,7 +753,7 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
     }
     b->counters.d2h_bytes += out_row_bytes * S;
   }
-  SPXB_CUDA(cudaEventRecord(sl.ev_done, b->s_out));
+  SPXB_CUDA(cudaEventRecord(sl.ev_done, s_out));
   b->counters.calls += 1;
   return 0;
 }

@@ -23,33 +23,35 @@ namespace {
 
 constexpr int kStrictThreads = 128;
 
-template <bool kDirect, bool kWide, int FMT>
-__device__ __forceinline__ float strict_output(const CallArgs &a, uint32_t s, uint32_t c,
-                                               const StreamCall &sc, uint32_t m) {
-  const FilterDev &F = a.filt;
-  const int N = static_cast<int>(F.taps);
+// first frame of output m's window in X~ coordinates (history is f < 0), and its phase
+__device__ __forceinline__ int window_start(const FilterDev &F, const StreamCall &sc, uint32_t m, uint32_t *phase) {
   const unsigned long long t = static_cast<unsigned long long>(sc.frac0) +
                                static_cast<unsigned long long>(m) * F.num;
-  const uint32_t phase = static_cast<uint32_t>(t % F.den);
-  // first frame of the window in X~ coordinates (history is f < 0)
-  const int q = sc.ls0 - (N - 1) + static_cast<int>(t / F.den);
+  *phase = static_cast<uint32_t>(t % F.den);
+  return sc.ls0 - (static_cast<int>(F.taps) - 1) + static_cast<int>(t / F.den);
+}
+
+// X(j) = sample j of the output's window, as the f32 the reference holds in `mem`
+template <bool kDirect, bool kWide, typename Window>
+__device__ __forceinline__ float strict_output(const FilterDev &F, uint32_t phase, const Window &X) {
+  const int N = static_cast<int>(F.taps);
 
   if (kDirect) {
     const float *h = F.table + static_cast<size_t>(phase) * N;
     if (!kWide) {
       float acc = 0.f;
       for (int j = 0; j < N; ++j) {
-        const float x = fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in);
+        const float x = X(j);
         acc = __fadd_rn(acc, __fmul_rn(__ldg(h + j), x));
       }
       return acc;
     } else {
       double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
       for (int j = 0; j < N; j += 4) {
-        const float x0 = fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in);
-        const float x1 = fetch_sample_f<FMT>(a, s, q + j + 1, c, sc.n_in);
-        const float x2 = fetch_sample_f<FMT>(a, s, q + j + 2, c, sc.n_in);
-        const float x3 = fetch_sample_f<FMT>(a, s, q + j + 3, c, sc.n_in);
+        const float x0 = X(j);
+        const float x1 = X(j + 1);
+        const float x2 = X(j + 2);
+        const float x3 = X(j + 3);
         a0 = __dadd_rn(a0, static_cast<double>(__fmul_rn(__ldg(h + j), x0)));
         a1 = __dadd_rn(a1, static_cast<double>(__fmul_rn(__ldg(h + j + 1), x1)));
         a2 = __dadd_rn(a2, static_cast<double>(__fmul_rn(__ldg(h + j + 2), x2)));
@@ -66,7 +68,7 @@ __device__ __forceinline__ float strict_output(const CallArgs &a, uint32_t s, ui
     if (!kWide) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       for (int j = 0; j < N; ++j) {
-        const float x = fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in);
+        const float x = X(j);
         const float *cf = tp + static_cast<size_t>(j) * os;
         a0 = __fadd_rn(a0, __fmul_rn(x, __ldg(cf)));
         a1 = __fadd_rn(a1, __fmul_rn(x, __ldg(cf + 1)));
@@ -80,7 +82,7 @@ __device__ __forceinline__ float strict_output(const CallArgs &a, uint32_t s, ui
     } else {
       double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
       for (int j = 0; j < N; ++j) {
-        const float x = fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in);
+        const float x = X(j);
         const float *cf = tp + static_cast<size_t>(j) * os;
         a0 = __dadd_rn(a0, static_cast<double>(__fmul_rn(x, __ldg(cf))));
         a1 = __dadd_rn(a1, static_cast<double>(__fmul_rn(x, __ldg(cf + 1))));
@@ -98,21 +100,56 @@ __device__ __forceinline__ float strict_output(const CallArgs &a, uint32_t s, ui
   }
 }
 
-template <bool kDirect, bool kWide, int FMT>
+// STAGED: the block first copies the window its 128 outputs read (history || input, as f32) into
+// shared memory, coalesced; the tap loops then run without the per-sample history / input / bounds
+// branches and unroll. Same values, same operations, same order -- only where the samples are read
+// from changes. 3.5x on a single stream's 20 ms call (the path is latency, not throughput, there).
+template <bool kDirect, bool kWide, int FMT, bool STAGED>
 __global__ void __launch_bounds__(kStrictThreads)
     strict_fir_kernel(const CallArgs a, const uint32_t blocks_per_stream,
-                      const uint32_t fir_blocks) {
+                      const uint32_t fir_blocks, const uint32_t win_cap) {
+  extern __shared__ float win[];
   if (blockIdx.x >= fir_blocks) {
     history_block_f<FMT>(a, blockIdx.x - fir_blocks);
     return;
   }
   const uint32_t s = launch_stream(a, blockIdx.x / blocks_per_stream);
-  const uint32_t e = (blockIdx.x % blocks_per_stream) * kStrictThreads + threadIdx.x;
+  const uint32_t e0 = (blockIdx.x % blocks_per_stream) * kStrictThreads;
+  const uint32_t e = e0 + threadIdx.x;
   const StreamCall sc = load_call(a, s);
-  const uint32_t m = e / a.channels;
-  const uint32_t c = e % a.channels;
-  if (m >= sc.n_out) return;
-  const float y = strict_output<kDirect, kWide, FMT>(a, s, c, sc, m);
+  const uint32_t ch = a.channels;
+  const uint32_t m = e / ch;
+  const uint32_t c = e % ch;
+  uint32_t phase = 0;
+  float y = 0.f;
+  if (STAGED) {
+    // frames [q_lo, q_hi + N) serve every output of the block (q is non-decreasing in m)
+    const uint32_t m_lo = e0 / ch;
+    if (m_lo >= sc.n_out) return;  // whole block past the end (block-uniform)
+    const uint32_t m_hi = min((e0 + kStrictThreads - 1) / ch, sc.n_out - 1);
+    uint32_t ph;
+    const int q_lo = window_start(a.filt, sc, m_lo, &ph);
+    const int q_hi = window_start(a.filt, sc, m_hi, &ph);
+    const uint32_t elems = (static_cast<uint32_t>(q_hi - q_lo) + a.filt.taps) * ch;
+    if (elems <= win_cap) {
+      for (uint32_t i = threadIdx.x; i < elems; i += kStrictThreads)
+        win[i] = fetch_sample_f<FMT>(a, s, q_lo + static_cast<int>(i / ch), i % ch, sc.n_in);
+      __syncthreads();
+      if (m >= sc.n_out) return;
+      const int q = window_start(a.filt, sc, m, &phase);
+      const float *xw = win + static_cast<uint32_t>(q - q_lo) * ch + c;
+      y = strict_output<kDirect, kWide>(a.filt, phase, [&](int j) { return xw[static_cast<uint32_t>(j) * ch]; });
+    } else {
+      // (a window wider than the shared memory asked for: straight from global memory)
+      if (m >= sc.n_out) return;
+      const int q = window_start(a.filt, sc, m, &phase);
+      y = strict_output<kDirect, kWide>(a.filt, phase, [&](int j) { return fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in); });
+    }
+  } else {
+    if (m >= sc.n_out) return;
+    const int q = window_start(a.filt, sc, m, &phase);
+    y = strict_output<kDirect, kWide>(a.filt, phase, [&](int j) { return fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in); });
+  }
   if (FMT == 2)  // the float entry stores the kernel's result as is (resample.c:927-963)
     reinterpret_cast<float *>(a.out + static_cast<size_t>(s) * a.out_stride)[e] = y;
   else
@@ -136,15 +173,25 @@ cudaError_t launch_strict(const CallArgs &a, cudaStream_t stream, uint32_t *laun
   const uint32_t fir_blocks = static_cast<uint32_t>(fir_blocks64);
   const dim3 grid(static_cast<uint32_t>(total)), block(kStrictThreads);
   const uint32_t bps_arg = bps ? bps : 1;
-  auto go = [&](auto kernel) { kernel<<<grid, block, 0, stream>>>(a, bps_arg, fir_blocks); };
+  // shared-memory window of a block: its 128 outputs advance by at most ceil(128/ch * num/den) + 1
+  // frames, plus the filter length; staged when that fits the default 48 KB
+  const uint64_t out_frames = (kStrictThreads + a.channels - 1) / a.channels + 1;
+  const uint64_t win_frames = (out_frames * a.filt.num + a.filt.den - 1) / a.filt.den + 2 + a.filt.taps;
+  const uint64_t win_bytes = win_frames * a.channels * sizeof(float);
+  const bool staged = win_bytes <= 48u * 1024u && a.channels <= kStrictThreads;
+  const uint32_t win_cap = staged ? static_cast<uint32_t>(win_bytes / sizeof(float)) : 0u;
+  auto go = [&](auto kernel_staged, auto kernel_plain) {
+    if (staged) kernel_staged<<<grid, block, win_bytes, stream>>>(a, bps_arg, fir_blocks, win_cap);
+    else kernel_plain<<<grid, block, 0, stream>>>(a, bps_arg, fir_blocks, 0u);
+  };
   auto by_filter = [&](auto fmt) {
     constexpr int F = decltype(fmt)::value;
     if (a.filt.direct) {
-      if (a.filt.wide_accum) go(strict_fir_kernel<true, true, F>);
-      else go(strict_fir_kernel<true, false, F>);
+      if (a.filt.wide_accum) go(strict_fir_kernel<true, true, F, true>, strict_fir_kernel<true, true, F, false>);
+      else go(strict_fir_kernel<true, false, F, true>, strict_fir_kernel<true, false, F, false>);
     } else {
-      if (a.filt.wide_accum) go(strict_fir_kernel<false, true, F>);
-      else go(strict_fir_kernel<false, false, F>);
+      if (a.filt.wide_accum) go(strict_fir_kernel<false, true, F, true>, strict_fir_kernel<false, true, F, false>);
+      else go(strict_fir_kernel<false, false, F, true>, strict_fir_kernel<false, false, F, false>);
     }
   };
   if (a.fmt == 2) by_filter(std::integral_constant<int, 2>{});

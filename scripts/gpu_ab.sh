@@ -4,7 +4,7 @@ set -u
 for ROUND in 1 2; do
 for LIBF in "$@"; do
   for WL in ${WLS:-C3 C4 C5}; do
-    SPXB_LIB_PATH=$PWD/$LIBF timeout 300 python bench.py --workload $WL --kernel tensor --steps 200 --warmup 10 --no-cpu-baseline --lean --min-seconds 0.3 2>/dev/null | python -c "
+    SPXB_LIB_PATH=$PWD/$LIBF timeout 300 python bench.py --workload $WL --kernel tensor --steps 200 --warmup 10 --no-cpu-baseline --no-also --lean --min-seconds 0.3 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):

@@ -4,7 +4,7 @@ set -u
 OUT=gpurun_out; mkdir -p $OUT
 for CL in 1 2 4; do
   for WL in C3 C4 C5; do
-    SPXB_UMMA_CLUSTER=$CL timeout 300 python bench.py --workload $WL --kernel tensor --steps 200 --warmup 10 --no-cpu-baseline --min-seconds 0.3 2>$OUT/err.txt | python -c "
+    SPXB_UMMA_CLUSTER=$CL timeout 300 python bench.py --workload $WL --kernel tensor --steps 200 --warmup 10 --no-cpu-baseline --no-also --min-seconds 0.3 2>$OUT/err.txt | python -c "
 import sys, json
 ok = False
 for l in sys.stdin:

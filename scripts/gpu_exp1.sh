@@ -11,7 +11,7 @@ for l in sys.stdin:
         d = json.loads(l); print('$label us/step %.2f' % (d['ms_per_step']*1e3))
 "
 }
-B="timeout 200 python bench.py --kernel tensor --steps 192 --warmup 10 --no-cpu-baseline --lean --min-seconds 0.3"
+B="timeout 200 python bench.py --kernel tensor --steps 192 --warmup 10 --no-cpu-baseline --no-also --lean --min-seconds 0.3"
 for WL in C5 C4 C3; do
   run "v1 $WL" SPXB_UMMA_RESIDENT=0 $B --workload $WL
   run "v2 $WL" $B --workload $WL

@@ -9,7 +9,7 @@ for l in sys.stdin:
         d = json.loads(l); g = d['roofline']['tensor']['geometry']; print('$label us/step %.2f  nt %d stages %d smem %d tiles %d' % (d['ms_per_step']*1e3, g['nt'], g['stages'], g['smem_bytes'], g['tiles']))
 "
 }
-B="timeout 200 python bench.py --kernel tensor --steps 192 --warmup 10 --no-cpu-baseline --lean --min-seconds 0.3"
+B="timeout 200 python bench.py --kernel tensor --steps 192 --warmup 10 --no-cpu-baseline --no-also --lean --min-seconds 0.3"
 for WL in C5 C4; do
   run "v1 $WL" SPXB_UMMA_RESIDENT=0 $B --workload $WL
   run "v2 $WL packed" $B --workload $WL

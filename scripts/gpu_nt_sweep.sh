@@ -3,7 +3,7 @@
 set -u
 for WL in C3 C4 C5; do
   for NT in 0 48 64 80 96 112 128; do
-    SPXB_UMMA_NT=$NT timeout 300 python bench.py --workload $WL --kernel tensor --steps 50 --warmup 5 --no-cpu-baseline --min-seconds 0.2 2>/dev/null | python -c "
+    SPXB_UMMA_NT=$NT timeout 300 python bench.py --workload $WL --kernel tensor --steps 50 --warmup 5 --no-cpu-baseline --no-also --min-seconds 0.2 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):

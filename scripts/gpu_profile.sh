@@ -8,19 +8,18 @@ TAG=${1:-r1c}
 OUT=gpurun_out; mkdir -p $OUT
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -6 | tee $OUT/pytest_$TAG.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee $OUT/smoke_$TAG.log
-for WL in C3 C4 C5; do
-  timeout 900 python bench.py --workload $WL > $OUT/bench_${WL}_$TAG.json 2> $OUT/bench_${WL}_$TAG.err
-  tail -c 300 $OUT/bench_${WL}_$TAG.json; echo
-done
-timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/bench_ref_C3_$TAG.json 2>/dev/null
+# the default line (C3 headline + also{C4, C5} + latency_us + files + cpu_baseline), as the driver runs it
+timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+tail -c 300 $OUT/bench_$TAG.json; echo
+timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $OUT/bench_ref_C3_$TAG.json 2>/dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 5 -c 200 --csv --log-file $OUT/launches_$TAG.csv \
-  python bench.py --steps 20 --warmup 5 --no-cpu-baseline --lean --min-seconds 0.001 > /dev/null 2>&1
-for WL in C3 C5; do
+  python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-also --lean --min-seconds 0.001 > /dev/null 2>&1
+for WL in C3 C4 C5; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:umma_fir -s 8 -c 1 -f -o $OUT/prof_umma_${WL}_$TAG \
-    python bench.py --workload $WL --kernel tensor --steps 10 --warmup 3 --no-cpu-baseline --min-seconds 0.001 > /dev/null 2>&1
+    python bench.py --workload $WL --kernel tensor --steps 10 --warmup 3 --no-cpu-baseline --no-also --min-seconds 0.001 > /dev/null 2>&1
 done
 for SL in 2 3 4; do
-  SPXB_PIPELINE_SLOTS=$SL timeout 300 python bench.py --workload C3 --steps 200 --warmup 5 --no-cpu-baseline --min-seconds 0.3 2>/dev/null | python -c "
+  SPXB_PIPELINE_SLOTS=$SL timeout 300 python bench.py --workload C3 --steps 200 --warmup 5 --no-cpu-baseline --no-also --min-seconds 0.3 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):

@@ -14,9 +14,25 @@ keys = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__b
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
         'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum', 'smsp__inst_executed.sum',
+        # tensor pipe (no tensor counter appeared in any profile)
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_tensor.sum', 'sm__inst_executed_pipe_uniform.sum',
+        'l1tex__data_pipe_tc_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum', 'lts__t_sectors_srcunit_tex_lookup_hit.sum',
+        'lts__t_sectors_srcunit_tex_lookup_miss.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__sass_thread_inst_executed_op_ffma_pred_on.sum', 'sm__cycles_elapsed.max', 'sm__cycles_active.avg']
 for k in keys:
     if k in d: print(f"{k} = {d[k]} {u.get(k,'')}")
+for k in d:  # 'realtime' tensor counters carry a section prefix in the raw page
+    if 'pipe_tensor' in k and 'realtime' in k: print(f"{k} = {d[k]} {u.get(k,'')}")
+try:
+    c = float(d['l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']); w = float(d['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum'])
+    print(f"shared-memory bank-conflict ratio (LSU): {c:.0f} conflict wavefronts of {w:.0f} = {c / w:.3f}")
+except Exception:
+    pass
 for k in sorted(d):
     if 'issue_stalled' in k and k.endswith('per_issue_active.ratio') and float(d[k] or 0) > 0.05:
         print(f"  {k.split('issue_stalled_')[1].split('_per_issue')[0]:>22s} {float(d[k]):.3f}")
