@@ -104,6 +104,21 @@ SPXB_API int speex_resampler_set_rate(SpeexResamplerState *st, uint32_t in_rate,
 SPXB_API int speex_resampler_set_rate_frac(SpeexResamplerState *st, uint32_t ratio_num,
                                            uint32_t ratio_den, uint32_t in_rate, uint32_t out_rate);
 SPXB_API int speex_resampler_set_quality(SpeexResamplerState *st, int quality);
+/* Per-channel entries and strides (speex_resampler.h:169-193, :285-309; resample.c:925-1036,
+ * :1170-1188): channel `channel_index` of the state alone, reading in[i * in_stride] and writing
+ * out[m * out_stride]. The first such call turns the state into a planar one (one mono device
+ * stream per channel, each with its own position), which also serves the interleaved entries
+ * from then on -- bit-exactly, on the strict kernel. */
+SPXB_API int speex_resampler_process_int(SpeexResamplerState *st, uint32_t channel_index,
+                                         const int16_t *in, uint32_t *in_len, int16_t *out,
+                                         uint32_t *out_len);
+SPXB_API int speex_resampler_process_float(SpeexResamplerState *st, uint32_t channel_index,
+                                           const float *in, uint32_t *in_len, float *out,
+                                           uint32_t *out_len);
+SPXB_API void speex_resampler_set_input_stride(SpeexResamplerState *st, uint32_t stride);   /* :1170 */
+SPXB_API void speex_resampler_get_input_stride(SpeexResamplerState *st, uint32_t *stride);  /* :1175 */
+SPXB_API void speex_resampler_set_output_stride(SpeexResamplerState *st, uint32_t stride);  /* :1180 */
+SPXB_API void speex_resampler_get_output_stride(SpeexResamplerState *st, uint32_t *stride); /* :1185 */
 SPXB_API int speex_resampler_skip_zeros(SpeexResamplerState *st);         /* resample.c:1200 */
 SPXB_API int speex_resampler_reset_mem(SpeexResamplerState *st);          /* resample.c:1208 */
 
@@ -168,6 +183,16 @@ SPXB_API int spxb_batch_process(spxb_batch *b, const int16_t *in, size_t in_stri
 SPXB_API int spxb_batch_process_f32(spxb_batch *b, const float *in, size_t in_stride_frames,
                                     uint32_t *in_frames, float *out, size_t out_stride_frames,
                                     uint32_t *out_frames);
+
+/* Strided call, all streams of the batch (backs the per-channel Speex entries): stream s reads
+ * sample f of its channel c at in[s*in_stream_stride + f*in_step + c] and writes
+ * out[s*out_stream_stride + m*out_step + c]; strides and steps count samples of the call's format
+ * (float_io != 0: f32, float batch only). Samples between the strided ones are neither read nor
+ * written. Synchronous; bit-exact (strict kernel). */
+SPXB_API int spxb_batch_process_strided(spxb_batch *b, const void *in, size_t in_stream_stride,
+                                        uint32_t in_step, uint32_t *in_frames, void *out,
+                                        size_t out_stream_stride, uint32_t out_step,
+                                        uint32_t *out_frames, int float_io);
 
 /* Same, split for pipelining host<->device copies against the kernel: submit() stages
  * H2D + kernel + D2H on the batch's streams and returns a ticket at once (in_frames /

@@ -96,6 +96,12 @@ struct spxb_batch {
   uint32_t in_block = kInBlock;           // input frames per block of the reference walk (call_plan.h)
   const CallPlan *forced_plan = nullptr;  // set by the C API around a call that has magic samples pending
   uint32_t io_words = 1;    // int16 units per in/out sample of the call being issued
+  // strided call in progress (spxb_batch_process_strided): samples between consecutive frames of a
+  // series in the caller's buffers; 0 = rows are channels-interleaved (every other entry)
+  uint32_t in_step = 0, out_step = 0;
+  // the streams of this batch are the CHANNELS of one Speex state that has used the per-channel
+  // entries (capi.cu): reset_mem reproduces the reference's channel-major layout quirk across them
+  bool planar_state = false;
   // filter bank in HBM
   float *d_table = nullptr, *d_taps = nullptr, *d_blend = nullptr, *d_band = nullptr;
   uint32_t band_kp = 0, band_pad = 0, band_row = 0;
@@ -281,6 +287,9 @@ static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elem
   a.fmt = !b->f32 ? 0u : (b->io_words == 2 ? 2u : 1u);
   a.ids = nullptr;
   a.n_ids = 0;
+  a.in_step = b->in_step ? b->in_step : b->channels;
+  a.out_step = b->out_step ? b->out_step : b->channels;
+  const bool strided = a.in_step != b->channels || a.out_step != b->channels;
 
   uint32_t launches = 0;
   cudaError_t ce = cudaSuccess;
@@ -288,8 +297,10 @@ static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elem
   TiledConfig cfg;
   const int pref = b->kernel_pref;
   // float batches run the strict kernel only (the fast families are built around int16 history)
-  const bool want_tensor = !b->f32 && (pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TENSOR);
-  const bool want_tiled = !b->f32 && (pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TILED);
+  // float batches and strided calls run the strict kernel only (the fast families are built around
+  // int16 history and channels-interleaved rows)
+  const bool want_tensor = !b->f32 && !strided && (pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TENSOR);
+  const bool want_tiled = !b->f32 && !strided && (pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TILED);
   bool grouped = false;
   if (want_tensor && d_calls && rh.calls && max_n_out != 0 && b->umma && !b->dry_run) {
     // ragged batch: groups of streams that share one position run on the tensor kernel
@@ -303,14 +314,14 @@ static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elem
     used = SPXB_KERNEL_TENSOR;
   } else if (ce != cudaSuccess) {
     // planning failed on a CUDA error (not merely "not covered")
-  } else if (pref == SPXB_KERNEL_TENSOR && max_n_out != 0) {
+  } else if (pref == SPXB_KERNEL_TENSOR && max_n_out != 0 && !strided) {
     set_error("SPXB_KERNEL_TENSOR requested but this call does not qualify for the tensor kernel");
     return RESAMPLER_ERR_BAD_STATE;
   } else if (want_tiled && b->d_band && tiled_qualifies(a, b->sm_count, &cfg)) {
     if (b->dry_run) launches += 1;
     else ce = launch_tiled(a, cfg, b->s_compute, &launches);
     used = SPXB_KERNEL_TILED;
-  } else if (pref == SPXB_KERNEL_TILED && max_n_out != 0) {
+  } else if (pref == SPXB_KERNEL_TILED && max_n_out != 0 && !strided) {
     set_error("SPXB_KERNEL_TILED requested but this call does not qualify for the tiled kernel");
     return RESAMPLER_ERR_BAD_STATE;
   } else {
@@ -766,7 +777,8 @@ static int submit_host(spxb_batch *b, const int16_t *in, size_t in_stride_frames
 // c * mem_alloc_size + j < nb_channels * (filt_len - 1). Reproduced as it is (a stereo stream keeps
 // its right-channel history across a reset in the reference, and so it does here).
 __global__ void reset_hist_kernel(int16_t *hist, uint32_t n_streams, uint32_t hist_stride, uint32_t hist_frames,
-                                  uint32_t channels, uint32_t words, uint32_t live, uint32_t mem_alloc) {
+                                  uint32_t channels, uint32_t words, uint32_t live, uint32_t mem_alloc,
+                                  uint32_t planar_state) {
   const size_t per_stream = static_cast<size_t>(hist_frames) * channels;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= per_stream * n_streams) return;
@@ -775,7 +787,9 @@ __global__ void reset_hist_kernel(int16_t *hist, uint32_t n_streams, uint32_t hi
   bool zero = frame < lead;  // padding in front of the live history is always zero
   if (!zero) {
     const uint64_t j = frame - lead;
-    zero = static_cast<uint64_t>(c) * mem_alloc + j < static_cast<uint64_t>(channels) * live;
+    // (a planar state: its streams are the channels of one Speex state)
+    zero = planar_state ? static_cast<uint64_t>(s) * mem_alloc + j < static_cast<uint64_t>(n_streams) * live
+                        : static_cast<uint64_t>(c) * mem_alloc + j < static_cast<uint64_t>(channels) * live;
   }
   if (zero)
     for (uint32_t w = 0; w < words; ++w) hist[static_cast<size_t>(s) * hist_stride + static_cast<size_t>(e) * words + w] = 0;
@@ -920,6 +934,77 @@ int spxb_batch_process_f32(spxb_batch *b, const float *in, size_t in_stride_fram
   b->io_words = 1;
   if (e) return e;
   return spxb_batch_wait(b, t);
+}
+
+// Strided call (the per-channel entries of the Speex API, resample.c:925-1036): stream s reads sample
+// f of its channel c at in[s * in_stream_stride + f * in_step + c] and writes out[s * out_stream_stride
+// + m * out_step + c]; strides and steps count SAMPLES of the call's format (float_io: f32, float
+// batch only). Elements between the strided ones are never read or written. Synchronous, strict kernel.
+int spxb_batch_process_strided(spxb_batch *b, const void *in, size_t in_stream_stride, uint32_t in_step,
+                               uint32_t *in_frames, void *out, size_t out_stream_stride, uint32_t out_step,
+                               uint32_t *out_frames, int float_io) {
+  if (!b || !in_frames || !out_frames || !in || !out || in_step == 0 || out_step == 0) return RESAMPLER_ERR_INVALID_ARG;
+  if (float_io && !b->f32) {
+    set_error("float samples need a batch made by spxb_batch_create_f32 (float history)");
+    return RESAMPLER_ERR_BAD_STATE;
+  }
+  if (int e = spxb_batch_synchronize(b)) return e;
+  DeviceGuard g(b->device);
+  const uint32_t S = b->n_streams, ch = b->channels;
+  const uint32_t words = float_io ? 2u : 1u;  // int16 units per sample
+  Slot &sl = b->slots[0];
+  if (!sl.h_calls) {
+    SPXB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_calls), S * sizeof(StreamCall), cudaHostAllocDefault));
+    SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&sl.d_calls), S * sizeof(StreamCall)));
+    SPXB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_ids), S * sizeof(uint32_t), cudaHostAllocDefault));
+    SPXB_CUDA(cudaMalloc(reinterpret_cast<void **>(&sl.d_ids), S * sizeof(uint32_t)));
+  }
+  std::vector<uint32_t> offered_in(in_frames, in_frames + S);
+  b->io_words = words;
+  // every stream gets its own plan (a per-channel call moves one stream of a planar state only)
+  const bool was_uniform = b->uniform_pos;
+  b->uniform_pos = false;
+  Decided d = decide(b, in_frames, out_frames, sl.h_calls);
+  b->uniform_pos = was_uniform;
+  b->io_words = 1;
+  if (!d.any_work) return 0;
+  // spans of the caller's buffers the call touches, in samples
+  size_t span_in = 0, span_out = 0;
+  for (uint32_t s = 0; s < S; ++s) {
+    if (offered_in[s]) span_in = std::max(span_in, s * in_stream_stride + static_cast<size_t>(offered_in[s] - 1) * in_step + ch);
+    if (out_frames[s]) span_out = std::max(span_out, s * out_stream_stride + static_cast<size_t>(out_frames[s] - 1) * out_step + ch);
+  }
+  if (int e = grow_device(&sl.d_in, &sl.d_in_cap, std::max<size_t>(span_in * words, 8))) return e;
+  if (int e = grow_device(&sl.d_out, &sl.d_out_cap, std::max<size_t>(span_out * words, 8))) return e;
+  if (int e = grow_pinned(&sl.h_in, &sl.h_in_cap, std::max<size_t>(span_in * words, 8))) return e;
+  if (int e = grow_pinned(&sl.h_out, &sl.h_out_cap, std::max<size_t>(span_out * words, 8))) return e;
+  std::memcpy(sl.h_in, in, span_in * words * sizeof(int16_t));
+  SPXB_CUDA(cudaMemcpyAsync(sl.d_in, sl.h_in, span_in * words * sizeof(int16_t), cudaMemcpyHostToDevice, b->s_compute));
+  SPXB_CUDA(cudaMemcpyAsync(sl.d_calls, sl.h_calls, S * sizeof(StreamCall), cudaMemcpyHostToDevice, b->s_compute));
+  b->counters.h2d_bytes += span_in * words * sizeof(int16_t) + S * sizeof(StreamCall);
+  b->in_step = in_step;
+  b->out_step = out_step;
+  b->io_words = words;
+  const int e = launch_call(b, sl.d_in, in_stream_stride * words, sl.d_out, out_stream_stride * words, sl.d_calls, d.uni,
+                            d.max_n_out);
+  b->in_step = b->out_step = 0;
+  b->io_words = 1;
+  if (e) return e;
+  d.uniform = false;
+  commit_positions(b, d, sl.h_calls);
+  if (span_out) {
+    SPXB_CUDA(cudaMemcpyAsync(sl.h_out, sl.d_out, span_out * words * sizeof(int16_t), cudaMemcpyDeviceToHost, b->s_compute));
+    b->counters.d2h_bytes += span_out * words * sizeof(int16_t);
+  }
+  SPXB_CUDA(cudaStreamSynchronize(b->s_compute));
+  // only the samples the call produced go to the caller's buffer
+  for (uint32_t s = 0; s < S; ++s)
+    for (uint32_t m = 0; m < out_frames[s]; ++m) {
+      const size_t at = (s * out_stream_stride + static_cast<size_t>(m) * out_step) * words;
+      std::memcpy(static_cast<int16_t *>(out) + at, sl.h_out + at, static_cast<size_t>(ch) * words * sizeof(int16_t));
+    }
+  b->counters.calls += 1;
+  return 0;
 }
 
 int spxb_batch_process_device(spxb_batch *b, const int16_t *d_in, size_t in_stride_frames,
@@ -1275,7 +1360,7 @@ int spxb_batch_reset(spxb_batch *b) {
   if (elems) {
     reset_hist_kernel<<<static_cast<unsigned>((elems + 255) / 256), 256, 0, b->s_compute>>>(
         b->d_hist[b->hist_cur], b->n_streams, b->hist_stride, b->hist_frames, b->channels, b->hist_words, live,
-        mem_alloc);
+        mem_alloc, b->planar_state ? 1u : 0u);
     SPXB_CUDA(cudaGetLastError());
   }
   SPXB_CUDA(cudaMemsetAsync(b->d_last_sample, 0, b->n_streams * sizeof(int32_t), b->s_compute));
@@ -1517,4 +1602,6 @@ void batch_set_in_block(spxb_batch *b, uint32_t in_block) {
   b->memo_valid = false;
 }
 void batch_force_plan(spxb_batch *b, const CallPlan *plan) { b->forced_plan = plan; }
+void batch_set_planar_state(spxb_batch *b, bool planar) { b->planar_state = planar; }
+uint32_t batch_in_block(const spxb_batch *b) { return b->in_block; }
 }

@@ -18,6 +18,8 @@ const FilterSpec &batch_spec(const spxb_batch *b);
 int batch_kernel_pref(const spxb_batch *b);
 void batch_set_in_block(spxb_batch *b, uint32_t in_block);
 void batch_force_plan(spxb_batch *b, const CallPlan *plan);
+void batch_set_planar_state(spxb_batch *b, bool planar);
+uint32_t batch_in_block(const spxb_batch *b);
 void set_error(const std::string &msg);
 }
 
@@ -39,6 +41,13 @@ struct SpeexResamplerState_ {
   std::vector<float> joined_f;
   std::vector<int16_t> silence;  // stands in for in == NULL (resample.c:1007-1010)
   std::vector<float> fsilence;   // the same for the float entry (resample.c:950-952)
+  // st->in_stride / st->out_stride of the reference (resample.c:836-837, :1170-1188): used by the
+  // per-channel entries only (the interleaved ones override them with nb_channels, :1066-1068)
+  uint32_t in_stride = 1, out_stride = 1;
+  // A state that has used a per-channel entry is PLANAR: its batch holds one mono stream per channel,
+  // each with its own position (the reference keeps last_sample / samp_frac_num / mem per channel).
+  bool planar = false;
+  std::vector<uint32_t> lens_in, lens_out;
 };
 
 extern "C" {
@@ -120,59 +129,111 @@ int speex_resampler_get_output_latency(SpeexResamplerState *st) {
 //  * mid-stream, longer filter (:727-758 with no magic samples pending): the old history moves to
 //    the end of the new one behind zeros and last_sample advances by half the growth;
 //  * mid-stream, shorter filter: the surplus history stays behind as "magic samples" that the next
-//    calls resample before their own input (:759-776, :904-922; process_with_magic below). Only a
-//    further change of the filter LENGTH while such samples are pending is refused.
+//    calls resample before their own input (:759-776, :904-922; process_with_magic below);
+//  * any of these again while such samples are still pending (reshape_memory below).
+// The reference's memory around a filter-length change, per channel (resample.c:727-776), as one
+// sequence of frames V = history (N_old - 1 frames) ++ pending magic frames (M):
+//  * shorter filter (:759-776): m = (N_old - N_new) / 2 frames move out of the history into the
+//    magic region: history' = V[m, m + N_new - 1), magic' = the next m + M frames;
+//  * longer filter (:727-758): the pending frames are first folded back "as if nothing had
+//    happened" -- B = M zero frames ++ V, olen = N_old + 2M -- then, if N_new > olen, history' =
+//    zeros ++ B and last_sample advances by (N_new - olen) / 2; otherwise m2 = (olen - N_new) / 2
+//    frames of B turn into magic again: history' = B[m2, m2 + N_new - 1), magic' = the next m2.
+// All channels of a state move together here, so the frames stay interleaved.
+extern "C++" {
+template <typename T>
+static void reshape_memory(std::vector<T> &V, size_t ch, uint32_t n_old, uint32_t n_new, uint32_t M,
+                           std::vector<T> *hist, std::vector<T> *magic, uint32_t *magic_frames, int32_t *last_sample) {
+  auto frames = [&](const std::vector<T> &src, size_t f0, size_t n) {
+    std::vector<T> out(n * ch, T(0));
+    for (size_t f = 0; f < n; ++f)
+      for (size_t c = 0; c < ch; ++c)
+        if ((f0 + f) * ch + c < src.size()) out[f * ch + c] = src[(f0 + f) * ch + c];
+    return out;
+  };
+  if (n_new < n_old) {
+    const uint32_t m = (n_old - n_new) / 2;
+    *hist = frames(V, m, n_new - 1);
+    *magic = frames(V, static_cast<size_t>(m) + n_new - 1, static_cast<size_t>(m) + M);
+    *magic_frames = m + M;
+  } else {
+    const uint32_t olen = n_old + 2 * M;
+    std::vector<T> B(static_cast<size_t>(M) * ch, T(0));
+    B.insert(B.end(), V.begin(), V.begin() + static_cast<size_t>(n_old - 1 + M) * ch);
+    if (n_new > olen) {
+      hist->assign(static_cast<size_t>(n_new - olen) * ch, T(0));
+      hist->insert(hist->end(), B.begin(), B.end());
+      magic->clear();
+      *magic_frames = 0;
+      *last_sample += static_cast<int32_t>((n_new - olen) / 2);
+    } else {
+      const uint32_t m2 = (olen - n_new) / 2;
+      *hist = frames(B, m2, n_new - 1);
+      *magic = frames(B, static_cast<size_t>(m2) + n_new - 1, m2);
+      *magic_frames = m2;
+    }
+  }
+}
+}  // extern "C++"
+
 static int refilter(SpeexResamplerState *st, uint32_t ratio_num, uint32_t ratio_den, int quality) {
   spxb::FilterSpec next;
   if (int e = spxb::derive_filter_spec(ratio_num, ratio_den, quality, &next)) return e;
   const spxb::FilterSpec old = spxb::batch_spec(st->batch);
-  if (st->magic != 0 && next.taps != old.taps) {
-    spxb::set_error("changing the filter length again while magic samples are pending is not supported");
+  if (st->planar && st->started) {
+    spxb::set_error("changing the filter mid-stream on a state that has used the per-channel entries is not supported");
     return RESAMPLER_ERR_BAD_STATE;
   }
-  const bool shrink = st->started && next.taps < old.taps;
-  const uint32_t new_magic = shrink ? (old.taps - next.taps) / 2 : 0;  // resample.c:767
   const bool f32 = spxb_batch_is_f32(st->batch) != 0;
   int32_t last = 0;
   uint32_t frac = 0, magic = 0;
-  const size_t old_live = static_cast<size_t>(old.taps - 1) * st->channels;
-  const size_t new_live = static_cast<size_t>(next.taps - 1) * st->channels;
-  std::vector<float> hist_f(f32 ? old_live + 1 : 1), grown_f(f32 ? new_live + 1 : 1, 0.f);
-  std::vector<int16_t> hist_i(f32 ? 1 : old_live + 1), grown_i(f32 ? 1 : new_live + 1, 0);
+  const size_t ch = st->channels;
+  const size_t old_live = static_cast<size_t>(old.taps - 1) * ch;
+  std::vector<float> hist_f(f32 ? old_live + 1 : 1), new_hist_f, new_magic_f;
+  std::vector<int16_t> hist_i(f32 ? 1 : old_live + 1), new_hist_i, new_magic_i;
   int e = f32 ? spxb_batch_get_state_f32(st->batch, 0, &last, &frac, &magic, st->started ? hist_f.data() : nullptr)
               : spxb_batch_get_state(st->batch, 0, &last, &frac, &magic, st->started ? hist_i.data() : nullptr);
   if (e) return e;
+  uint32_t new_magic = st->magic;
+  const bool reshape = st->started && next.taps != old.taps;
   if (st->started) {
     // :1131-1140: samp_frac_num * den_new / den_old (it is < den_old, so the product fits 64 bits), clamped
     uint64_t scaled = static_cast<uint64_t>(frac) * next.den / old.den;
     if (frac != 0 && frac > 0xffffffffu / next.den) return RESAMPLER_ERR_OVERFLOW;  // multiply_frac's check
     if (scaled >= next.den) scaled = next.den - 1;
     frac = static_cast<uint32_t>(scaled);
-    if (!shrink) {
-      const size_t pad = new_live - old_live;  // >= 0: growth or same length
-      if (f32) std::copy(hist_f.begin(), hist_f.begin() + old_live, grown_f.begin() + pad);
-      else std::copy(hist_i.begin(), hist_i.begin() + old_live, grown_i.begin() + pad);
-      last += static_cast<int32_t>((next.taps - old.taps) / 2);  // :748
-    } else {
-      // :770-771 mem[j] = mem[j + magic] for j < filt_len - 1 + magic: the first filt_len - 1 are the
-      // new history, the next `magic` frames wait to be resampled before the next input
-      const size_t ch = st->channels, skip = static_cast<size_t>(new_magic) * ch;
-      if (f32) {
-        std::copy(hist_f.begin() + skip, hist_f.begin() + skip + new_live, grown_f.begin());
-        st->magic_f.assign(hist_f.begin() + skip + new_live, hist_f.begin() + skip + new_live + skip);
+    if (f32) {
+      hist_f.resize(old_live);
+      if (st->magic_f.empty() && !st->magic_i.empty()) st->magic_f.assign(st->magic_i.begin(), st->magic_i.end());
+      if (reshape) {
+        std::vector<float> V(hist_f);
+        V.insert(V.end(), st->magic_f.begin(), st->magic_f.begin() + static_cast<size_t>(st->magic) * ch);
+        reshape_memory<float>(V, ch, old.taps, next.taps, st->magic, &new_hist_f, &new_magic_f, &new_magic, &last);
       } else {
-        std::copy(hist_i.begin() + skip, hist_i.begin() + skip + new_live, grown_i.begin());
-        st->magic_i.assign(hist_i.begin() + skip + new_live, hist_i.begin() + skip + new_live + skip);
+        new_hist_f = hist_f;  // same length: only the table changes, pending frames stay pending
+        new_magic_f = st->magic_f;
+      }
+    } else {
+      hist_i.resize(old_live);
+      if (reshape) {
+        std::vector<int16_t> V(hist_i);
+        V.insert(V.end(), st->magic_i.begin(), st->magic_i.begin() + static_cast<size_t>(st->magic) * ch);
+        reshape_memory<int16_t>(V, ch, old.taps, next.taps, st->magic, &new_hist_i, &new_magic_i, &new_magic, &last);
+      } else {
+        new_hist_i = hist_i;
+        new_magic_i = st->magic_i;
       }
     }
   } else {
     frac = 0;
   }
+  new_hist_f.resize(static_cast<size_t>(next.taps - 1) * ch + 1);
+  new_hist_i.resize(static_cast<size_t>(next.taps - 1) * ch + 1);
   spxb_batch *nb = f32 ? spxb_batch_create_f32(1, st->channels, ratio_num, ratio_den, quality, 0, &e)
                        : spxb_batch_create(1, st->channels, ratio_num, ratio_den, quality, 0, &e);
   if (!nb) return e ? e : RESAMPLER_ERR_ALLOC_FAILED;
-  e = f32 ? spxb_batch_set_state_f32(nb, 0, last, frac, st->started ? grown_f.data() : nullptr)
-          : spxb_batch_set_state(nb, 0, last, frac, st->started ? grown_i.data() : nullptr);
+  e = f32 ? spxb_batch_set_state_f32(nb, 0, last, frac, st->started ? new_hist_f.data() : nullptr)
+          : spxb_batch_set_state(nb, 0, last, frac, st->started ? new_hist_i.data() : nullptr);
   if (e) {
     spxb_batch_destroy(nb);
     return e;
@@ -180,7 +241,15 @@ static int refilter(SpeexResamplerState *st, uint32_t ratio_num, uint32_t ratio_
   spxb_batch_set_kernel(nb, spxb::batch_kernel_pref(st->batch));
   spxb_batch_destroy(st->batch);
   st->batch = nb;
-  if (shrink) st->magic = new_magic;
+  if (st->started) {
+    st->magic = new_magic;
+    if (f32) {
+      st->magic_f = new_magic_f;
+      st->magic_i.clear();
+    } else {
+      st->magic_i = new_magic_i;
+    }
+  }
   st->mem_alloc = std::max(st->mem_alloc, next.taps - 1 + spxb::kInBlock);  // :709-719: never shrinks
   spxb::batch_set_in_block(nb, st->mem_alloc - (next.taps - 1));
   return RESAMPLER_ERR_SUCCESS;
@@ -220,6 +289,74 @@ static int process_with_magic(SpeexResamplerState *st, const T *in, uint32_t *in
   st->magic -= mp.magic_used;
   *in_len = mp.plan.consumed;
   *out_len = mp.plan.n_out;
+  return RESAMPLER_ERR_SUCCESS;
+}
+}  // extern "C++"
+
+// ---- per-channel entries (resample.c:925-1036) ------------------------------------------------
+// The interleaved batch keeps ONE position for all channels of the stream (they move together as
+// long as only the interleaved entries are used). The first per-channel call splits it: one mono
+// stream per channel, same history, same position, free to diverge from then on.
+static int to_planar(SpeexResamplerState *st, bool want_f32) {
+  const bool f32 = spxb_batch_is_f32(st->batch) != 0;
+  if (st->planar && (f32 || !want_f32)) return RESAMPLER_ERR_SUCCESS;
+  if (st->magic != 0) {
+    spxb::set_error("per-channel calls while magic samples are pending are not supported");
+    return RESAMPLER_ERR_BAD_STATE;
+  }
+  const spxb::FilterSpec s = spxb::batch_spec(st->batch);
+  const uint32_t ch = st->channels, live = s.taps - 1;
+  const uint32_t src_streams = st->planar ? ch : 1, src_ch = st->planar ? 1 : ch;
+  const bool to_f32 = f32 || want_f32;
+  int e = 0;
+  spxb_batch *nb = to_f32 ? spxb_batch_create_f32(ch, 1, st->ratio_num, st->ratio_den, st->quality, 0, &e)
+                          : spxb_batch_create(ch, 1, st->ratio_num, st->ratio_den, st->quality, 0, &e);
+  if (!nb) return e ? e : RESAMPLER_ERR_ALLOC_FAILED;
+  std::vector<float> hist(static_cast<size_t>(live) * src_ch + 1), mono(live + 1);
+  for (uint32_t src = 0; src < src_streams && !e; ++src) {
+    int32_t last = 0;
+    uint32_t frac = 0, magic = 0;
+    e = spxb_batch_get_state_f32(st->batch, src, &last, &frac, &magic, hist.data());
+    for (uint32_t c = 0; c < src_ch && !e; ++c) {
+      for (uint32_t j = 0; j < live; ++j) mono[j] = hist[static_cast<size_t>(j) * src_ch + c];
+      e = spxb_batch_set_state_f32(nb, st->planar ? src : c, last, frac, mono.data());
+    }
+  }
+  if (e) {
+    spxb_batch_destroy(nb);
+    return e;
+  }
+  spxb_batch_set_kernel(nb, SPXB_KERNEL_STRICT);
+  spxb::batch_set_in_block(nb, st->mem_alloc - live);
+  spxb::batch_set_planar_state(nb, true);
+  spxb_batch_destroy(st->batch);
+  st->batch = nb;
+  st->planar = true;
+  return RESAMPLER_ERR_SUCCESS;
+}
+
+extern "C++" {
+// one call on a planar state: channel `only` alone (per-channel entries) or, with only == ~0u, every
+// channel of an interleaved buffer (step nb_channels, channel c starting at element c)
+template <typename T>
+static int planar_call(SpeexResamplerState *st, uint32_t only, const T *in, uint32_t *in_len, T *out, uint32_t *out_len,
+                       uint32_t in_step, uint32_t out_step, bool float_io) {
+  const uint32_t ch = st->channels;
+  st->lens_in.assign(ch, 0u);
+  st->lens_out.assign(ch, 0u);
+  for (uint32_t c = 0; c < ch; ++c)
+    if (only == ~0u || c == only) {
+      st->lens_in[c] = *in_len;
+      st->lens_out[c] = *out_len;
+    }
+  // stream c starts at element c of an interleaved buffer; a per-channel call passes its own pointer
+  const size_t stream_stride = only == ~0u ? 1 : 0;
+  const int e = spxb_batch_process_strided(st->batch, in, stream_stride, in_step, st->lens_in.data(), out, stream_stride,
+                                           out_step, st->lens_out.data(), float_io ? 1 : 0);
+  if (e) return e;
+  const uint32_t rep = only == ~0u ? ch - 1 : only;  // the interleaved entries report the last channel's lengths
+  *in_len = st->lens_in[rep];
+  *out_len = st->lens_out[rep];
   return RESAMPLER_ERR_SUCCESS;
 }
 }  // extern "C++"
@@ -279,6 +416,8 @@ int speex_resampler_process_interleaved_int(SpeexResamplerState *st, const int16
     in = st->silence.data();
   }
   st->started = true;
+  if (st->planar)  // every channel of the interleaved buffers, each from its own position (resample.c:1066-1078)
+    return planar_call<int16_t>(st, ~0u, in, in_len, out, out_len, st->channels, st->channels, false);
   if (st->magic != 0) {
     if (spxb_batch_is_f32(st->batch)) {
       spxb::set_error("int16 call on a float-history state with magic samples pending is not supported");
@@ -301,6 +440,15 @@ int speex_resampler_process_interleaved_float(SpeexResamplerState *st, const flo
     return RESAMPLER_ERR_SUCCESS;
   }
   if (!out) return RESAMPLER_ERR_INVALID_ARG;
+  if (st->planar) {
+    if (int e = to_planar(st, true)) return e;
+    if (!in) {
+      st->fsilence.assign(static_cast<size_t>(*in_len) * st->channels, 0.f);
+      in = st->fsilence.data();
+    }
+    st->started = true;
+    return planar_call<float>(st, ~0u, in, in_len, out, out_len, st->channels, st->channels, true);
+  }
   if (!spxb_batch_is_f32(st->batch)) {
     // first float call: the state moves to a float-history batch (int16 history converts exactly)
     int e = 0;
@@ -337,6 +485,51 @@ int speex_resampler_process_interleaved_float(SpeexResamplerState *st, const flo
   }
   return spxb_batch_process_f32(st->batch, in, *in_len, in_len, out, *out_len, out_len);
 }
+
+int speex_resampler_process_int(SpeexResamplerState *st, uint32_t channel_index, const int16_t *in, uint32_t *in_len,
+                                int16_t *out, uint32_t *out_len) {
+  if (!st || !in_len || !out_len || channel_index >= st->channels) return RESAMPLER_ERR_INVALID_ARG;
+  if (*in_len == 0 || *out_len == 0) {  // resample.c:988: the loop does not run
+    *in_len = 0;
+    *out_len = 0;
+    return RESAMPLER_ERR_SUCCESS;
+  }
+  if (!out) return RESAMPLER_ERR_INVALID_ARG;
+  if (int e = to_planar(st, false)) return e;
+  uint32_t in_step = st->in_stride;
+  if (!in) {  // resample.c:1007-1010: zeros instead of input
+    st->silence.assign(*in_len, 0);
+    in = st->silence.data();
+    in_step = 1;
+  }
+  st->started = true;
+  return planar_call<int16_t>(st, channel_index, in, in_len, out, out_len, in_step, st->out_stride, false);
+}
+
+int speex_resampler_process_float(SpeexResamplerState *st, uint32_t channel_index, const float *in, uint32_t *in_len,
+                                  float *out, uint32_t *out_len) {
+  if (!st || !in_len || !out_len || channel_index >= st->channels) return RESAMPLER_ERR_INVALID_ARG;
+  if (*in_len == 0 || *out_len == 0) {  // resample.c:939
+    *in_len = 0;
+    *out_len = 0;
+    return RESAMPLER_ERR_SUCCESS;
+  }
+  if (!out) return RESAMPLER_ERR_INVALID_ARG;
+  if (int e = to_planar(st, true)) return e;
+  uint32_t in_step = st->in_stride;
+  if (!in) {
+    st->fsilence.assign(*in_len, 0.f);
+    in = st->fsilence.data();
+    in_step = 1;
+  }
+  st->started = true;
+  return planar_call<float>(st, channel_index, in, in_len, out, out_len, in_step, st->out_stride, true);
+}
+
+void speex_resampler_set_input_stride(SpeexResamplerState *st, uint32_t stride) { st->in_stride = stride; }
+void speex_resampler_get_input_stride(SpeexResamplerState *st, uint32_t *stride) { *stride = st->in_stride; }
+void speex_resampler_set_output_stride(SpeexResamplerState *st, uint32_t stride) { st->out_stride = stride; }
+void speex_resampler_get_output_stride(SpeexResamplerState *st, uint32_t *stride) { *stride = st->out_stride; }
 
 spxb_batch *spxb_resampler_batch(SpeexResamplerState *st) { return st ? st->batch : nullptr; }
 

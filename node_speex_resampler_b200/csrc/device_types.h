@@ -72,6 +72,11 @@ struct CallArgs {
   // that share one position on the tensor kernel, and the remainder on the strict kernel.
   const uint32_t *ids;
   uint32_t n_ids;
+  // Element distance between consecutive frames of a series in `in` / `out` (strict kernel only;
+  // the fast kernels take channels-interleaved rows, i.e. step == channels). The per-channel
+  // entries of the Speex API (resample.c:925-1036 with st->in_stride / st->out_stride) read and
+  // write one channel at the caller's stride. Counted in samples of the call's format.
+  uint32_t in_step, out_step;
 };
 
 }  // namespace spxb

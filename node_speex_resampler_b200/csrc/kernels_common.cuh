@@ -25,7 +25,7 @@ __device__ __forceinline__ int fetch_sample(const CallArgs &a, uint32_t s, int f
     return a.hist_src[static_cast<size_t>(s) * a.hist_stride + static_cast<size_t>(hf) * a.channels + c];
   }
   if (static_cast<uint32_t>(f) >= n_in) return 0;
-  return a.in[static_cast<size_t>(s) * a.in_stride + static_cast<size_t>(f) * a.channels + c];
+  return a.in[static_cast<size_t>(s) * a.in_stride + static_cast<size_t>(f) * a.in_step + c];
 }
 
 // Format-generic variants (CallArgs::fmt): the sample as the f32 the reference holds in `mem`
@@ -40,7 +40,7 @@ __device__ __forceinline__ float fetch_sample_f(const CallArgs &a, uint32_t s, i
     return h[static_cast<size_t>(hf) * a.channels + c];
   }
   if (static_cast<uint32_t>(f) >= n_in) return 0.f;
-  const size_t e = static_cast<size_t>(f) * a.channels + c;
+  const size_t e = static_cast<size_t>(f) * a.in_step + c;
   if (FMT == 2) return reinterpret_cast<const float *>(a.in + static_cast<size_t>(s) * a.in_stride)[e];
   return static_cast<float>(a.in[static_cast<size_t>(s) * a.in_stride + e]);
 }
@@ -107,10 +107,12 @@ __device__ __forceinline__ void slide_history_elem(const CallArgs &a, uint32_t s
   const uint32_t hist_elems = a.hist_frames * a.channels;
   const size_t src = static_cast<size_t>(sc.consumed) * a.channels + e;
   int16_t v;
-  if (src < hist_elems)
+  if (src < hist_elems) {
     v = a.hist_src[static_cast<size_t>(s) * a.hist_stride + src];
-  else
-    v = a.in[static_cast<size_t>(s) * a.in_stride + (src - hist_elems)];
+  } else {
+    const size_t i = src - hist_elems;  // element of the call's input, frames channels apart unless strided
+    v = a.in[static_cast<size_t>(s) * a.in_stride + (i / a.channels) * a.in_step + i % a.channels];
+  }
   a.hist_dst[static_cast<size_t>(s) * a.hist_stride + e] = v;
 }
 
@@ -123,12 +125,14 @@ __device__ __forceinline__ void slide_history_elem_f(const CallArgs &a, uint32_t
   const uint32_t hist_elems = a.hist_frames * a.channels;
   const size_t src = static_cast<size_t>(sc.consumed) * a.channels + e;
   float v;
+  const size_t i = src < hist_elems ? 0 : src - hist_elems;
+  const size_t ie = (i / a.channels) * a.in_step + i % a.channels;  // frames in_step apart (== channels unless strided)
   if (src < hist_elems)
     v = reinterpret_cast<const float *>(a.hist_src + static_cast<size_t>(s) * a.hist_stride)[src];
   else if (FMT == 2)
-    v = reinterpret_cast<const float *>(a.in + static_cast<size_t>(s) * a.in_stride)[src - hist_elems];
+    v = reinterpret_cast<const float *>(a.in + static_cast<size_t>(s) * a.in_stride)[ie];
   else
-    v = static_cast<float>(a.in[static_cast<size_t>(s) * a.in_stride + (src - hist_elems)]);
+    v = static_cast<float>(a.in[static_cast<size_t>(s) * a.in_stride + ie]);
   reinterpret_cast<float *>(a.hist_dst + static_cast<size_t>(s) * a.hist_stride)[e] = v;
 }
 

@@ -150,10 +150,11 @@ __global__ void __launch_bounds__(kStrictThreads)
     const int q = window_start(a.filt, sc, m, &phase);
     y = strict_output<kDirect, kWide>(a.filt, phase, [&](int j) { return fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in); });
   }
+  const size_t oe = static_cast<size_t>(m) * a.out_step + c;  // == e unless the call is strided
   if (FMT == 2)  // the float entry stores the kernel's result as is (resample.c:927-963)
-    reinterpret_cast<float *>(a.out + static_cast<size_t>(s) * a.out_stride)[e] = y;
+    reinterpret_cast<float *>(a.out + static_cast<size_t>(s) * a.out_stride)[oe] = y;
   else
-    a.out[static_cast<size_t>(s) * a.out_stride + e] = word2int_exact(y);
+    a.out[static_cast<size_t>(s) * a.out_stride + oe] = word2int_exact(y);
 }
 
 }  // namespace

@@ -814,9 +814,19 @@ def test_c_api_mid_stream_rate_and_quality_changes_match_the_reference(ch):
     change("speex_resampler_set_quality", 1)
     both(300, 600)
     both(441, 600)
-    assert L.speex_resampler_set_quality(ours, 0) == 0 and R.speex_resampler_set_quality(ref, 0) == 0
-    assert L.speex_resampler_set_quality(ours, 4) == 2   # a second length change with magic pending: refused
-    assert "magic samples" in _lib.last_error()
+    # further length changes while magic samples are still pending (resample.c:727-776 with
+    # magic_samples != 0): shorter again, then longer -- first below, then above the "augmented" length
+    change("speex_resampler_set_quality", 0)
+    change("speex_resampler_set_quality", 4)
+    both(50, 3)
+    both(441, 600)
+    change("speex_resampler_set_quality", 10)
+    both(300, 40)
+    change("speex_resampler_set_quality", 3)              # shorter with magic pending: the magic regions add up
+    both(10, 2)
+    change("speex_resampler_set_quality", 1)
+    both(200, 600)
+    both(441, 600)
     L.speex_resampler_destroy(ours)
     R.speex_resampler_destroy(ref)
 
@@ -1018,3 +1028,77 @@ def test_persistent_kernel_parity(shape):
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "resident ok" in r.stdout and "'stages'" in r.stdout
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not present")
+def test_c_api_per_channel_entries_and_strides_match_the_reference():
+    """speex_resampler_process_int / _process_float on single channels with input / output strides
+    (resample.c:925-1036, :1170-1188), mixed with the interleaved entries on the same state, call for
+    call against the reference's own build: lengths, every written sample bit for bit, and the samples
+    BETWEEN the strided ones untouched. Channels are advanced by different amounts, so their positions
+    diverge -- the reference keeps last_sample / samp_frac_num / mem per channel."""
+    L, R = lib(), O._load_ref()
+    for fn in ("speex_resampler_process_int", "speex_resampler_process_float"):
+        getattr(R, fn).restype = C.c_int
+        getattr(R, fn).argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p,
+                                   C.POINTER(C.c_uint32)]
+    for fn in ("speex_resampler_set_input_stride", "speex_resampler_set_output_stride"):
+        getattr(R, fn).argtypes = [C.c_void_p, C.c_uint32]
+    R.speex_resampler_get_input_stride.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+    ch, i, o, q = 3, 44100, 48000, 5
+    err = C.c_int(0)
+    ours = L.speex_resampler_init(ch, i, o, q, C.byref(err))
+    ref = R.speex_resampler_init(ch, i, o, q, C.byref(err))
+    x = synth_pcm(1, ch, 9000, i, seed=4242)[0]
+    pos = [0]
+
+    def interleaved(n, cap, kind="i"):
+        dt = np.int16 if kind == "i" else np.float32
+        chunk = np.ascontiguousarray(x[pos[0] * ch:(pos[0] + n) * ch].astype(dt))
+        pos[0] += n
+        res = []
+        for lib_, st in ((L, ours), (R, ref)):
+            out = np.full(cap * ch + 5, 77, dt)
+            n_in, n_out = C.c_uint32(n), C.c_uint32(cap)
+            fn = lib_.speex_resampler_process_interleaved_int if kind == "i" else lib_.speex_resampler_process_interleaved_float
+            assert fn(st, chunk.ctypes.data, C.byref(n_in), out.ctypes.data, C.byref(n_out)) == 0, _lib.last_error()
+            res.append((n_in.value, n_out.value, out.copy()))
+        assert res[0][:2] == res[1][:2], ("interleaved", pos[0], res[0][:2], res[1][:2])
+        assert np.array_equal(res[0][2].view(np.uint8), res[1][2].view(np.uint8)), ("interleaved", pos[0])
+
+    def channel(c, n, cap, istride, ostride, kind="i", null_in=False):
+        dt = np.int16 if kind == "i" else np.float32
+        src = np.full(n * istride + 3, -5, dt)
+        src[: n * istride: istride] = x[(pos[0] * ch + c): (pos[0] + n) * ch: ch].astype(dt)
+        res = []
+        for lib_, st in ((L, ours), (R, ref)):
+            lib_.speex_resampler_set_input_stride(st, istride)
+            lib_.speex_resampler_set_output_stride(st, ostride)
+            out = np.full(cap * ostride + 7, 99, dt)
+            n_in, n_out = C.c_uint32(n), C.c_uint32(cap)
+            fn = lib_.speex_resampler_process_int if kind == "i" else lib_.speex_resampler_process_float
+            assert fn(st, c, None if null_in else src.ctypes.data, C.byref(n_in), out.ctypes.data, C.byref(n_out)) == 0, \
+                _lib.last_error()
+            res.append((n_in.value, n_out.value, out.copy()))
+        assert res[0][:2] == res[1][:2], ("channel", c, pos[0], res[0][:2], res[1][:2])
+        # written samples equal, everything between and after them still holds the fill value
+        assert np.array_equal(res[0][2].view(np.uint8), res[1][2].view(np.uint8)), ("channel", c, pos[0])
+        return res[0][0]
+
+    interleaved(441, 600)
+    interleaved(300, 100)                      # capacity binds
+    s = C.c_uint32(0)
+    L.speex_resampler_get_input_stride(ours, C.byref(s))
+    assert s.value == 1                        # resample.c:836: strides start at 1
+    used = [channel(c, 200 + 30 * c, 600, 1 + c, 3 - c) for c in range(ch)]   # channels advance differently
+    assert used == [200, 230, 260]
+    channel(1, 100, 7, 2, 2)                   # capacity binds on one channel only
+    channel(0, 50, 600, 1, 1, null_in=True)    # in == NULL: zeros (resample.c:1007-1010)
+    interleaved(441, 600)                      # interleaved entry on the planar state: channels keep their own positions
+    channel(2, 160, 600, 4, 1, kind="f")       # float per-channel entry (the state turns float)
+    interleaved(333, 600, kind="f")
+    interleaved(200, 30)
+    L.speex_resampler_get_input_stride(ours, C.byref(s))
+    assert s.value == 4                        # the interleaved entries restore the caller's strides (resample.c:1080)
+    L.speex_resampler_destroy(ours)
+    R.speex_resampler_destroy(ref)
