@@ -184,6 +184,14 @@ SPXB_API int spxb_batch_process_f32(spxb_batch *b, const float *in, size_t in_st
                                     uint32_t *in_frames, float *out, size_t out_stride_frames,
                                     uint32_t *out_frames);
 
+/* Scaled float PCM (+-1.0 full scale) in and out on an int16 batch: converted to int16 as the
+ * kernel loads it (round to nearest even of x*32768, saturated) and back as it stores; history,
+ * arithmetic and lengths are the int16 path's. Strict kernel, bit-exact against the oracle fed the
+ * converted samples. */
+SPXB_API int spxb_batch_process_pcm_f32(spxb_batch *b, const float *in, size_t in_stride_frames,
+                                        uint32_t *in_frames, float *out, size_t out_stride_frames,
+                                        uint32_t *out_frames);
+
 /* Strided call, all streams of the batch (backs the per-channel Speex entries): stream s reads
  * sample f of its channel c at in[s*in_stream_stride + f*in_step + c] and writes
  * out[s*out_stream_stride + m*out_step + c]; strides and steps count samples of the call's format

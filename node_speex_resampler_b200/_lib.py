@@ -31,7 +31,7 @@ DECLARED_SYMBOLS = (
     "speex_resampler_process_interleaved_float", "spxb_batch_create_f32", "spxb_batch_is_f32",
     "spxb_batch_process_f32", "spxb_batch_get_state_f32", "spxb_batch_set_state_f32", "spxb_plan_call_f32", "spxb_plan_call_ex",
     "spxb_measure_fp32_peak", "spxb_tensor_packed_plan", "spxb_tensor_tap_tile_packed",
-    "spxb_batch_process_strided", "speex_resampler_process_int", "speex_resampler_process_float",
+    "spxb_batch_process_strided", "spxb_batch_process_pcm_f32", "speex_resampler_process_int", "speex_resampler_process_float",
     "speex_resampler_set_input_stride", "speex_resampler_get_input_stride",
     "speex_resampler_set_output_stride", "speex_resampler_get_output_stride",
 )
@@ -117,6 +117,7 @@ def _bind(L):
     L.spxb_tensor_packed_plan.argtypes = [u32, u32, C.c_int, u32, vp, sz, pu32]
     L.spxb_tensor_tap_tile_packed.restype = C.c_long
     L.spxb_tensor_tap_tile_packed.argtypes = [u32, u32, C.c_int, u32, u32, u32, vp, sz]
+    L.spxb_batch_process_pcm_f32.argtypes = [vp, vp, sz, vp, vp, sz, vp]
     L.spxb_batch_process_strided.argtypes = [vp, vp, sz, u32, vp, vp, sz, u32, vp, C.c_int]
     L.speex_resampler_process_int.argtypes = [vp, u32, vp, pu32, vp, pu32]
     L.speex_resampler_process_float.argtypes = [vp, u32, vp, pu32, vp, pu32]

@@ -102,6 +102,7 @@ struct spxb_batch {
   // the streams of this batch are the CHANNELS of one Speex state that has used the per-channel
   // entries (capi.cu): reset_mem reproduces the reference's channel-major layout quirk across them
   bool planar_state = false;
+  bool pcm_float = false;  // the call being issued takes / returns scaled float PCM (CallArgs::fmt 3)
   // filter bank in HBM
   float *d_table = nullptr, *d_taps = nullptr, *d_blend = nullptr, *d_band = nullptr;
   uint32_t band_kp = 0, band_pad = 0, band_row = 0;
@@ -161,7 +162,8 @@ struct DeviceGuard {
 
 static CallPlan plan_memo(spxb_batch *b, StreamPos p, uint32_t n_in, uint32_t cap) {
   // the float entry has no 1024-sample output block (resample.c:944)
-  const uint32_t out_block = b->io_words == 2 ? kOutBlockUnbounded : kOutBlock;
+  // (scaled float PCM is the int16 path behind a format conversion: it keeps the int16 walk)
+  const uint32_t out_block = b->io_words == 2 && !b->pcm_float ? kOutBlockUnbounded : kOutBlock;
   if (b->memo_valid && b->memo_pos.last_sample == p.last_sample &&
       b->memo_pos.samp_frac_num == p.samp_frac_num && b->memo_n_in == n_in &&
       b->memo_cap == cap && b->memo_out_block == out_block)
@@ -284,7 +286,7 @@ static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elem
   a.per_stream = d_calls;
   a.uniform = uniform;
   a.max_n_out = max_n_out;
-  a.fmt = !b->f32 ? 0u : (b->io_words == 2 ? 2u : 1u);
+  a.fmt = b->pcm_float ? 3u : !b->f32 ? 0u : (b->io_words == 2 ? 2u : 1u);
   a.ids = nullptr;
   a.n_ids = 0;
   a.in_step = b->in_step ? b->in_step : b->channels;
@@ -299,8 +301,8 @@ static int launch_call(spxb_batch *b, const int16_t *d_in, size_t in_stride_elem
   // float batches run the strict kernel only (the fast families are built around int16 history)
   // float batches and strided calls run the strict kernel only (the fast families are built around
   // int16 history and channels-interleaved rows)
-  const bool want_tensor = !b->f32 && !strided && (pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TENSOR);
-  const bool want_tiled = !b->f32 && !strided && (pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TILED);
+  const bool want_tensor = !b->f32 && !b->pcm_float && !strided && (pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TENSOR);
+  const bool want_tiled = !b->f32 && !b->pcm_float && !strided && (pref == SPXB_KERNEL_AUTO || pref == SPXB_KERNEL_TILED);
   bool grouped = false;
   if (want_tensor && d_calls && rh.calls && max_n_out != 0 && b->umma && !b->dry_run) {
     // ragged batch: groups of streams that share one position run on the tensor kernel
@@ -932,6 +934,29 @@ int spxb_batch_process_f32(spxb_batch *b, const float *in, size_t in_stride_fram
   int e = submit_host(b, reinterpret_cast<const int16_t *>(in), in_stride_frames, in_frames,
                       reinterpret_cast<int16_t *>(out), out_stride_frames, out_frames, &t);
   b->io_words = 1;
+  if (e) return e;
+  return spxb_batch_wait(b, t);
+}
+
+// Scaled float PCM in and out (+-1.0 full scale) on an int16 batch: samples are converted to int16 as
+// the kernel loads them (round to nearest even of x * 32768, saturated) and back as it stores them;
+// history, arithmetic and lengths are the int16 path's. Fused into the strict kernel (bit-exact
+// against the oracle fed the converted samples); the step in front of / behind the resampler in
+// float pipelines.
+int spxb_batch_process_pcm_f32(spxb_batch *b, const float *in, size_t in_stride_frames, uint32_t *in_frames,
+                               float *out, size_t out_stride_frames, uint32_t *out_frames) {
+  if (!b) return RESAMPLER_ERR_INVALID_ARG;
+  if (b->f32) {
+    set_error("spxb_batch_process_pcm_f32 takes an int16 batch (spxb_batch_create)");
+    return RESAMPLER_ERR_BAD_STATE;
+  }
+  b->io_words = 2;
+  b->pcm_float = true;
+  uint64_t t = 0;
+  int e = submit_host(b, reinterpret_cast<const int16_t *>(in), in_stride_frames, in_frames,
+                      reinterpret_cast<int16_t *>(out), out_stride_frames, out_frames, &t);
+  b->io_words = 1;
+  b->pcm_float = false;
   if (e) return e;
   return spxb_batch_wait(b, t);
 }

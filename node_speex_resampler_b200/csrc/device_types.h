@@ -66,6 +66,8 @@ struct CallArgs {
   //   0  int16 history, int16 in/out                 (the hot path)
   //   1  float history, int16 in/out                 (a state that has seen float calls)
   //   2  float history, float in/out, no rounding    (speex_resampler_process_interleaved_float)
+  //   3  int16 history, SCALED float in/out          (float PCM, +-1.0 full scale: converted to the
+  //      int16 sample on load and back on store, the int16 path in between -- spxb_batch_process_pcm_f32)
   uint32_t fmt;
   // Optional subset: when ids != nullptr the launch covers streams ids[0 .. n_ids) only (device
   // array), in that order, instead of 0 .. n_streams. Used to run the groups of a ragged batch

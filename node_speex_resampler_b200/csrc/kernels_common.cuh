@@ -28,11 +28,23 @@ __device__ __forceinline__ int fetch_sample(const CallArgs &a, uint32_t s, int f
   return a.in[static_cast<size_t>(s) * a.in_stride + static_cast<size_t>(f) * a.in_step + c];
 }
 
+// scaled float PCM ([-1, 1) full scale) -> the int16 sample the path computes with: round to nearest
+// even of x * 32768, saturated (CallArgs::fmt == 3)
+__device__ __forceinline__ int16_t pcm16_from_float(float x) {
+  return static_cast<int16_t>(max(-32768, min(32767, __float2int_rn(__fmul_rn(x, 32768.f)))));
+}
+
 // Format-generic variants (CallArgs::fmt): the sample as the f32 the reference holds in `mem`
 // (resample.c:1005 converts int16 input exactly; the float entry stores its input as is).
 template <int FMT>
 __device__ __forceinline__ float fetch_sample_f(const CallArgs &a, uint32_t s, int f, uint32_t c, uint32_t n_in) {
   if (FMT == 0) return static_cast<float>(fetch_sample(a, s, f, c, n_in));
+  if (FMT == 3) {  // int16 history, scaled float in/out
+    if (f < 0) return static_cast<float>(fetch_sample(a, s, f, c, n_in));
+    if (static_cast<uint32_t>(f) >= n_in) return 0.f;
+    const float x = reinterpret_cast<const float *>(a.in + static_cast<size_t>(s) * a.in_stride)[static_cast<size_t>(f) * a.in_step + c];
+    return static_cast<float>(pcm16_from_float(x));
+  }
   if (f < 0) {
     const int hf = f + static_cast<int>(a.hist_frames);
     if (hf < 0) return 0.f;
@@ -120,6 +132,19 @@ template <int FMT>
 __device__ __forceinline__ void slide_history_elem_f(const CallArgs &a, uint32_t s, const StreamCall &sc, uint32_t e) {
   if (FMT == 0) {
     slide_history_elem(a, s, sc, e);
+    return;
+  }
+  if (FMT == 3) {  // int16 history fed from scaled float input
+    const uint32_t he = a.hist_frames * a.channels;
+    const size_t from = static_cast<size_t>(sc.consumed) * a.channels + e;
+    int16_t v;
+    if (from < he) {
+      v = a.hist_src[static_cast<size_t>(s) * a.hist_stride + from];
+    } else {
+      const size_t i = from - he;
+      v = pcm16_from_float(reinterpret_cast<const float *>(a.in + static_cast<size_t>(s) * a.in_stride)[(i / a.channels) * a.in_step + i % a.channels]);
+    }
+    a.hist_dst[static_cast<size_t>(s) * a.hist_stride + e] = v;
     return;
   }
   const uint32_t hist_elems = a.hist_frames * a.channels;

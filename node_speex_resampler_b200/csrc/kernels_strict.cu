@@ -153,6 +153,8 @@ __global__ void __launch_bounds__(kStrictThreads)
   const size_t oe = static_cast<size_t>(m) * a.out_step + c;  // == e unless the call is strided
   if (FMT == 2)  // the float entry stores the kernel's result as is (resample.c:927-963)
     reinterpret_cast<float *>(a.out + static_cast<size_t>(s) * a.out_stride)[oe] = y;
+  else if (FMT == 3)  // scaled float PCM out: the int16 result (WORD2INT, exact) over full scale
+    reinterpret_cast<float *>(a.out + static_cast<size_t>(s) * a.out_stride)[oe] = static_cast<float>(word2int_exact(y)) * (1.f / 32768.f);
   else
     a.out[static_cast<size_t>(s) * a.out_stride + oe] = word2int_exact(y);
 }
@@ -195,7 +197,8 @@ cudaError_t launch_strict(const CallArgs &a, cudaStream_t stream, uint32_t *laun
       else go(strict_fir_kernel<false, false, F, true>, strict_fir_kernel<false, false, F, false>);
     }
   };
-  if (a.fmt == 2) by_filter(std::integral_constant<int, 2>{});
+  if (a.fmt == 3) by_filter(std::integral_constant<int, 3>{});
+  else if (a.fmt == 2) by_filter(std::integral_constant<int, 2>{});
   else if (a.fmt == 1) by_filter(std::integral_constant<int, 1>{});
   else by_filter(std::integral_constant<int, 0>{});
   if (launches) *launches += 1;

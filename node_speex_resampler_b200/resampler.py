@@ -328,6 +328,22 @@ class StreamBatch:
             raise RuntimeError(_lib.strerror(e) + ": " + _lib.last_error())
         return out, nin, nout
 
+    def process_pcm_f32(self, pcm: np.ndarray, in_frames, out_cap):
+        """Scaled float PCM (+-1.0 full scale) in and out on an int16 batch: converted to int16 on load
+        and back on store inside the kernel. Shapes and results like process()."""
+        L = _lib.lib()
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32).reshape(self.n_streams, -1)
+        in_stride = pcm.shape[1] // self.channels
+        nin = np.ascontiguousarray(np.broadcast_to(np.asarray(in_frames, dtype=np.uint32), (self.n_streams,))).copy()
+        nout = np.ascontiguousarray(np.broadcast_to(np.asarray(out_cap, dtype=np.uint32), (self.n_streams,))).copy()
+        out_stride = max(int(nout.max()), 1)
+        out = np.zeros((self.n_streams, out_stride * self.channels), dtype=np.float32)
+        e = L.spxb_batch_process_pcm_f32(self._h, pcm.ctypes.data, in_stride, nin.ctypes.data,
+                                         out.ctypes.data, out_stride, nout.ctypes.data)
+        if e:
+            raise RuntimeError(_lib.strerror(e) + ": " + _lib.last_error())
+        return out, nin, nout
+
     def processChunks(self, chunks: Sequence) -> List[bytes]:
         """One processChunk per stream (the capacity rule of index.ts:80-95 per stream)."""
         if len(chunks) != self.n_streams:

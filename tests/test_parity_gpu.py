@@ -1102,3 +1102,104 @@ def test_c_api_per_channel_entries_and_strides_match_the_reference():
     assert s.value == 4                        # the interleaved entries restore the caller's strides (resample.c:1080)
     L.speex_resampler_destroy(ours)
     R.speex_resampler_destroy(ref)
+
+
+# ---------------------------------------------------------------------------
+# formats either side of the path, on the device
+# ---------------------------------------------------------------------------
+def test_scaled_float_pcm_is_converted_inside_the_kernel():
+    """float PCM (+-1.0 full scale) in and out of an int16 batch: converted on load / store inside the
+    strict kernel. Must equal, bit for bit, the oracle fed the converted int16 samples, scaled back;
+    saturating inputs (|x| >= 1) and values between two int16 steps included."""
+    S, ch, i, o, q, n = 37, 2, 44100, 48000, 7, 882
+    cap = 962
+    b = StreamBatch(S, ch, i, o, q)
+    refs = [O.OracleResampler(ch, i, o, q) for _ in range(S)]
+    rng = np.random.default_rng(12)
+    for k in range(3):
+        pcm = synth_pcm(S, ch, n, i, seed=0xF10A, start_frame=k * n)
+        x = pcm.astype(np.float32) / np.float32(32768.0)
+        x += rng.uniform(-0.49, 0.49, size=x.shape).astype(np.float32) / np.float32(32768.0)  # off the int16 grid
+        x[3, :40] = 1.5       # saturates high
+        x[4, :40] = -1.25     # saturates low
+        want_in = np.clip(np.rint(x.astype(np.float32) * np.float32(32768.0)), -32768, 32767).astype(np.int16)
+        out, used, made = b.process_pcm_f32(x, n, cap)
+        assert b.last_kernel() == KERNEL_STRICT
+        for s in range(S):
+            y, u, m = refs[s].process(want_in[s], cap)
+            assert (u, m) == (int(used[s]), int(made[s]))
+            assert np.array_equal(out[s, : m * ch], y.astype(np.float32) / np.float32(32768.0)), (k, s)
+    # the same batch keeps serving int16 calls from the same state
+    pcm = synth_pcm(S, ch, n, i, seed=0xF10A, start_frame=3 * n)
+    out, used, made = b.process(pcm, n, cap)
+    y, u, m = refs[5].process(pcm[5], cap)
+    assert np.abs(out[5, : m * ch].astype(np.int32) - y.astype(np.int32)).max() <= 1
+    b.close()
+
+
+def test_planar_layout_is_a_mono_batch_on_the_tensor_kernel():
+    """planar PCM ([stream][channel][frame]) needs no kernel of its own: channel c of stream s is
+    series s*channels + c of a MONO batch, and the tensor kernel's rows are series anyway. Against
+    the oracle run on the interleaved form of the same audio, channel by channel."""
+    S, ch, i, o, q, n = 48, 2, 44100, 48000, 7, 882
+    cap = 962
+    planar = StreamBatch(S * ch, 1, i, o, q)
+    planar.set_kernel(KERNEL_TENSOR)
+    refs = [O.OracleResampler(ch, i, o, q) for _ in range(S)]
+    for k in range(3):
+        inter = synth_pcm(S, ch, n, i, seed=0x91A, start_frame=k * n)                 # [S, n*ch] interleaved
+        rows = np.ascontiguousarray(inter.reshape(S, n, ch).transpose(0, 2, 1)).reshape(S * ch, n)  # [S*ch, n] planar
+        out, used, made = planar.process(rows, n, cap)
+        assert planar.last_kernel() == KERNEL_TENSOR
+        for s in (0, 7, S - 1):
+            y, u, m = refs[s].process(inter[s], cap)
+            for c in range(ch):
+                got = out[s * ch + c, :m]
+                assert (u, m) == (int(used[s * ch + c]), int(made[s * ch + c]))
+                d = np.abs(got.astype(np.int32) - y.reshape(m, ch)[:, c].astype(np.int32))
+                assert d.max() <= 1 and O.snr_db(y.reshape(m, ch)[:, c], got) >= 90.0
+    planar.close()
+
+
+@pytest.mark.skipif(O.fixture_path("44100hz_test.pcm") is None, reason="oracle/_ref/resources absent")
+@pytest.mark.parametrize("kernel", [KERNEL_TENSOR, KERNEL_STRICT], ids=["tensor", "strict"])
+def test_wav_payload_is_read_in_place_past_the_riff_header(kernel):
+    """The reference's fixtures are RIFF/WAVE files; formats.wav_pcm finds the payload 44 bytes in.
+    The kernels read it IN PLACE -- device-visible rows that start 44 bytes into a buffer are only
+    4-byte aligned, which takes the tensor kernel's unaligned load path -- 20 ms hop after hop."""
+    from node_speex_resampler_b200 import wav_pcm
+    L = lib()
+    blob = open(O.fixture_path("44100hz_test.pcm"), "rb").read()
+    w = wav_pcm(blob)
+    off = len(blob) - len(w.data)
+    assert off == 44 and (w.channels, w.sample_rate) == (2, 44100)
+    ch, i, o, q, n, cap = 2, 44100, 48000, 7, 882, 960
+    hops = 40
+    host = L.spxb_host_alloc(len(blob))           # pinned, device-visible under UVA: the kernel reads it over PCIe
+    C.memmove(host, blob, len(blob))
+    hout = L.spxb_host_alloc(hops * cap * ch * 2)
+    b = StreamBatch(1, ch, i, o, q)
+    b.set_kernel(kernel)
+    ref = O.OracleResampler(ch, i, o, q)
+    payload = np.frombuffer(w.data, np.int16)
+    wants, gots = [], []
+    for k in range(hops):
+        nin, nout = np.array([n], np.uint32), np.array([cap], np.uint32)
+        e = L.spxb_batch_process_device(b._h, C.c_void_p(host + off + k * n * ch * 2), n, nin.ctypes.data,
+                                        C.c_void_p(hout + k * cap * ch * 2), cap, nout.ctypes.data)
+        assert e == 0, _lib.last_error()
+        b.synchronize()
+        y, u, m = ref.process(payload[k * n * ch:(k + 1) * n * ch], cap)
+        assert (u, m) == (int(nin[0]), int(nout[0]))
+        got = np.frombuffer((C.c_char * (m * ch * 2)).from_address(hout + k * cap * ch * 2), np.int16)
+        if kernel == KERNEL_STRICT:
+            check_close(y, got, exact=True, what=("wav payload", k))
+        else:  # +-1 LSB per hop; the 90 dB bar over the whole excerpt (single quiet hops sit a little below it)
+            assert np.abs(y.astype(np.int32) - got.astype(np.int32)).max() <= LSB_TOL, k
+        wants.append(y)
+        gots.append(got.copy())
+    assert O.snr_db(np.concatenate(wants), np.concatenate(gots)) >= SNR_MIN_DB
+    assert b.last_kernel() == kernel
+    b.close()
+    L.spxb_host_free(host)
+    L.spxb_host_free(hout)
