@@ -32,17 +32,18 @@ __device__ __forceinline__ int window_start(const FilterDev &F, const StreamCall
 }
 
 // X(j) = sample j of the output's window, as the f32 the reference holds in `mem`
+// `table` = the reference-layout sinc table, in global or (staged) shared memory
 template <bool kDirect, bool kWide, typename Window>
-__device__ __forceinline__ float strict_output(const FilterDev &F, uint32_t phase, const Window &X) {
+__device__ __forceinline__ float strict_output(const FilterDev &F, const float *table, uint32_t phase, const Window &X) {
   const int N = static_cast<int>(F.taps);
 
   if (kDirect) {
-    const float *h = F.table + static_cast<size_t>(phase) * N;
+    const float *h = table + static_cast<size_t>(phase) * N;
     if (!kWide) {
       float acc = 0.f;
       for (int j = 0; j < N; ++j) {
         const float x = X(j);
-        acc = __fadd_rn(acc, __fmul_rn(__ldg(h + j), x));
+        acc = __fadd_rn(acc, __fmul_rn(h[j], x));
       }
       return acc;
     } else {
@@ -52,10 +53,10 @@ __device__ __forceinline__ float strict_output(const FilterDev &F, uint32_t phas
         const float x1 = X(j + 1);
         const float x2 = X(j + 2);
         const float x3 = X(j + 3);
-        a0 = __dadd_rn(a0, static_cast<double>(__fmul_rn(__ldg(h + j), x0)));
-        a1 = __dadd_rn(a1, static_cast<double>(__fmul_rn(__ldg(h + j + 1), x1)));
-        a2 = __dadd_rn(a2, static_cast<double>(__fmul_rn(__ldg(h + j + 2), x2)));
-        a3 = __dadd_rn(a3, static_cast<double>(__fmul_rn(__ldg(h + j + 3), x3)));
+        a0 = __dadd_rn(a0, static_cast<double>(__fmul_rn(h[j], x0)));
+        a1 = __dadd_rn(a1, static_cast<double>(__fmul_rn(h[j + 1], x1)));
+        a2 = __dadd_rn(a2, static_cast<double>(__fmul_rn(h[j + 2], x2)));
+        a3 = __dadd_rn(a3, static_cast<double>(__fmul_rn(h[j + 3], x3)));
       }
       return static_cast<float>(__dadd_rn(__dadd_rn(__dadd_rn(a0, a1), a2), a3));
     }
@@ -63,17 +64,17 @@ __device__ __forceinline__ float strict_output(const FilterDev &F, uint32_t phas
     const uint32_t os = F.oversample;
     // resample.c:454: prototype cell of this phase; tap k of input j is tp[j*os + k]
     const uint32_t cell = static_cast<uint32_t>((static_cast<unsigned long long>(phase) * os) / F.den);
-    const float *tp = F.table + 4 + os - cell - 2;
+    const float *tp = table + 4 + os - cell - 2;
     const float4 w = __ldg(reinterpret_cast<const float4 *>(F.blend) + phase);
     if (!kWide) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       for (int j = 0; j < N; ++j) {
         const float x = X(j);
         const float *cf = tp + static_cast<size_t>(j) * os;
-        a0 = __fadd_rn(a0, __fmul_rn(x, __ldg(cf)));
-        a1 = __fadd_rn(a1, __fmul_rn(x, __ldg(cf + 1)));
-        a2 = __fadd_rn(a2, __fmul_rn(x, __ldg(cf + 2)));
-        a3 = __fadd_rn(a3, __fmul_rn(x, __ldg(cf + 3)));
+        a0 = __fadd_rn(a0, __fmul_rn(x, cf[0]));
+        a1 = __fadd_rn(a1, __fmul_rn(x, cf[1]));
+        a2 = __fadd_rn(a2, __fmul_rn(x, cf[2]));
+        a3 = __fadd_rn(a3, __fmul_rn(x, cf[3]));
       }
       // resample.c:476
       return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w.x, a0), __fmul_rn(w.y, a1)),
@@ -84,10 +85,10 @@ __device__ __forceinline__ float strict_output(const FilterDev &F, uint32_t phas
       for (int j = 0; j < N; ++j) {
         const float x = X(j);
         const float *cf = tp + static_cast<size_t>(j) * os;
-        a0 = __dadd_rn(a0, static_cast<double>(__fmul_rn(x, __ldg(cf))));
-        a1 = __dadd_rn(a1, static_cast<double>(__fmul_rn(x, __ldg(cf + 1))));
-        a2 = __dadd_rn(a2, static_cast<double>(__fmul_rn(x, __ldg(cf + 2))));
-        a3 = __dadd_rn(a3, static_cast<double>(__fmul_rn(x, __ldg(cf + 3))));
+        a0 = __dadd_rn(a0, static_cast<double>(__fmul_rn(x, cf[0])));
+        a1 = __dadd_rn(a1, static_cast<double>(__fmul_rn(x, cf[1])));
+        a2 = __dadd_rn(a2, static_cast<double>(__fmul_rn(x, cf[2])));
+        a3 = __dadd_rn(a3, static_cast<double>(__fmul_rn(x, cf[3])));
       }
       // resample.c:539: f32 weight * f64 sum, summed in f64, demoted once
       const double r = __dadd_rn(
@@ -107,7 +108,7 @@ __device__ __forceinline__ float strict_output(const FilterDev &F, uint32_t phas
 template <bool kDirect, bool kWide, int FMT, bool STAGED>
 __global__ void __launch_bounds__(kStrictThreads)
     strict_fir_kernel(const CallArgs a, const uint32_t blocks_per_stream,
-                      const uint32_t fir_blocks, const uint32_t win_cap) {
+                      const uint32_t fir_blocks, const uint32_t win_cap, const uint32_t tab_floats) {
   extern __shared__ float win[];
   if (blockIdx.x >= fir_blocks) {
     history_block_f<FMT>(a, blockIdx.x - fir_blocks);
@@ -134,21 +135,31 @@ __global__ void __launch_bounds__(kStrictThreads)
     if (elems <= win_cap) {
       for (uint32_t i = threadIdx.x; i < elems; i += kStrictThreads)
         win[i] = fetch_sample_f<FMT>(a, s, q_lo + static_cast<int>(i / ch), i % ch, sc.n_in);
+      // the sinc table too when it fits beside the window (tab_floats != 0): every tap of the
+      // interpolating kernels reads four of its entries
+      const float *table = a.filt.table;
+      if (tab_floats) {
+        float *tab = win + win_cap;
+        for (uint32_t i = threadIdx.x; i < tab_floats; i += kStrictThreads) tab[i] = __ldg(a.filt.table + i);
+        table = tab;
+      }
       __syncthreads();
       if (m >= sc.n_out) return;
       const int q = window_start(a.filt, sc, m, &phase);
       const float *xw = win + static_cast<uint32_t>(q - q_lo) * ch + c;
-      y = strict_output<kDirect, kWide>(a.filt, phase, [&](int j) { return xw[static_cast<uint32_t>(j) * ch]; });
+      y = strict_output<kDirect, kWide>(a.filt, table, phase, [&](int j) { return xw[static_cast<uint32_t>(j) * ch]; });
     } else {
       // (a window wider than the shared memory asked for: straight from global memory)
       if (m >= sc.n_out) return;
       const int q = window_start(a.filt, sc, m, &phase);
-      y = strict_output<kDirect, kWide>(a.filt, phase, [&](int j) { return fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in); });
+      y = strict_output<kDirect, kWide>(a.filt, a.filt.table, phase,
+                                        [&](int j) { return fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in); });
     }
   } else {
     if (m >= sc.n_out) return;
     const int q = window_start(a.filt, sc, m, &phase);
-    y = strict_output<kDirect, kWide>(a.filt, phase, [&](int j) { return fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in); });
+    y = strict_output<kDirect, kWide>(a.filt, a.filt.table, phase,
+                                      [&](int j) { return fetch_sample_f<FMT>(a, s, q + j, c, sc.n_in); });
   }
   const size_t oe = static_cast<size_t>(m) * a.out_step + c;  // == e unless the call is strided
   if (FMT == 2)  // the float entry stores the kernel's result as is (resample.c:927-963)
@@ -183,9 +194,15 @@ cudaError_t launch_strict(const CallArgs &a, cudaStream_t stream, uint32_t *laun
   const uint64_t win_bytes = win_frames * a.channels * sizeof(float);
   const bool staged = win_bytes <= 48u * 1024u && a.channels <= kStrictThreads;
   const uint32_t win_cap = staged ? static_cast<uint32_t>(win_bytes / sizeof(float)) : 0u;
+  // the reference-layout table beside it when both fit the default 48 KB
+  const uint64_t table_floats = a.filt.direct ? static_cast<uint64_t>(a.filt.den) * a.filt.taps
+                                              : static_cast<uint64_t>(a.filt.oversample) * a.filt.taps + 8;
+  const uint32_t tab_floats = staged && win_bytes + table_floats * sizeof(float) <= 48u * 1024u
+                                  ? static_cast<uint32_t>(table_floats) : 0u;
+  const size_t smem_bytes = static_cast<size_t>(win_bytes) + static_cast<size_t>(tab_floats) * sizeof(float);
   auto go = [&](auto kernel_staged, auto kernel_plain) {
-    if (staged) kernel_staged<<<grid, block, win_bytes, stream>>>(a, bps_arg, fir_blocks, win_cap);
-    else kernel_plain<<<grid, block, 0, stream>>>(a, bps_arg, fir_blocks, 0u);
+    if (staged) kernel_staged<<<grid, block, smem_bytes, stream>>>(a, bps_arg, fir_blocks, win_cap, tab_floats);
+    else kernel_plain<<<grid, block, 0, stream>>>(a, bps_arg, fir_blocks, 0u, 0u);
   };
   auto by_filter = [&](auto fmt) {
     constexpr int F = decltype(fmt)::value;
