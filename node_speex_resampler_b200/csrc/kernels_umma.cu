@@ -850,6 +850,11 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
       const uint32_t stage_bytes = x_stage(static_cast<int>(a.channels)) + kStageChunks * 3 * nt * 16;
       const uint32_t n_iters = (2 * c->ksteps + kStageChunks - 1) / kStageChunks;
       uint32_t stages = std::min<uint32_t>(kMaxStages, kMaxSmem / stage_bytes);
+      static const uint32_t stage_cap = [] {  // experiment: shared memory given up = L1 gained
+        const char *e = getenv("SPXB_UMMA_STAGES");
+        return e ? static_cast<uint32_t>(atoi(e)) : 0u;
+      }();
+      if (stage_cap) stages = std::min(stages, stage_cap);
       stages = std::max(1u, std::min(stages, n_iters));
       c->stages = stages;
       c->smem_bytes = stages * stage_bytes;
