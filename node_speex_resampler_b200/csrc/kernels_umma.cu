@@ -842,6 +842,8 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
         return false;
       }
       c->resident = true;
+      c->n_acc = 8 * nt <= 512 ? 2u : 1u;
+      c->tmem_cols = pow2_cols(c->n_acc * 4 * nt);
       c->tile_bytes = c->packed.tile_bytes;
       c->stages = x_stages;
       c->smem_bytes = x_stages * x_stage(static_cast<int>(a.channels)) + c->tile_bytes;

@@ -52,24 +52,29 @@ using namespace ptx;
 using namespace ummac;
 
 constexpr int kMaxXStages = 6;
-// 12 warps (168 registers per thread): 0-7 converters + epilogue (two groups of four on alternate
-// stages), 8 MMA issue (owns TMEM and the barriers, loads the tap tile of each run), 9 idle spare,
-// 10-11 history slide. (Sixteen converter warps, two per stage share, were tried: at 96 registers
-// they spill, and with the shared memory this kernel takes L1 is ~25 KB, so spills go to L2.)
+// 16 warps (128 registers per thread), every role on its own warps:
+//   0-7   converters, two groups of four on alternate stages;
+//   8-11  epilogue, one warp per TMEM lane quarter (warp % 4 selects the quarter);
+//   12    MMA issue (owns TMEM and the barriers, loads the tap tile of each run);
+//   13    warms the constant cache with the MMA records, then idles;
+//   14-15 history slide.
+// (Sixteen converter warps, two per stage share, were tried: at 96 registers they spill, and with
+// the shared memory this kernel takes L1 is ~25 KB, so spills go to L2.)
 constexpr int kConvWarps2 = 8, kGroupWarps = 4;
-constexpr int kMmaWarp2 = 8, kHistWarp0 = 10, kHistWarps = 2;
-constexpr int kThreads2 = 12 * 32;
+constexpr int kEpiWarp0 = 8, kEpiWarps = 4;
+constexpr int kMmaWarp2 = 12, kSpareWarp = 13, kHistWarp0 = 14, kHistWarps = 2;
+constexpr int kThreads2 = 16 * 32;
 constexpr uint32_t kMaxTapStages = kUmmaMaxKsteps / 2;
 constexpr uint32_t kInlineTiles2 = 32;
-// dynamic shared memory this kernel may ask for: 227 KB minus its static part (barriers + the
-// K-step table, 3 KB with the alignment of the dynamic array)
+// dynamic shared memory this kernel may ask for: 227 KB minus its static part (barriers, 1 KB with
+// the alignment of the dynamic array)
 constexpr uint32_t kMaxSmem2 = 227u * 1024u - 5120u;
 
-// What the kernel needs of the packed plan, ready to use (built on the host, kept in HBM, copied
-// to shared memory by the producer warp): per 64-frame stage the tap bytes to load and its run of
-// MMA records; per record everything one hi/lo pair of MMAs needs except the ring slot -- the
-// issuing lane adds three bases and goes (a table of raw block ranges cost ~190 cycles of
-// descriptor building per MMA in that one lane).
+// What the kernel needs of the packed plan, ready to use (built on the host, carried in the kernel
+// parameters): per 64-frame stage the tap bytes to load and its run of MMA records; per record
+// everything one hi/lo pair of MMAs needs except the ring slot -- the issuing lane adds three bases
+// and goes (a table of raw block ranges cost ~190 cycles of descriptor building per MMA in that
+// one lane).
 struct MmaRec {
   uint32_t b;         // added to the B descriptor: (K step offset + first row) | rows per chunk << 16
   uint32_t idesc_hi;  // instruction descriptor of the hi-plane MMA (the lo plane clears the A sign bit)
@@ -95,6 +100,8 @@ struct Umma2Args {
   uint32_t ksteps;
   uint32_t x_stages;
   uint32_t tmem_cols;
+  uint32_t dense;         // every K step is one MMA pair over all 3 nt columns (no packing, 3 nt <= 256): the issue loop needs no records
+  uint32_t n_acc;         // accumulator sets in TMEM (2 when 8 nt <= 512: the epilogue of a tile runs under the next tile's MMAs)
   int shift;
   unsigned long long *trace;
   InlineTile2 inl[kInlineTiles2];
@@ -131,12 +138,6 @@ __device__ __forceinline__ uint4 ld_pcm16(const void *p) {
   return __ldg(reinterpret_cast<const uint4 *>(p));
 #endif
 }
-
-// Rolling L2 prefetch distance of the converters, in 64-frame stages (0: off). The demand loads of
-// a stage are two stages ahead in registers; the prefetch runs further ahead without registers.
-#ifndef SPXB_PF_DIST
-#define SPXB_PF_DIST 0
-#endif
 
 #ifdef SPXB_UMMA2_TRACE
 constexpr int kTraceSlots2 = 128;
@@ -200,13 +201,19 @@ __device__ __forceinline__ void slide_streams(const CallArgs &a, uint32_t step, 
 // (group 0 the even stages of the CTA's stage sequence, group 1 the odd ones), each thread taking
 // 8 items of its group's stage: two stages are in the making at any time, the chain is paid once
 // per two stages' worth of data, and with two of its own stages of loads in registers per warp
-// 64 KB are in flight per SM.
+// 64 KB are in flight per SM. The converters never look at tile boundaries: the CTA's tiles are one
+// sequence of stages to them.
+//
+// Accumulators. With 8 nt <= 512 TMEM holds two accumulator sets: the MMA warp moves on to the next
+// tile the moment the last MMA of a tile is issued, and the four epilogue warps read the finished
+// set out underneath. With one set (wider tiles) the MMA warp waits for the epilogue's last
+// tcgen05.ld before the next tile's first MMA.
 template <int CH, bool FAST, bool IDS>
 __global__ void __launch_bounds__(kThreads2, 1)
     umma2_fir_kernel(const __grid_constant__ CallArgs a, const __grid_constant__ Umma2Args u) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t x_full[kMaxXStages], x_empty[kMaxXStages], tap_full[kMaxTapStages];
-  __shared__ uint64_t taps_free, acc_full, acc_empty, tmem_ready;
+  __shared__ uint64_t taps_free, acc_full[2], acc_empty[2], tmem_ready;
   __shared__ uint32_t tmem_slot;
 
   constexpr int kStreams = kUmmaRows / CH;  // streams per series group
@@ -216,6 +223,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
   // this CTA's share of the tile list (tile index major: w = t * G + g)
   const uint32_t w_begin = static_cast<uint32_t>(static_cast<unsigned long long>(blockIdx.x) * u.n_work / gridDim.x);
   const uint32_t w_end = static_cast<uint32_t>(static_cast<unsigned long long>(blockIdx.x + 1) * u.n_work / gridDim.x);
+  const uint32_t n_tiles_mine = w_end - w_begin;
   constexpr uint32_t kXPlaneBytes = x_plane(CH), kXStageBytes = x_stage(CH);
   const uint32_t S = u.x_stages;
   const uint32_t n_iters = (u.ksteps + 1) / 2;  // 64-frame stages per tile
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
   const int in_align = FAST ? 16 : (row_bits & 15u) == 0 ? 16 : (row_bits & 7u) == 0 ? 8 : (row_bits & 3u) == 0 ? 4 : 2;
 
   // Programmatic dependent launch: the next call's grid may be scheduled as SMs drain; it blocks in
-  // griddepcontrol.wait below until this grid has completed, before it touches PCM or history.
+  // griddepcontrol.wait below until this grid has completed, before it touches PCM, history or output.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) TRACE2(u, 0);
   if (tid == kThreads2 - 64) {
@@ -246,16 +254,16 @@ __global__ void __launch_bounds__(kThreads2, 1)
 #endif
   }
 
-  // ---- prologue: the barriers, one per lane of the producer warp; then everybody may proceed ----
+  // ---- prologue: the barriers, one per lane of the MMA warp; then everybody may proceed ----
   if (warp == kMmaWarp2) {
-    const uint32_t n_bar = 2 * S + n_iters + 4;
+    const uint32_t n_bar = 2 * S + n_iters + 6;
     for (uint32_t i = lane; i < n_bar; i += 32) {
       if (i < S) mbar_init(&x_full[i], kGroupWarps);             // one elected arrival per warp of a group
       else if (i < 2 * S) mbar_init(&x_empty[i - S], 1);
       else if (i < 2 * S + n_iters) mbar_init(&tap_full[i - 2 * S], 1);
       else if (i == 2 * S + n_iters) mbar_init(&taps_free, 1);
-      else if (i == 2 * S + n_iters + 1) mbar_init(&acc_full, 1);
-      else if (i == 2 * S + n_iters + 2) mbar_init(&acc_empty, kConvWarps2);
+      else if (i <= 2 * S + n_iters + 2) mbar_init(&acc_full[i - (2 * S + n_iters + 1)], 1);
+      else if (i <= 2 * S + n_iters + 4) mbar_init(&acc_empty[i - (2 * S + n_iters + 3)], kEpiWarps);
       else mbar_init(&tmem_ready, 1);
     }
     fence_mbar_init();
@@ -263,7 +271,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
   __syncthreads();
 
   // One bulk copy per K stage of the packed tile, each completing its own barrier: lane `it` of the
-  // producer warp issues stage `it` (offsets and sizes come with the kernel parameters).
+  // MMA warp issues stage `it` (offsets and sizes come with the kernel parameters).
   auto load_tap_tile = [&](uint32_t t) {
     const int8_t *src = u.pool + static_cast<size_t>(tile_slot(t)) * u.tile_bytes;
     if (static_cast<uint32_t>(lane) < n_iters) {
@@ -274,11 +282,11 @@ __global__ void __launch_bounds__(kThreads2, 1)
   };
 
   if (warp < kConvWarps2) {
-    // ================= converters: PCM -> byte planes in UMMA layout; then the epilogue =================
+    // ================= converters: PCM -> byte planes in UMMA layout =================
     // A stage is 64 frames of 128 series = kStreams stream segments of 64*CH*2 bytes. Lanes of a warp
     // walk ALONG a segment in 16-byte items (PPS items per stream, SPI streams per warp instruction),
     // so one LDG.128 covers four full 128-byte lines; each thread owns kItems items per stage, item i
-    // of warp gw (of its group) belonging to stream (4 gw + i) * SPI + lane / PPS of the tile's group.
+    // of warp gw (of its group) belonging to stream (8 gw + i) * SPI + lane / PPS of the tile's group.
     constexpr int FPI = 8 / CH;          // frames per 16-byte item
     constexpr int PPS = 64 / FPI;        // items per stream per stage (16 stereo, 8 mono)
     constexpr int SPI = 32 / PPS;        // streams per warp instruction (2 stereo, 4 mono)
@@ -296,7 +304,6 @@ __global__ void __launch_bounds__(kThreads2, 1)
       const uint32_t byte_in_row = static_cast<uint32_t>(conv_p * FPI) % kUmmaChunkFrames;
       return (j >> 1) * x_kstep(CH) + (j & 1) * x_lbo(CH) + sl0 * (16 * CH) + byte_in_row;
     }();
-    const uint32_t n_tiles_mine = w_end - w_begin;
     const uint32_t total_stages = n_tiles_mine * n_iters;
 
     // fetch cursor: (tile index, stage) whose loads go out next; advances two stages at a time
@@ -380,50 +387,97 @@ __global__ void __launch_bounds__(kThreads2, 1)
       }
     };
 
-    // ---- epilogue of one tile: straight from TMEM to the interleaved int16 output ----
-    // a lane owns one series (TMEM lane) and 16 consecutive outputs per column group; mono packs them
+    // ---- this warp's stages: q = group, group + 2, ... of the CTA's stage sequence ----
+    uint32_t slot = group % S, par = 1u ^ ((group / S) & 1u);  // ring slot of stage q, parity its `empty` wait expects
+#ifdef SPXB_UMMA2_TRACE
+    uint32_t step_no = 0;
+#define STEP_MARK(k) \
+  if (tid == 0 && step_no == n_iters + 3) TRACE2(u, 56 + (k))
+#else
+#define STEP_MARK(k)
+#endif
+    auto convert_step = [&](const uint4 (&raw)[kItems]) {
+      STEP_MARK(0);
+      mbar_wait(&x_empty[slot], par);
+      STEP_MARK(1);
+      convert_store(smem + slot * kXStageBytes, raw);
+      STEP_MARK(2);
+      // every thread makes its own stores visible to the async proxy, then one lane per warp arrives
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&x_full[slot]);
+      STEP_MARK(3);
+      slot += 2;
+      if (slot >= S) {
+        slot -= S;
+        par ^= 1u;
+      }
+    };
+    // The two register sets take turns strictly (never moved: a move of a register that a load in
+    // flight will write waits for that load).
+    fetch(raw0);
+    fetch(raw1);
+    if (tid == 0) TRACE2(u, 2);
+    for (uint32_t q = group; q < total_stages; q += 4) {
+      convert_step(raw0);
+      fetch(raw0);
+      STEP_MARK(4);
+#ifdef SPXB_UMMA2_TRACE
+      ++step_no;
+#endif
+      if (q + 2 >= total_stages) break;
+      convert_step(raw1);
+      fetch(raw1);
+#ifdef SPXB_UMMA2_TRACE
+      ++step_no;
+#endif
+    }
+    if (tid == 0) TRACE2(u, 10);
+  } else if (warp < kEpiWarp0 + kEpiWarps) {
+    // ================= epilogue: straight from TMEM to the interleaved int16 output =================
+    // A lane owns one series (TMEM lane) and 16 consecutive outputs per column group; mono packs them
     // into 32 contiguous bytes, stereo first swaps halves with the neighbouring lane (the other
     // channel of the same stream) so that each lane of the pair holds 8 whole frames = 32 bytes.
     // (Groups of 8 columns took 1.7x as long: an iteration costs ~600 cycles of TMEM-load and
     // dependent-arithmetic latency whatever its width.)
-    // The two warps of a TMEM lane quarter share the column groups.
     const uint32_t out_bits = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(a.out)) |
                               (static_cast<uint32_t>(a.out_stride) * 2u);
     const int out_align = FAST ? 16 : (out_bits & 15u) == 0 ? 16 : (out_bits & 3u) == 0 ? 4 : 2;
-    uint32_t tmem = 0;
-    auto epilogue = [&](uint32_t tile_no) {
+    const uint32_t quarter = static_cast<uint32_t>(warp) & 3u;
+    const uint32_t row = quarter * 32 + lane;  // TMEM lane = series of the tile
+    const uint32_t sl_out = CH == 2 ? row >> 1 : row, ch_out = CH == 2 ? (row & 1u) : 0u;
+    // the previous call's grid may still be writing the output rows this call overwrites
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    mbar_wait(&tmem_ready, 0);
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = tmem + ((quarter * 32u) << 16);
+    uint32_t buf = 0, use_par = 0;  // accumulator set of the tile, parity of its `full` barrier
+    for (uint32_t tile_no = 0; tile_no < n_tiles_mine; ++tile_no) {
       const uint32_t w = w_begin + tile_no, t = w / G, g = w - t * G;
-      const uint32_t row = (warp & 3) * 32 + lane;  // TMEM lane = series of the tile
-      const uint32_t sl_out = CH == 2 ? row >> 1 : row, ch_out = CH == 2 ? (row & 1u) : 0u;
       const uint32_t m0 = t * nt;
       const uint32_t n_valid = min(nt, sc.n_out - m0);
       const uint32_t s_out = g * kStreams + sl_out;
       const bool live_out = s_out < n_rows;
       int16_t *out_row = a.out + stream_of(live_out ? s_out : 0) * a.out_stride + static_cast<size_t>(m0) * CH;
-      if (tile_no == 0) {
-        mbar_wait(&tmem_ready, 0);
-        tc_fence_after_sync();
-        tmem = tmem_slot;
-      }
-      mbar_wait(&acc_full, tile_no & 1u);
+      if (lane == 0 && quarter == 0) TRACE2(u, 16 + 8 * min(tile_no, 4u) + 1);
+      mbar_wait(&acc_full[buf], use_par);
       tc_fence_after_sync();
-      const uint32_t lane_addr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+      const uint32_t lane_addr = lane_base + buf * 4u * nt;
       const uint32_t cg_end = (n_valid + 15) / 16;
-      constexpr uint32_t kCgStep = kConvWarps2 / 4;  // warps per TMEM lane quarter
-      const uint32_t cg0 = static_cast<uint32_t>(warp) >> 2;
-      for (uint32_t cg = cg0; cg < cg_end; cg += kCgStep) {
+      for (uint32_t cg = 0; cg < cg_end; ++cg) {
         uint32_t p0[16], p1[16], p2[16], p3[16];
         tmem_ld16(lane_addr + cg * 16, p0);
         tmem_ld16(lane_addr + nt + cg * 16, p1);
         tmem_ld16(lane_addr + 2 * nt + cg * 16, p2);
         tmem_ld16(lane_addr + 3 * nt + cg * 16, p3);
         tmem_ld_wait();
-        if (cg + kCgStep >= cg_end) {
-          // this warp's last read of the accumulator: hand it back before the arithmetic and the
-          // stores of this group, so the next tile's MMAs start underneath them
+        if (cg + 1 == cg_end) {
+          // this warp's last read of the accumulator set: hand it back before the arithmetic and
+          // the stores of this group
           tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty);
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
         int r16[16];
         combine16(p0, p1, p2, p3, u.shift, r16);  // rounded, not yet saturated
@@ -467,96 +521,10 @@ __global__ void __launch_bounds__(kThreads2, 1)
           }
         }
       }
-      if (cg0 >= cg_end) {
-        // (a warp with no column group in this tile still owes its arrival)
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty);
-      }
-    };
-
-    // ---- this warp's stages: q = group, group + 2, ... of the CTA's stage sequence ----
-    uint32_t slot = group % S, par = 1u ^ ((group / S) & 1u);  // ring slot of stage q, parity its `empty` wait expects
-    uint32_t c_tile = 0, c_it = group;                         // (tile, stage) of stage q
-    uint32_t done_tile = 0;                                    // tiles whose epilogue this warp has run
-#ifdef SPXB_UMMA2_TRACE
-    uint32_t step_no = 0;
-#define STEP_MARK(k) \
-  if (tid == 0 && step_no == n_iters + 3) TRACE2(u, 56 + (k))
-#else
-#define STEP_MARK(k)
-#endif
-    // The two register sets take turns strictly (never moved: a move of a register that a load
-    // in flight will write waits for that load). Two priming rounds only fetch; the epilogue
-    // appears once in the code, the conversion and the loads twice -- the start-up path of a
-    // launch runs with a cold instruction cache.
-    auto convert_step = [&](const uint4 (&raw)[kItems]) {
-      STEP_MARK(0);
-      mbar_wait(&x_empty[slot], par);
-      STEP_MARK(1);
-      convert_store(smem + slot * kXStageBytes, raw);
-      STEP_MARK(2);
-      // every thread makes its own stores visible to the async proxy, then one lane per warp arrives
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&x_full[slot]);
-      STEP_MARK(3);
-    };
-    auto run_epilogues = [&](uint32_t upto) {
-      while (done_tile < upto) {
-        if (tid == 0) TRACE2(u, 16 + 8 * min(done_tile, 4u) + 1);
-        epilogue(done_tile);
-        if (tid == 0) TRACE2(u, 16 + 8 * min(done_tile, 4u) + 3);
-        ++done_tile;
-      }
-    };
-    uint32_t q = group;
-    bool odd = false, defer_epilogue = false;
-    for (int step = -2;; ++step) {
-      const bool live = step >= 0;
-      if (live) {
-        while (c_it >= n_iters) {
-          c_it -= n_iters;
-          ++c_tile;
-        }
-        // All of this warp's stages of the tiles before c_tile are stored: their epilogues are due
-        // (the MMAs of c_tile cannot start before the accumulator of c_tile - 1 has been read out).
-        // This warp's FIRST stage of the new tile goes in front of the epilogue when it can: its
-        // ring slot was last used by the old tile, so it cannot wait on anything the epilogue
-        // holds up, and the next tile's MMAs find it ready the moment the accumulator is free.
-        defer_epilogue = done_tile + 1 == c_tile && c_tile < n_tiles_mine && c_it < S && n_iters >= S;
-        if (!defer_epilogue) run_epilogues(min(c_tile, n_tiles_mine));
-        if (q >= total_stages) break;
-        if (tid == 0 && c_it == 0) TRACE2(u, 16 + 8 * min(c_tile, 4u) + 0);
-      }
-      // convert this warp's stage q, then send out the loads of its stage two of its stages ahead
-      // into the registers just consumed
-      // (a deferred epilogue runs between the two: the register set just converted is free then,
-      // which is what lets the epilogue work on 16 columns at a time without spilling)
-      if (!odd) {
-        if (live) convert_step(raw0);
-        if (live && defer_epilogue) run_epilogues(c_tile);
-        fetch(raw0);
-      } else {
-        if (live) convert_step(raw1);
-        if (live && defer_epilogue) run_epilogues(c_tile);
-        fetch(raw1);
-      }
-      defer_epilogue = false;
-      if (step == -1 && tid == 0) TRACE2(u, 2);
-      STEP_MARK(4);
-      odd = !odd;
-      if (live) {
-        q += 2;
-        slot += 2;
-        if (slot >= S) {
-          slot -= S;
-          par ^= 1u;
-        }
-        c_it += 2;
-#ifdef SPXB_UMMA2_TRACE
-        ++step_no;
-#endif
+      if (lane == 0 && quarter == 0) TRACE2(u, 16 + 8 * min(tile_no, 4u) + 3);
+      if (++buf == u.n_acc) {
+        buf = 0;
+        use_par ^= 1u;
       }
     }
   } else if (warp == kMmaWarp2) {
@@ -564,8 +532,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
     // The whole warp walks the tiles and stages (uniform control flow, descriptors in uniform
     // registers); one elected lane issues. First: the tap tile of the first run (the tile table and
     // the tap pool are only ever rewritten by stream-ordered work, and a call that re-planned launches
-    // without the programmatic edge: safe to read before the grid dependency resolves), TMEM, and the
-    // MMA records into shared memory.
+    // without the programmatic edge: safe to read before the grid dependency resolves), then TMEM.
     load_tap_tile(w_begin / G);
     if (lane == 0) TRACE2(u, 12);
     tmem_alloc(&tmem_slot, u.tmem_cols);
@@ -585,6 +552,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
     const uint64_t b_fixed = umma_smem_desc(smem_u32(tap_smem), 0, 128);
     constexpr uint32_t a_stage16 = kXStageBytes >> 4, a_lo16 = kXPlaneBytes >> 4;
     uint32_t slot = 0, par = 0, tile_no = 0, run = 0;
+    uint32_t buf = 0, buf_use = 0;  // accumulator set of the tile, how many times it has been used before
     uint64_t a_st = a_base;
     uint32_t cur_t = 0xffffffffu;
     for (uint32_t w = w_begin; w < w_end; ++w, ++tile_no) {
@@ -604,68 +572,68 @@ __global__ void __launch_bounds__(kThreads2, 1)
       }
       const bool run_ends = w + 1 == w_end || (w + 1) / G != t;
       const uint32_t tr = 16 + 8 * min(tile_no, 4u);  // trace slots of this tile
-      if (tile_no) {
-        // the epilogue has read the previous tile's accumulator out of TMEM
-        mbar_wait(&acc_empty, (tile_no - 1) & 1u);
+      if (buf_use) {
+        // the epilogue has read this set's previous tile out of TMEM
+        mbar_wait(&acc_empty[buf], (buf_use - 1) & 1u);
         tc_fence_after_sync();
       }
+      const uint32_t acc = tmem + buf * 4u * nt;
       if (lane == 0) TRACE2(u, tr + 4);
-      // A stage is issued in two halves (its two K steps). Between them the warp waits for the NEXT
-      // stage of the tile: the wait and the hand-over bookkeeping then run while the first half's
-      // MMAs are still queued in the tensor pipe, instead of after it has drained.
-      bool have_stage = false;  // the stage about to be issued has already been waited for
       for (uint32_t it = 0; it < n_iters; ++it) {
         if (tile_no == 1 && it < 16 && lane == 0) TRACE2(u, 64 + 3 * it);
-        if (!have_stage) {
-          if (new_run) mbar_wait(&tap_full[it], tap_par);
-          mbar_wait(&x_full[slot], par);
-        }
+        if (new_run) mbar_wait(&tap_full[it], tap_par);
+        mbar_wait(&x_full[slot], par);
         tc_fence_after_sync();
         if (tile_no == 1 && it < 16 && lane == 0) TRACE2(u, 65 + 3 * it);
         if (it == 0 && lane == 0) TRACE2(u, tr + 5);
         const bool last = it + 1 == n_iters;
-        const uint32_t m_mid = u.stage_mid[it], m_end = u.stage_rec[it + 1];
-        auto issue = [&](uint32_t m0, uint32_t m1) {
-#pragma unroll 1
-          for (uint32_t m = m0; m < m1; ++m) {
-            const uint32_t rb = u.rec[m].b, ri = u.rec[m].idesc_hi, rd = u.rec[m].d_a;
-            const uint64_t b = b_fixed + rb;
-            const uint64_t a_hi = a_st + (rd >> 16);
-            const uint32_t d_hi = tmem + (rd & 0xffffu);
-#ifndef SPXB_DBG_NOMMA
-            umma_i8(d_hi, a_hi, b, ri, 1u);
-            umma_i8(d_hi + nt, a_hi + a_lo16, b, ri & ~(1u << 7), 1u);
-#else
-            if (b == 1 && a_hi == 2 && d_hi == 3) umma_i8(d_hi, a_hi, b, ri, 1u);  // timing experiment: no MMAs
-#endif
-          }
-        };
         if (elect_one()) {
           if (it == 0) {
             // K step 0 is stored whole and initialises every accumulator column
             const uint64_t b_k = b_fixed + (static_cast<uint64_t>(n3) << 16), a_lo = a_st + a_lo16;
-            umma_i8(tmem, a_st, b_k, with_n(id_hi, np0), 0u);
-            if (np1) umma_i8(tmem + 256, a_st, b_k + 256, with_n(id_hi, np1), 0u);
+            umma_i8(acc, a_st, b_k, with_n(id_hi, np0), 0u);
+            if (np1) umma_i8(acc + 256, a_st, b_k + 256, with_n(id_hi, np1), 0u);
             // columns [nt,3nt) already hold hi*B: accumulate; columns [3nt,4nt) are fresh
-            umma_i8(tmem + nt, a_lo, b_k, with_n(id_lo, nq0), 1u);
-            if (nq1) umma_i8(tmem + nt + 256, a_lo, b_k + 256, with_n(id_lo, nq1), 1u);
-            umma_i8(tmem + 3 * nt, a_lo, b_k + 2 * nt, with_n(id_lo, nt), 0u);
+            umma_i8(acc + nt, a_lo, b_k, with_n(id_lo, nq0), 1u);
+            if (nq1) umma_i8(acc + nt + 256, a_lo, b_k + 256, with_n(id_lo, nq1), 1u);
+            umma_i8(acc + 3 * nt, a_lo, b_k + 2 * nt, with_n(id_lo, nt), 0u);
           }
-          issue(u.stage_rec[it], m_mid);  // first K step of the stage (K step 0: its own code above)
-        }
-        __syncwarp();
-        have_stage = false;
-        if (!last) {
-          const uint32_t nslot = slot + 1 == S ? 0u : slot + 1, npar = slot + 1 == S ? par ^ 1u : par;
-          if (new_run) mbar_wait(&tap_full[it + 1], tap_par);
-          mbar_wait(&x_full[nslot], npar);
-          have_stage = true;
-        }
-        if (elect_one()) {
-          issue(m_mid, m_end);  // second K step
+          if (u.dense) {
+            // one MMA pair per K step, every operand a constant step from the previous one: nothing
+            // but uniform adds between the MMAs (the record walk below costs ~100 cycles of dependent
+            // uniform loads and arithmetic per MMA -- more than the tensor pipe needs to run one)
+            const uint32_t id_h3 = with_n(id_hi, n3), id_l3 = with_n(id_lo, n3);
+            const uint64_t b_row = b_fixed + (static_cast<uint64_t>(n3) << 16);
+#pragma unroll
+            for (uint32_t h = 0; h < 2; ++h) {
+              const uint32_t k = 2 * it + h;
+              if (k == 0 || k >= u.ksteps) continue;
+              const uint64_t b = b_row + k * (2 * n3);
+              const uint64_t a_hi = a_st + h * (x_kstep(CH) >> 4);
+#ifndef SPXB_DBG_NOMMA
+              umma_i8(acc, a_hi, b, id_h3, 1u);
+              umma_i8(acc + nt, a_hi + a_lo16, b, id_l3, 1u);
+#endif
+            }
+          } else {
+            const uint32_t m_end = u.stage_rec[it + 1];
+#pragma unroll 1
+            for (uint32_t m = u.stage_rec[it]; m < m_end; ++m) {
+              const uint32_t rb = u.rec[m].b, ri = u.rec[m].idesc_hi, rd = u.rec[m].d_a;
+              const uint64_t b = b_fixed + rb;
+              const uint64_t a_hi = a_st + (rd >> 16);
+              const uint32_t d_hi = acc + (rd & 0xffffu);
+#ifndef SPXB_DBG_NOMMA
+              umma_i8(d_hi, a_hi, b, ri, 1u);
+              umma_i8(d_hi + nt, a_hi + a_lo16, b, ri & ~(1u << 7), 1u);
+#else
+              if (b == 1 && a_hi == 2 && d_hi == 3) umma_i8(d_hi, a_hi, b, ri, 1u);  // timing experiment: no MMAs
+#endif
+            }
+          }
           umma_commit(&x_empty[slot]);
           if (last) {
-            umma_commit(&acc_full);
+            umma_commit(&acc_full[buf]);
             if (run_ends) umma_commit(&taps_free);
           }
         }
@@ -679,14 +647,18 @@ __global__ void __launch_bounds__(kThreads2, 1)
           a_st = a_base;
         }
       }
+      if (++buf == u.n_acc) {
+        buf = 0;
+        ++buf_use;
+      }
     }
     if (lane == 0) TRACE2(u, 11);
-  } else if (warp == kMmaWarp2 + 1) {
+  } else if (warp == kSpareWarp) {
     // ================= spare warp: pull the MMA records into the constant cache =================
     uint32_t acc = 0;
     for (uint32_t i = lane * 4; i <= u.n_rec; i += 32 * 4) acc ^= u.rec[i].b;  // one read per 64-byte line
     if (acc == 0xdeadbeefu && u.n_rec == 0xffffffffu) a.samp_frac[0] = acc;     // (keeps the reads alive)
-  } else if (warp >= kHistWarp0) {
+  } else {
     // ================= history slide (resample.c:898-899) and the new position =================
     // Runs beside the FIR: it reads the old history and this call's input, writes the other half
     // of the ping-pong. Stream sl of group g is handled with the tile (t, g) for which
@@ -862,6 +834,13 @@ cudaError_t launch_umma2(UmmaContext *c, const CallArgs &a, cudaStream_t stream,
   u.ksteps = c->ksteps;
   u.x_stages = c->stages;
   u.tmem_cols = c->tmem_cols;
+  u.n_acc = c->n_acc;
+  u.dense = 3 * c->nt <= 256 ? 1u : 0u;
+  for (uint32_t k = 0; k < c->ksteps && u.dense; ++k) {
+    const UmmaKStep &ks = c->packed.k[k];
+    if (ks.n_ent != 1 || ks.ent[0].row != 0 || ks.ent[0].dcol != 0 || ks.ent[0].n != 3 * c->nt || ks.off16 != k * 6 * c->nt)
+      u.dense = 0u;
+  }
   u.shift = c->ft.shift;
   u.n_rec = static_cast<uint32_t>(c->recs.size() / 4);
   std::memcpy(u.rec, c->recs.data(), c->recs.size() * sizeof(uint32_t));

@@ -15,9 +15,9 @@ import node_speex_resampler_b200 as pkg  # noqa: E402
 SHAPES = {"C3": (1024, 2, 44100, 48000, 7, 882), "C4": (4096, 1, 48000, 16000, 10, 960),
           "C5": (8192, 2, 96000, 44100, 10, 1920), "X6": (1024, 2, 44100, 48000, 10, 882)}
 NAMES = {0: "start", 1: "setup done", 2: "first fetches issued", 3: "before griddepcontrol.wait", 4: "after griddepcontrol.wait", 12: "tap loads issued", 8: "history done",
-         11: "mma: all issued", 9: "exit"}
-TILE = ["conv: tile start", "conv: stages stored", "conv: acc ready", "conv: epilogue done",
-        "mma: acc handed back", "mma: stage 0 full", "mma: last stage issued"]
+         11: "mma: all issued", 10: "converters done", 9: "exit"}
+TILE = ["", "epi: waits for the accumulator", "", "epi: tile stored",
+        "mma: accumulator set free", "mma: stage 0 full", "mma: last stage issued"]
 L = pkg.lib()
 for wl in (sys.argv[1:] or ["C3", "C4", "C5"]):
     S, ch, i, o, q, n = SHAPES[wl]
@@ -44,13 +44,14 @@ for wl in (sys.argv[1:] or ["C3", "C4", "C5"]):
         show(NAMES[slot], slot)
     for j in range(5):
         for k, nm in enumerate(TILE):
-            show(f"tile {j} {nm}", 16 + 8 * j + k)
+            if nm:
+                show(f"tile {j} {nm}", 16 + 8 * j + k)
     for k, nm in enumerate(("step: enter", "step: slot empty", "step: converted + stored", "step: fenced + arrived", "step: next loads issued")):
-        show(f"tile 1 stage 6 {nm}", 56 + k)
+        show(f"converter step n_iters+3 {nm}", 56 + k)
     for it in range(16):
         for k, nm in enumerate(("wait", "full", "issued")):
             show(f"mma tile 1 stage {it} {nm}", 64 + 3 * it + k)
-    for slot in (8, 11, 9):
+    for slot in (8, 10, 11, 9):
         show(NAMES[slot], slot)
     gt0, gt1 = t[:, 14], t[:, 15]
     print(f"  globaltimer: first start -> last end {int(gt1.max() - gt0.min())} ns; CTA duration median "
