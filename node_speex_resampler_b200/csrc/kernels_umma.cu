@@ -796,32 +796,34 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
   const uint32_t n_rows = a.ids ? a.n_ids : a.n_streams;
   const uint32_t n_groups = (n_rows * a.channels + kUmmaRows - 1) / kUmmaRows;
   const StreamCall &sc = a.uniform;
+  // the persistent, TMA-fed kernel is opt-in (SPXB_UMMA_RESIDENT=1) and covers whole batches with
+  // 16-byte aligned rows; a call it does not cover re-plans for the one-tile-per-CTA kernel
+  static const bool allow_resident = [] {
+    const char *e = getenv("SPXB_UMMA_RESIDENT");
+    return e && atoi(e) != 0;
+  }();
+  const bool want_resident = allow_resident && umma2_covers(a);
   if (c->memo && c->m_ls0 == sc.ls0 && c->m_frac0 == sc.frac0 && c->m_n_out == sc.n_out &&
-      c->m_hist_frames == a.hist_frames && c->m_groups == n_groups) {
+      c->m_hist_frames == a.hist_frames && c->m_groups == n_groups && c->resident_wanted == want_resident) {
     return true;  // steady state: same tiles as the previous call
   }
   const uint64_t ops_before = c->stream_ops;
 
   const uint32_t nt = pick_nt(*c, n_groups, sc.n_out);
-  if (nt != c->nt && c->frozen) {
+  if ((nt != c->nt || want_resident != c->resident_wanted) && c->frozen) {
     *err = cudaErrorNotSupported;
     return false;
   }
-  if (nt != c->nt) {
+  if (nt != c->nt || want_resident != c->resident_wanted) {
     drop_pool(c);
     c->nt = nt;
+    c->resident_wanted = want_resident;
     c->ksteps = umma_ksteps(c->spec.taps, c->spec.num, c->spec.den, nt);
     c->tmem_cols = pow2_cols(4 * nt);
     // the persistent kernel with a packed, shared-memory-resident tap tile when that tile fits
     c->resident = false;
-    // opt-in (SPXB_UMMA_RESIDENT=1): measured slower than the one-tile-per-CTA kernel on every
-    // BASELINE shape
-    static const bool allow_resident = [] {
-      const char *e = getenv("SPXB_UMMA_RESIDENT");
-      return e && atoi(e) != 0;
-    }();
     uint32_t x_stages = 0;
-    if (allow_resident && build_packed_plan(c->spec, c->ft, nt, &c->packed))
+    if (want_resident && build_packed_plan(c->spec, c->ft, nt, &c->packed))
       x_stages = umma2_x_stages(a.channels, c->packed.tile_bytes, c->ksteps);
     if (x_stages >= 2) {
       c->stream_ops += 1;
@@ -842,11 +844,9 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
         return false;
       }
       c->resident = true;
-      c->n_acc = 8 * nt <= 512 ? 2u : 1u;
-      c->tmem_cols = pow2_cols(c->n_acc * 4 * nt);
       c->tile_bytes = c->packed.tile_bytes;
       c->stages = x_stages;
-      c->smem_bytes = x_stages * x_stage(static_cast<int>(a.channels)) + c->tile_bytes;
+      c->smem_bytes = x_stages * x_slot(static_cast<int>(a.channels)) + c->tile_bytes;
     } else {
       c->tile_bytes = 2 * c->ksteps * 3 * nt * 16;
       const uint32_t stage_bytes = x_stage(static_cast<int>(a.channels)) + kStageChunks * 3 * nt * 16;

@@ -31,8 +31,11 @@
 //   10   slides the history (resample.c:898-899) of this CTA's share of streams beside the FIR and
 //        publishes the new stream position.
 // One instantiation per (CH, FAST, IDS); the schedule is written down, not induced by probes.
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstddef>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -52,18 +55,14 @@ using namespace ptx;
 using namespace ummac;
 
 constexpr int kMaxXStages = 6;
-// 16 warps (128 registers per thread), every role on its own warps:
-//   0-7   converters, two groups of four on alternate stages;
-//   8-11  epilogue, one warp per TMEM lane quarter (warp % 4 selects the quarter);
-//   12    MMA issue (owns TMEM and the barriers, loads the tap tile of each run);
-//   13    warms the constant cache with the MMA records, then idles;
-//   14-15 history slide.
-// (Sixteen converter warps, two per stage share, were tried: at 96 registers they spill, and with
-// the shared memory this kernel takes L1 is ~25 KB, so spills go to L2.)
+// 12 warps (168 registers per thread):
+//   0-7   converters + epilogue, two groups of four on alternate stages (warp % 4 = TMEM lane quarter);
+//   8     MMA issue (owns TMEM and the barriers, loads the tap tile of each run);
+//   9     lane 0 feeds the ring: one tensor-map TMA box of raw PCM per stage;
+//   10-11 history slide.
 constexpr int kConvWarps2 = 8, kGroupWarps = 4;
-constexpr int kEpiWarp0 = 8, kEpiWarps = 4;
-constexpr int kMmaWarp2 = 12, kSpareWarp = 13, kHistWarp0 = 14, kHistWarps = 2;
-constexpr int kThreads2 = 16 * 32;
+constexpr int kMmaWarp2 = 8, kLoadWarp = 9, kHistWarp0 = 10, kHistWarps = 2;
+constexpr int kThreads2 = 12 * 32;
 constexpr uint32_t kMaxTapStages = kUmmaMaxKsteps / 2;
 constexpr uint32_t kInlineTiles2 = 32;
 // dynamic shared memory this kernel may ask for: 227 KB minus its static part (barriers, 1 KB with
@@ -79,13 +78,20 @@ struct MmaRec {
   uint32_t b;         // added to the B descriptor: (K step offset + first row) | rows per chunk << 16
   uint32_t idesc_hi;  // instruction descriptor of the hi-plane MMA (the lo plane clears the A sign bit)
   uint32_t d_a;       // first accumulator column (hi plane) | A offset of the K step inside the stage << 16
-  uint32_t pad_;
 };
 constexpr uint32_t kMaxRecs = kUmmaMaxKsteps * kUmmaMaxEntries;
 
 struct InlineTile2 {
   int32_t kf0;
   uint32_t slot;
+};
+
+// Tensor maps over the call's PCM (bytes; row = stream): the input rows and the history rows, each
+// with a box of one whole stage (64 frames x the tile's streams) and a box of a quarter stage (16
+// frames) for the one stage of a tile that straddles the end of the history. Elements outside the
+// tensor (frames past the call's input, streams past the end of the batch) arrive as zeros.
+struct alignas(64) Umma2Maps {
+  CUtensorMap in64, in16, hist64, hist16;
 };
 
 struct Umma2Args {
@@ -101,7 +107,6 @@ struct Umma2Args {
   uint32_t x_stages;
   uint32_t tmem_cols;
   uint32_t dense;         // every K step is one MMA pair over all 3 nt columns (no packing, 3 nt <= 256): the issue loop needs no records
-  uint32_t n_acc;         // accumulator sets in TMEM (2 when 8 nt <= 512: the epilogue of a tile runs under the next tile's MMAs)
   int shift;
   unsigned long long *trace;
   InlineTile2 inl[kInlineTiles2];
@@ -112,32 +117,9 @@ struct Umma2Args {
   // The MMA records live in the kernel parameters (constant bank): the issuing lane reads them with
   // uniform loads straight into uniform registers. (From shared memory every operand of a
   // tcgen05.mma went through a register-to-uniform move: ~150 cycles of issue per MMA, three times
-  // what the tensor pipe needs for it.) A spare warp touches them during the prologue so that the
-  // first tile does not pay a cold constant-cache miss per line.
+  // what the tensor pipe needs for it.)
   MmaRec rec[kMaxRecs + 1];
 };
-
-// PCM loads of the converters. With the tap tile resident the CTA's shared memory leaves the SM's
-// unified L1 only ~25 KB, less than the two stages of loads (32 KB) the converters keep in flight:
-// SPXB_LD_NOALLOC=1 asks for loads that do not allocate L1 lines.
-#ifndef SPXB_LD_NOALLOC
-#define SPXB_LD_NOALLOC 0
-#endif
-__device__ __forceinline__ uint4 ld_pcm16(const void *p) {
-#if defined(SPXB_DBG_NOLOAD)
-  return make_uint4(0u, 0u, 0u, reinterpret_cast<uintptr_t>(p) == 1 ? 1u : 0u);  // timing experiment: no PCM loads
-#elif SPXB_LD_NOALLOC == 2
-  return *reinterpret_cast<const uint4 *>(p);  // plain ld.global (LSU path instead of the read-only path)
-#elif SPXB_LD_NOALLOC
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p));
-  return v;
-#else
-  return __ldg(reinterpret_cast<const uint4 *>(p));
-#endif
-}
 
 #ifdef SPXB_UMMA2_TRACE
 constexpr int kTraceSlots2 = 128;
@@ -151,9 +133,53 @@ constexpr int kTraceSlots2 = 128;
   } while (0)
 #endif
 
+// SPXB_UMMA2_WATCHDOG: a barrier wait that gives up after ~a second, records who waited for what in
+// a host-mapped buffer (u.trace) and carries on (the results are garbage; the point is the record)
+#ifdef SPXB_UMMA2_WATCHDOG
+__device__ __noinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, uint32_t tag, unsigned long long *dbg,
+                                          const volatile uint32_t *prog = nullptr) {
+  for (uint32_t i = 0; i < (1u << 22); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  if (dbg) {
+    const unsigned long long n = atomicAdd(dbg, 1ull);
+    if (n < 500) {
+      dbg[1 + n] = (static_cast<unsigned long long>(blockIdx.x) << 48) | (static_cast<unsigned long long>(threadIdx.x) << 32) | tag;
+      __threadfence_system();
+    }
+    if (prog && n < 40) {
+      for (int w = 0; w < 12; ++w) {
+        const unsigned long long k = atomicAdd(dbg, 1ull);
+        if (k < 500) dbg[1 + k] = (static_cast<unsigned long long>(blockIdx.x) << 48) | (static_cast<unsigned long long>(w * 32) << 32) | 0xE0000000ull | (prog[w] & 0x0fffffffu) | ((prog[w] >> 24) << 24 & 0x0f000000u);
+      }
+      __threadfence_system();
+    }
+  }
+}
+#define WAIT(bar, par, tag) mbar_wait_wd(bar, par, tag, u.trace)
+#define WAIT_L(bar, par, tag) mbar_wait_wd(bar, par, tag, u.trace, wd_prog)
+#else
+#define WAIT(bar, par, tag) mbar_wait(bar, par)
+#define WAIT_L(bar, par, tag) mbar_wait(bar, par)
+#endif
+
+__device__ __forceinline__ void tma_box_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+#ifndef SPXB_DBG_NOLOAD
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+#endif
+}
+
+// named barrier of one converter group (ids 1, 2; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(uint32_t group) {
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupWarps * 32) : "memory");
+}
+
 // History slide (resample.c:898-899) of streams first, first + step, ... (n_mine of them), four at
 // a time: four streams x four vectors of type V per lane are loaded before any store.
-template <typename V, bool IDS>
+template <typename V>
 __device__ __forceinline__ void slide_streams(const CallArgs &a, uint32_t step, uint32_t first, uint32_t n_mine,
                                               uint32_t hist_elems, size_t shift, int lane, uint32_t part,
                                               uint32_t parts) {
@@ -163,8 +189,7 @@ __device__ __forceinline__ void slide_streams(const CallArgs &a, uint32_t step, 
       V val[4][4];
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        const size_t s = !IDS ? first + static_cast<size_t>(k0 + kk) * step
-                              : k0 + kk < n_mine ? a.ids[first + (k0 + kk) * step] : 0;
+        const size_t s = first + static_cast<size_t>(k0 + kk) * step;
         const int16_t *hsrc = a.hist_src + s * a.hist_stride;
         const int16_t *isrc = a.in + s * a.in_stride;
 #pragma unroll
@@ -177,8 +202,7 @@ __device__ __forceinline__ void slide_streams(const CallArgs &a, uint32_t step, 
       }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        const size_t s = !IDS ? first + static_cast<size_t>(k0 + kk) * step
-                              : k0 + kk < n_mine ? a.ids[first + (k0 + kk) * step] : 0;
+        const size_t s = first + static_cast<size_t>(k0 + kk) * step;
         int16_t *hdst = a.hist_dst + s * a.hist_stride;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -190,31 +214,40 @@ __device__ __forceinline__ void slide_streams(const CallArgs &a, uint32_t step, 
   }
 }
 
-// FAST = every input and output row starts on a 16-byte boundary (every BASELINE shape): drops the
-// narrower load / store variants. IDS = the launch covers the stream subset a.ids[0 .. a.n_ids)
-// (a cohort of a ragged batch).
+// The launch covers whole batches whose input, output and history rows start on 16-byte boundaries
+// (every BASELINE shape); anything else -- cohorts of a ragged batch, odd row pitches -- runs on the
+// one-tile-per-CTA kernel (kernels_umma.cu).
 //
-// Converter schedule. One converter warp's share of a stage is a serial chain -- wait for the ring
-// slot, split the bytes, fence, arrive, address and issue the next loads -- of 650-800 cycles
-// however little data it covers (measured with loads and MMAs compiled out), and global loads come
-// back after ~2000 cycles. So the 8 converter warps work as TWO groups of four on ALTERNATE stages
-// (group 0 the even stages of the CTA's stage sequence, group 1 the odd ones), each thread taking
-// 8 items of its group's stage: two stages are in the making at any time, the chain is paid once
-// per two stages' worth of data, and with two of its own stages of loads in registers per warp
-// 64 KB are in flight per SM. The converters never look at tile boundaries: the CTA's tiles are one
-// sequence of stages to them.
-//
-// Accumulators. With 8 nt <= 512 TMEM holds two accumulator sets: the MMA warp moves on to the next
-// tile the moment the last MMA of a tile is issued, and the four epilogue warps read the finished
-// set out underneath. With one set (wider tiles) the MMA warp waits for the epilogue's last
-// tcgen05.ld before the next tile's first MMA.
-template <int CH, bool FAST, bool IDS>
+// A ring slot holds one 64-frame stage of the tile's 128 series, first as raw PCM (a TMA box: one row
+// of 64 * CH * 2 bytes per stream), then, converted IN PLACE by a converter group, as the two byte
+// planes in UMMA layout:
+//   loader lane : x_empty[slot] -> TMA box(es) -> raw_full[slot] (transaction bytes)
+//   group q & 1 : raw_full[slot] -> 8 items per thread into registers, bytes split -> group barrier
+//                 (every thread has read its raw bytes) -> planes stored -> fence -> x_full[slot]
+//   MMA lane    : x_full[slot] -> MMAs -> tcgen05.commit -> x_empty[slot]
+// PCM therefore reaches the SM through the copy engine (42 B/clk/SM measured in this access pattern,
+// csrc/ldg_rate.cu) instead of LDG.128 into registers (13-14 B/clk/SM from 8 warps, whatever is in
+// flight -- what bounded the earlier kernels at ~1100 cycles per stage), no registers hold loads in
+// flight, and the converters never compute a global address.
+template <int CH>
 __global__ void __launch_bounds__(kThreads2, 1)
-    umma2_fir_kernel(const __grid_constant__ CallArgs a, const __grid_constant__ Umma2Args u) {
+    umma2_fir_kernel(const __grid_constant__ CallArgs a, const __grid_constant__ Umma2Args u,
+                     const __grid_constant__ Umma2Maps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t x_full[kMaxXStages], x_empty[kMaxXStages], tap_full[kMaxTapStages];
-  __shared__ uint64_t taps_free, acc_full[2], acc_empty[2], tmem_ready;
+  __shared__ uint64_t raw_full[kMaxXStages], x_full[kMaxXStages], x_empty[kMaxXStages], tap_full[kMaxTapStages];
+  __shared__ uint64_t taps_free, acc_full, acc_empty, tmem_ready;
   __shared__ uint32_t tmem_slot;
+#ifdef SPXB_UMMA2_WATCHDOG
+  __shared__ volatile uint32_t wd_prog[16];
+#define PROG(code, v) \
+  do {                \
+    if ((threadIdx.x & 31) == 0) wd_prog[threadIdx.x >> 5] = ((code) << 24) | (v); \
+  } while (0)
+#else
+#define PROG(code, v) \
+  do {                \
+  } while (0)
+#endif
 
   constexpr int kStreams = kUmmaRows / CH;  // streams per series group
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -224,18 +257,18 @@ __global__ void __launch_bounds__(kThreads2, 1)
   const uint32_t w_begin = static_cast<uint32_t>(static_cast<unsigned long long>(blockIdx.x) * u.n_work / gridDim.x);
   const uint32_t w_end = static_cast<uint32_t>(static_cast<unsigned long long>(blockIdx.x + 1) * u.n_work / gridDim.x);
   const uint32_t n_tiles_mine = w_end - w_begin;
-  constexpr uint32_t kXPlaneBytes = x_plane(CH), kXStageBytes = x_stage(CH);
+  constexpr uint32_t kXPlaneBytes = x_plane(CH), kXStageBytes = x_slot(CH);  // slot pitch of the ring
+  constexpr int kStageFrames = kStageChunks * kUmmaChunkFrames;  // 64
+  constexpr uint32_t kRowBytes = kStageFrames * CH * 2;          // raw bytes of one stream in a stage box
+  constexpr uint32_t kRawBytes = kStreams * kRowBytes;           // 16 KB: the raw stage sits at the start of its slot
+  constexpr uint32_t kQuarterRow = kRowBytes / 4, kQuarterBytes = kRawBytes / 4;
+  static_assert(kRawBytes <= x_stage(CH) && kXStageBytes % 128 == 0, "a raw stage fits its slot; slots take TMA boxes");
   const uint32_t S = u.x_stages;
   const uint32_t n_iters = (u.ksteps + 1) / 2;  // 64-frame stages per tile
   uint8_t *const tap_smem = smem + S * kXStageBytes;
-  const uint32_t n_rows = IDS ? a.n_ids : a.n_streams;  // streams this launch covers
-  auto stream_of = [&](uint32_t i) -> size_t { return IDS ? a.ids[i] : i; };
+  const uint32_t n_rows = a.n_streams;
   auto tile_kf0 = [&](uint32_t t) -> int { return u.n_inline ? u.inl[t].kf0 : u.tiles[t].kf0; };
   auto tile_slot = [&](uint32_t t) -> uint32_t { return u.n_inline ? u.inl[t].slot : u.tiles[t].slot; };
-  // alignment every input row start shares (16-byte items start at multiples of 16 B in a row)
-  const uint32_t row_bits = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(a.in)) |
-                            (static_cast<uint32_t>(a.in_stride) * 2u);
-  const int in_align = FAST ? 16 : (row_bits & 15u) == 0 ? 16 : (row_bits & 7u) == 0 ? 8 : (row_bits & 3u) == 0 ? 4 : 2;
 
   // Programmatic dependent launch: the next call's grid may be scheduled as SMs drain; it blocks in
   // griddepcontrol.wait below until this grid has completed, before it touches PCM, history or output.
@@ -256,14 +289,15 @@ __global__ void __launch_bounds__(kThreads2, 1)
 
   // ---- prologue: the barriers, one per lane of the MMA warp; then everybody may proceed ----
   if (warp == kMmaWarp2) {
-    const uint32_t n_bar = 2 * S + n_iters + 6;
+    const uint32_t n_bar = 3 * S + n_iters + 4;
     for (uint32_t i = lane; i < n_bar; i += 32) {
-      if (i < S) mbar_init(&x_full[i], kGroupWarps);             // one elected arrival per warp of a group
-      else if (i < 2 * S) mbar_init(&x_empty[i - S], 1);
-      else if (i < 2 * S + n_iters) mbar_init(&tap_full[i - 2 * S], 1);
-      else if (i == 2 * S + n_iters) mbar_init(&taps_free, 1);
-      else if (i <= 2 * S + n_iters + 2) mbar_init(&acc_full[i - (2 * S + n_iters + 1)], 1);
-      else if (i <= 2 * S + n_iters + 4) mbar_init(&acc_empty[i - (2 * S + n_iters + 3)], kEpiWarps);
+      if (i < S) mbar_init(&raw_full[i], 1);                        // the loader's arrive + the box's bytes
+      else if (i < 2 * S) mbar_init(&x_full[i - S], kGroupWarps);   // one elected arrival per warp of a group
+      else if (i < 3 * S) mbar_init(&x_empty[i - 2 * S], 1);
+      else if (i < 3 * S + n_iters) mbar_init(&tap_full[i - 3 * S], 1);
+      else if (i == 3 * S + n_iters) mbar_init(&taps_free, 1);
+      else if (i == 3 * S + n_iters + 1) mbar_init(&acc_full, 1);
+      else if (i == 3 * S + n_iters + 2) mbar_init(&acc_empty, kConvWarps2);
       else mbar_init(&tmem_ready, 1);
     }
     fence_mbar_init();
@@ -282,23 +316,28 @@ __global__ void __launch_bounds__(kThreads2, 1)
   };
 
   if (warp < kConvWarps2) {
-    // ================= converters: PCM -> byte planes in UMMA layout =================
-    // A stage is 64 frames of 128 series = kStreams stream segments of 64*CH*2 bytes. Lanes of a warp
-    // walk ALONG a segment in 16-byte items (PPS items per stream, SPI streams per warp instruction),
-    // so one LDG.128 covers four full 128-byte lines; each thread owns kItems items per stage, item i
-    // of warp gw (of its group) belonging to stream (8 gw + i) * SPI + lane / PPS of the tile's group.
+    // ================= converters: raw PCM -> byte planes in UMMA layout, in place; epilogue =================
+    // A raw stage is kStreams rows of kRowBytes. Lanes of a warp walk ALONG a row in 16-byte items
+    // (PPS items per stream, SPI streams per warp instruction: conflict-free LDS.128); each thread owns
+    // kItems items per stage, item i of warp gw (of its group) belonging to stream
+    // (8 gw + i) * SPI + lane / PPS of the tile's group.
     constexpr int FPI = 8 / CH;          // frames per 16-byte item
     constexpr int PPS = 64 / FPI;        // items per stream per stage (16 stereo, 8 mono)
     constexpr int SPI = 32 / PPS;        // streams per warp instruction (2 stereo, 4 mono)
     constexpr int kItems = 8;
-    constexpr int kStageFrames = kStageChunks * kUmmaChunkFrames;  // 64
     const uint32_t group = static_cast<uint32_t>(warp) >> 2, gw = warp & 3;
-    const int conv_p = lane % PPS;       // item position inside the stage segment
-    // byte offset of item i's hi/left word(s) inside an X stage: conv_off0 + i * kItemStride
-    // (item i belongs to stream sl = (8 gw + i) * SPI + lane / PPS; stereo: left channel of stream sl
-    // -> row 2 sl, right channel -> row 2 sl + 1)
-    constexpr uint32_t kItemStride = SPI * 16 * CH;
+    const int conv_p = lane % PPS;       // item position inside the stream's row
     const uint32_t sl0 = static_cast<uint32_t>(8 * gw * SPI + lane / PPS);
+    // where item i sits in a raw stage: whole-stage box, or four quarter boxes (16 frames each)
+    const uint32_t raw_off0 = sl0 * kRowBytes + conv_p * 16;
+    constexpr uint32_t kRawItemStride = SPI * kRowBytes;
+    constexpr int kItemsPerQuarter = PPS / 4;
+    const uint32_t rawq_off0 = static_cast<uint32_t>(conv_p / kItemsPerQuarter) * kQuarterBytes + sl0 * kQuarterRow +
+                               static_cast<uint32_t>(conv_p % kItemsPerQuarter) * 16;
+    constexpr uint32_t kRawqItemStride = SPI * kQuarterRow;
+    // byte offset of item i's hi/left word(s) inside a converted stage: conv_off0 + i * kItemStride
+    // (stereo: left channel of stream sl -> row 2 sl, right channel -> row 2 sl + 1)
+    constexpr uint32_t kItemStride = SPI * 16 * CH;
     const uint32_t conv_off0 = [&] {
       const uint32_t j = static_cast<uint32_t>(conv_p * FPI) / kUmmaChunkFrames;
       const uint32_t byte_in_row = static_cast<uint32_t>(conv_p * FPI) % kUmmaChunkFrames;
@@ -306,178 +345,45 @@ __global__ void __launch_bounds__(kThreads2, 1)
     }();
     const uint32_t total_stages = n_tiles_mine * n_iters;
 
-    // fetch cursor: (tile index, stage) whose loads go out next; advances two stages at a time
-    uint32_t f_tile = 0, f_it = group;
-    while (f_it >= n_iters && f_tile < n_tiles_mine) {
-      f_it -= n_iters;
-      ++f_tile;
-    }
-    int f_kf0 = 0;
-    uint32_t f_sg0 = 0;  // first of this thread's streams in the fetch tile, as an index into the launch's rows
-    auto setup_fetch = [&]() {
-      const uint32_t w = w_begin + f_tile, t = w / G, g = w - t * G;
-      f_kf0 = tile_kf0(t);
-      f_sg0 = g * kStreams + sl0;
-    };
-    // row of the batch of item i (rows past the end of the batch read row 0; never stored)
-    auto item_row = [&](int i) -> size_t {
-      const uint32_t sg = f_sg0 + static_cast<uint32_t>(i * SPI);
-      return stream_of(sg < n_rows ? sg : 0);
-    };
-    auto fetch = [&](uint4 (&raw)[kItems]) {
-      if (f_tile >= n_tiles_mine) return;
-      const int f = f_kf0 + static_cast<int>(f_it) * kStageFrames + conv_p * FPI;  // this thread's first frame
-      const int rem = static_cast<int>(sc.n_in) - f;  // input frames left from f (when f >= 0)
-      if (f < 0) {
-#pragma unroll
-        for (int i = 0; i < kItems; ++i)
-          raw[i] = ld_pcm16(a.hist_src + item_row(i) * a.hist_stride + (static_cast<ptrdiff_t>(a.hist_frames) + f) * CH);
-      } else if (rem >= FPI && in_align == 16) {
-#pragma unroll
-        for (int i = 0; i < kItems; ++i)
-          raw[i] = ld_pcm16(a.in + item_row(i) * a.in_stride + static_cast<ptrdiff_t>(f) * CH);
-      } else if (rem <= 0) {
-#pragma unroll
-        for (int i = 0; i < kItems; ++i) raw[i] = make_uint4(0u, 0u, 0u, 0u);
-      } else {
-        // the item holding the end of the input, or rows less than 16-byte aligned
-#pragma unroll
-        for (int i = 0; i < kItems; ++i)
-          raw[i] = fetch_item_any(a.in + item_row(i) * a.in_stride + static_cast<ptrdiff_t>(f) * CH, min(rem, FPI) * CH,
-                                  in_align);
-      }
-      f_it += 2;
-      if (f_it >= n_iters) {
-        do {
-          f_it -= n_iters;
-          ++f_tile;
-        } while (f_it >= n_iters);
-        if (f_tile < n_tiles_mine) setup_fetch();
-      }
-    };
-    uint4 raw0[kItems], raw1[kItems];  // two of this warp's stages of loads in flight
-    // Everything above touched only kernel parameters and this CTA's own resources. The previous
-    // call's grid (which reads the history buffer this call overwrites, and writes the one this call
-    // reads) must have completed before any global access below.
-    if (tid == 0) TRACE2(u, 3);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (tid == 0) TRACE2(u, 4);
-    if (f_tile < n_tiles_mine) setup_fetch();
-
-    auto convert_store = [&](uint8_t *xs, const uint4 (&raw)[kItems]) {
-#pragma unroll
-      for (int i = 0; i < kItems; ++i) {
-        uint8_t *base = xs + conv_off0 + i * kItemStride;
-        const uint4 w = raw[i];
-        if (CH == 1) {
-          // 8 frames; word = (x[2k+1] << 16) | x[2k]: bytes lo0 hi0 lo1 hi1 -> 8 bytes per plane
-          const uint2 hi = make_uint2(__byte_perm(w.x, w.y, 0x7531), __byte_perm(w.z, w.w, 0x7531));
-          const uint2 lo = make_uint2(__byte_perm(w.x, w.y, 0x6420), __byte_perm(w.z, w.w, 0x6420));
-          *reinterpret_cast<uint2 *>(base) = hi;
-          *reinterpret_cast<uint2 *>(base + kXPlaneBytes) = lo;
-        } else {
-          // 4 frames; word f = (R_f << 16) | L_f -> one word per plane and channel (rows 2 sl, 2 sl + 1)
-          const uint32_t ul = __byte_perm(w.x, w.y, 0x5140), vl = __byte_perm(w.z, w.w, 0x5140);
-          const uint32_t ur = __byte_perm(w.x, w.y, 0x7362), vr = __byte_perm(w.z, w.w, 0x7362);
-          *reinterpret_cast<uint32_t *>(base) = __byte_perm(ul, vl, 0x7632);
-          *reinterpret_cast<uint32_t *>(base + 16) = __byte_perm(ur, vr, 0x7632);
-          *reinterpret_cast<uint32_t *>(base + kXPlaneBytes) = __byte_perm(ul, vl, 0x5410);
-          *reinterpret_cast<uint32_t *>(base + kXPlaneBytes + 16) = __byte_perm(ur, vr, 0x5410);
-        }
-      }
-    };
-
-    // ---- this warp's stages: q = group, group + 2, ... of the CTA's stage sequence ----
-    uint32_t slot = group % S, par = 1u ^ ((group / S) & 1u);  // ring slot of stage q, parity its `empty` wait expects
-#ifdef SPXB_UMMA2_TRACE
-    uint32_t step_no = 0;
-#define STEP_MARK(k) \
-  if (tid == 0 && step_no == n_iters + 3) TRACE2(u, 56 + (k))
-#else
-#define STEP_MARK(k)
-#endif
-    auto convert_step = [&](const uint4 (&raw)[kItems]) {
-      STEP_MARK(0);
-      mbar_wait(&x_empty[slot], par);
-      STEP_MARK(1);
-      convert_store(smem + slot * kXStageBytes, raw);
-      STEP_MARK(2);
-      // every thread makes its own stores visible to the async proxy, then one lane per warp arrives
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&x_full[slot]);
-      STEP_MARK(3);
-      slot += 2;
-      if (slot >= S) {
-        slot -= S;
-        par ^= 1u;
-      }
-    };
-    // The two register sets take turns strictly (never moved: a move of a register that a load in
-    // flight will write waits for that load).
-    fetch(raw0);
-    fetch(raw1);
-    if (tid == 0) TRACE2(u, 2);
-    for (uint32_t q = group; q < total_stages; q += 4) {
-      convert_step(raw0);
-      fetch(raw0);
-      STEP_MARK(4);
-#ifdef SPXB_UMMA2_TRACE
-      ++step_no;
-#endif
-      if (q + 2 >= total_stages) break;
-      convert_step(raw1);
-      fetch(raw1);
-#ifdef SPXB_UMMA2_TRACE
-      ++step_no;
-#endif
-    }
-    if (tid == 0) TRACE2(u, 10);
-  } else if (warp < kEpiWarp0 + kEpiWarps) {
-    // ================= epilogue: straight from TMEM to the interleaved int16 output =================
-    // A lane owns one series (TMEM lane) and 16 consecutive outputs per column group; mono packs them
+    // ---- epilogue of one tile: straight from TMEM to the interleaved int16 output ----
+    // a lane owns one series (TMEM lane) and 16 consecutive outputs per column group; mono packs them
     // into 32 contiguous bytes, stereo first swaps halves with the neighbouring lane (the other
     // channel of the same stream) so that each lane of the pair holds 8 whole frames = 32 bytes.
-    // (Groups of 8 columns took 1.7x as long: an iteration costs ~600 cycles of TMEM-load and
-    // dependent-arithmetic latency whatever its width.)
-    const uint32_t out_bits = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(a.out)) |
-                              (static_cast<uint32_t>(a.out_stride) * 2u);
-    const int out_align = FAST ? 16 : (out_bits & 15u) == 0 ? 16 : (out_bits & 3u) == 0 ? 4 : 2;
-    const uint32_t quarter = static_cast<uint32_t>(warp) & 3u;
-    const uint32_t row = quarter * 32 + lane;  // TMEM lane = series of the tile
+    // The two warps of a TMEM lane quarter (one of each group) share the column groups.
+    const uint32_t row = gw * 32 + lane;  // TMEM lane = series of the tile
     const uint32_t sl_out = CH == 2 ? row >> 1 : row, ch_out = CH == 2 ? (row & 1u) : 0u;
-    // the previous call's grid may still be writing the output rows this call overwrites
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    mbar_wait(&tmem_ready, 0);
-    tc_fence_after_sync();
-    const uint32_t tmem = tmem_slot;
-    const uint32_t lane_base = tmem + ((quarter * 32u) << 16);
-    uint32_t buf = 0, use_par = 0;  // accumulator set of the tile, parity of its `full` barrier
-    for (uint32_t tile_no = 0; tile_no < n_tiles_mine; ++tile_no) {
+    uint32_t tmem = 0;
+    auto epilogue = [&](uint32_t tile_no) {
       const uint32_t w = w_begin + tile_no, t = w / G, g = w - t * G;
       const uint32_t m0 = t * nt;
       const uint32_t n_valid = min(nt, sc.n_out - m0);
       const uint32_t s_out = g * kStreams + sl_out;
       const bool live_out = s_out < n_rows;
-      int16_t *out_row = a.out + stream_of(live_out ? s_out : 0) * a.out_stride + static_cast<size_t>(m0) * CH;
-      if (lane == 0 && quarter == 0) TRACE2(u, 16 + 8 * min(tile_no, 4u) + 1);
-      mbar_wait(&acc_full[buf], use_par);
+      int16_t *out_row = a.out + static_cast<size_t>(live_out ? s_out : 0) * a.out_stride + static_cast<size_t>(m0) * CH;
+      if (tile_no == 0) {
+        WAIT(&tmem_ready, 0, 0x01000000u);
+        tc_fence_after_sync();
+        tmem = tmem_slot;
+      }
+      PROG(5u, tile_no);
+      if (tid == 0) TRACE2(u, 16 + 8 * min(tile_no, 4u) + 1);
+      WAIT(&acc_full, tile_no & 1u, 0x02000000u | tile_no);
       tc_fence_after_sync();
-      const uint32_t lane_addr = lane_base + buf * 4u * nt;
+      const uint32_t lane_addr = tmem + ((gw * 32u) << 16);
       const uint32_t cg_end = (n_valid + 15) / 16;
-      for (uint32_t cg = 0; cg < cg_end; ++cg) {
+      for (uint32_t cg = group; cg < cg_end; cg += 2) {
         uint32_t p0[16], p1[16], p2[16], p3[16];
         tmem_ld16(lane_addr + cg * 16, p0);
         tmem_ld16(lane_addr + nt + cg * 16, p1);
         tmem_ld16(lane_addr + 2 * nt + cg * 16, p2);
         tmem_ld16(lane_addr + 3 * nt + cg * 16, p3);
         tmem_ld_wait();
-        if (cg + 1 == cg_end) {
-          // this warp's last read of the accumulator set: hand it back before the arithmetic and
-          // the stores of this group
+        if (cg + 2 >= cg_end) {
+          // this warp's last read of the accumulator: hand it back before the arithmetic and the
+          // stores of this group, so the next tile's MMAs start underneath them
           tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          if (lane == 0) mbar_arrive(&acc_empty);
         }
         int r16[16];
         combine16(p0, p1, p2, p3, u.shift, r16);  // rounded, not yet saturated
@@ -501,10 +407,12 @@ __global__ void __launch_bounds__(kThreads2, 1)
         const uint32_t total = n_valid * CH;
         const uint32_t n_here = first_elem >= total ? 0u : min(16u, total - first_elem);  // int16 elements
         int16_t *dst = out_row + first_elem;
-        if (n_here == 16 && out_align == 16) {
+        if (n_here == 16) {
           reinterpret_cast<uint4 *>(dst)[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
           reinterpret_cast<uint4 *>(dst)[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
-        } else if (out_align >= 4) {
+        } else {
+          // the ragged end of the call's output: rows are 16-byte aligned, so whole 32-bit words, then
+          // possibly one last int16
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (2u * j + 1 < n_here) reinterpret_cast<uint32_t *>(dst)[j] = wv[j];
@@ -513,20 +421,126 @@ __global__ void __launch_bounds__(kThreads2, 1)
             for (int j = 0; j < 8; ++j)
               if (2u * j + 1 == n_here) dst[2 * j] = static_cast<int16_t>(wv[j] & 0xffffu);
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (2u * j < n_here) dst[2 * j] = static_cast<int16_t>(wv[j] & 0xffffu);
-            if (2u * j + 1 < n_here) dst[2 * j + 1] = static_cast<int16_t>(wv[j] >> 16);
-          }
         }
       }
-      if (lane == 0 && quarter == 0) TRACE2(u, 16 + 8 * min(tile_no, 4u) + 3);
-      if (++buf == u.n_acc) {
-        buf = 0;
-        use_par ^= 1u;
+      if (group >= cg_end) {
+        // (a warp with no column group in this tile still owes its arrival)
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty);
+      }
+      PROG(6u, tile_no);
+      if (tid == 0) TRACE2(u, 16 + 8 * min(tile_no, 4u) + 3);
+    };
+
+    // The previous call's grid may still be writing the output rows this call overwrites.
+    if (tid == 0) TRACE2(u, 3);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid == 0) TRACE2(u, 4);
+
+    // ---- this group's stages: q = group, group + 2, ... of the CTA's stage sequence ----
+    // Every thread watches EVERY phase of the raw_full barriers in order, also those of the other
+    // group's stages: a parity wait tells "this phase" from "the one before" only. With an odd number
+    // of slots a group meets a slot every other time it is used; skipping a phase would let the wait
+    // for use k + 1 be satisfied by the completion of use k - 1 (seen as a hang, then a fault, on the
+    // first shape that got three slots).
+    uint32_t slot = 0, par = 0;         // ring slot of stage q, parity of its raw_full phase
+    uint32_t c_tile = 0, c_it = 0;      // (tile, stage) of stage q
+    uint32_t done_tile = 0;             // tiles whose epilogue this warp has run
+    int c_kf0 = 0;
+    bool have_kf0 = false;
+#ifdef SPXB_UMMA2_TRACE
+    uint32_t step_no = 0;
+#define STEP_MARK(k) \
+  if (tid == 0 && step_no == n_iters / 2 + 2) TRACE2(u, 56 + (k))
+#else
+#define STEP_MARK(k)
+#endif
+    for (uint32_t q = 0; q < total_stages; ++q, ++c_it) {
+      if ((q & 1u) != group) {
+        // the other group's stage: only follow the barrier
+        WAIT(&raw_full[slot], par, 0x09000000u | (slot << 20) | (par << 16) | q);
+        if (++slot == S) {
+          slot = 0;
+          par ^= 1u;
+        }
+        continue;
+      }
+      while (c_it >= n_iters) {
+        c_it -= n_iters;
+        ++c_tile;
+        have_kf0 = false;
+      }
+      // every stage of the tiles before c_tile is stored: their epilogues are due (the MMAs of
+      // c_tile cannot start before the accumulator of c_tile - 1 has been read out)
+      while (done_tile < c_tile) epilogue(done_tile++);
+      if (!have_kf0) {
+        c_kf0 = tile_kf0((w_begin + c_tile) / G);
+        have_kf0 = true;
+      }
+      const int f0 = c_kf0 + static_cast<int>(c_it) * kStageFrames;
+      const bool quarters = f0 < 0 && f0 + kStageFrames > 0;  // the stage that straddles the end of the history
+      uint8_t *xs = smem + slot * kXStageBytes;
+      STEP_MARK(0);
+      PROG(1u, q);
+      WAIT(&raw_full[slot], par, 0x03000000u | (slot << 20) | (par << 16) | q);
+      STEP_MARK(1);
+      const uint8_t *rp = xs + (quarters ? rawq_off0 : raw_off0);
+      const uint32_t rstride = quarters ? kRawqItemStride : kRawItemStride;
+      uint4 w[kItems];
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) w[i] = *reinterpret_cast<const uint4 *>(rp + i * rstride);
+      // split into the byte planes (in registers: the values depend on the loads, so every raw byte
+      // of this thread has been read when it reaches the barrier)
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) {
+        const uint4 v = w[i];
+        if (CH == 1) {
+          // 8 frames; word = (x[2k+1] << 16) | x[2k]: bytes lo0 hi0 lo1 hi1 -> 8 bytes per plane
+          w[i] = make_uint4(__byte_perm(v.x, v.y, 0x7531), __byte_perm(v.z, v.w, 0x7531),
+                            __byte_perm(v.x, v.y, 0x6420), __byte_perm(v.z, v.w, 0x6420));
+        } else {
+          // 4 frames; word f = (R_f << 16) | L_f -> one word per plane and channel (rows 2 sl, 2 sl + 1)
+          const uint32_t ul = __byte_perm(v.x, v.y, 0x5140), vl = __byte_perm(v.z, v.w, 0x5140);
+          const uint32_t ur = __byte_perm(v.x, v.y, 0x7362), vr = __byte_perm(v.z, v.w, 0x7362);
+          w[i] = make_uint4(__byte_perm(ul, vl, 0x7632), __byte_perm(ur, vr, 0x7632),
+                            __byte_perm(ul, vl, 0x5410), __byte_perm(ur, vr, 0x5410));
+        }
+      }
+      PROG(2u, q);
+      group_sync(group);  // every thread of the group holds its share of the slot in registers
+      STEP_MARK(2);
+      PROG(3u, q);
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) {
+        uint8_t *base = xs + conv_off0 + i * kItemStride;
+        if (CH == 1) {
+          *reinterpret_cast<uint2 *>(base) = make_uint2(w[i].x, w[i].y);
+          *reinterpret_cast<uint2 *>(base + kXPlaneBytes) = make_uint2(w[i].z, w[i].w);
+        } else {
+          *reinterpret_cast<uint32_t *>(base) = w[i].x;
+          *reinterpret_cast<uint32_t *>(base + 16) = w[i].y;
+          *reinterpret_cast<uint32_t *>(base + kXPlaneBytes) = w[i].z;
+          *reinterpret_cast<uint32_t *>(base + kXPlaneBytes + 16) = w[i].w;
+        }
+      }
+      STEP_MARK(3);
+      // every thread makes its own stores visible to the async proxy, then one lane per warp arrives
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&x_full[slot]);
+      PROG(4u, q);
+      STEP_MARK(4);
+#ifdef SPXB_UMMA2_TRACE
+      ++step_no;
+#endif
+      if (++slot == S) {
+        slot = 0;
+        par ^= 1u;
       }
     }
+    while (done_tile < n_tiles_mine) epilogue(done_tile++);
+    if (tid == 0) TRACE2(u, 10);
   } else if (warp == kMmaWarp2) {
     // ================= MMA issue =================
     // The whole warp walks the tiles and stages (uniform control flow, descriptors in uniform
@@ -541,7 +555,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_ready);
     tc_fence_after_sync();
-    const uint32_t tmem = tmem_slot;
+    const uint32_t acc = tmem_slot;
     const uint32_t n3 = 3 * nt;
     const uint32_t np0 = min(n3, 256u), np1 = n3 - np0;            // [0, 3nt)
     const uint32_t nq0 = min(2 * nt, 256u), nq1 = 2 * nt - nq0;    // [0, 2nt) (first K step, lo plane)
@@ -552,7 +566,6 @@ __global__ void __launch_bounds__(kThreads2, 1)
     const uint64_t b_fixed = umma_smem_desc(smem_u32(tap_smem), 0, 128);
     constexpr uint32_t a_stage16 = kXStageBytes >> 4, a_lo16 = kXPlaneBytes >> 4;
     uint32_t slot = 0, par = 0, tile_no = 0, run = 0;
-    uint32_t buf = 0, buf_use = 0;  // accumulator set of the tile, how many times it has been used before
     uint64_t a_st = a_base;
     uint32_t cur_t = 0xffffffffu;
     for (uint32_t w = w_begin; w < w_end; ++w, ++tile_no) {
@@ -563,7 +576,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
         if (run) {
           // every MMA that reads the resident tile has completed (this warp's own commit at the end
           // of the previous run): load the tile of the new run
-          mbar_wait(&taps_free, (run - 1) & 1u);
+          WAIT(&taps_free, (run - 1) & 1u, 0x04000000u | run);
           load_tap_tile(t);
         }
         cur_t = t;
@@ -572,18 +585,19 @@ __global__ void __launch_bounds__(kThreads2, 1)
       }
       const bool run_ends = w + 1 == w_end || (w + 1) / G != t;
       const uint32_t tr = 16 + 8 * min(tile_no, 4u);  // trace slots of this tile
-      if (buf_use) {
-        // the epilogue has read this set's previous tile out of TMEM
-        mbar_wait(&acc_empty[buf], (buf_use - 1) & 1u);
+      if (tile_no) {
+        // the epilogue has read the previous tile's accumulator out of TMEM
+        WAIT(&acc_empty, (tile_no - 1) & 1u, 0x05000000u | tile_no);
         tc_fence_after_sync();
       }
-      const uint32_t acc = tmem + buf * 4u * nt;
       if (lane == 0) TRACE2(u, tr + 4);
       for (uint32_t it = 0; it < n_iters; ++it) {
         if (tile_no == 1 && it < 16 && lane == 0) TRACE2(u, 64 + 3 * it);
-        if (new_run) mbar_wait(&tap_full[it], tap_par);
-        mbar_wait(&x_full[slot], par);
+        PROG(1u, (tile_no << 8) | it);
+        if (new_run) WAIT(&tap_full[it], tap_par, 0x06000000u | (it << 8) | run);
+        WAIT(&x_full[slot], par, 0x07000000u | (slot << 20) | (par << 16) | (tile_no << 8) | it);
         tc_fence_after_sync();
+        PROG(2u, (tile_no << 8) | it);
         if (tile_no == 1 && it < 16 && lane == 0) TRACE2(u, 65 + 3 * it);
         if (it == 0 && lane == 0) TRACE2(u, tr + 5);
         const bool last = it + 1 == n_iters;
@@ -600,8 +614,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
           }
           if (u.dense) {
             // one MMA pair per K step, every operand a constant step from the previous one: nothing
-            // but uniform adds between the MMAs (the record walk below costs ~100 cycles of dependent
-            // uniform loads and arithmetic per MMA -- more than the tensor pipe needs to run one)
+            // but uniform adds between the MMAs
             const uint32_t id_h3 = with_n(id_hi, n3), id_l3 = with_n(id_lo, n3);
             const uint64_t b_row = b_fixed + (static_cast<uint64_t>(n3) << 16);
 #pragma unroll
@@ -616,10 +629,14 @@ __global__ void __launch_bounds__(kThreads2, 1)
 #endif
             }
           } else {
+            // The record walk, one record ahead: the uniform loads of record m + 1 are issued before
+            // the MMAs of record m, so their latency is not part of the chain between two MMAs.
             const uint32_t m_end = u.stage_rec[it + 1];
+            uint32_t m = u.stage_rec[it];
+            uint32_t rb = u.rec[m].b, ri = u.rec[m].idesc_hi, rd = u.rec[m].d_a;
 #pragma unroll 1
-            for (uint32_t m = u.stage_rec[it]; m < m_end; ++m) {
-              const uint32_t rb = u.rec[m].b, ri = u.rec[m].idesc_hi, rd = u.rec[m].d_a;
+            for (; m < m_end; ++m) {
+              const uint32_t nb = u.rec[m + 1].b, ni = u.rec[m + 1].idesc_hi, nd = u.rec[m + 1].d_a;
               const uint64_t b = b_fixed + rb;
               const uint64_t a_hi = a_st + (rd >> 16);
               const uint32_t d_hi = acc + (rd & 0xffffu);
@@ -629,15 +646,19 @@ __global__ void __launch_bounds__(kThreads2, 1)
 #else
               if (b == 1 && a_hi == 2 && d_hi == 3) umma_i8(d_hi, a_hi, b, ri, 1u);  // timing experiment: no MMAs
 #endif
+              rb = nb;
+              ri = ni;
+              rd = nd;
             }
           }
           umma_commit(&x_empty[slot]);
           if (last) {
-            umma_commit(&acc_full[buf]);
+            umma_commit(&acc_full);
             if (run_ends) umma_commit(&taps_free);
           }
         }
         __syncwarp();
+        PROG(3u, (tile_no << 8) | it);
         if (tile_no == 1 && it < 16 && lane == 0) TRACE2(u, 66 + 3 * it);
         if (last && lane == 0) TRACE2(u, tr + 6);
         a_st += a_stage16;
@@ -647,17 +668,48 @@ __global__ void __launch_bounds__(kThreads2, 1)
           a_st = a_base;
         }
       }
-      if (++buf == u.n_acc) {
-        buf = 0;
-        ++buf_use;
-      }
     }
     if (lane == 0) TRACE2(u, 11);
-  } else if (warp == kSpareWarp) {
-    // ================= spare warp: pull the MMA records into the constant cache =================
-    uint32_t acc = 0;
-    for (uint32_t i = lane * 4; i <= u.n_rec; i += 32 * 4) acc ^= u.rec[i].b;  // one read per 64-byte line
-    if (acc == 0xdeadbeefu && u.n_rec == 0xffffffffu) a.samp_frac[0] = acc;     // (keeps the reads alive)
+  } else if (warp == kLoadWarp) {
+    // ================= loader: one TMA box of raw PCM per stage =================
+    if (lane == 0) {
+      // the previous call's grid wrote the history this call reads
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      uint32_t slot = 0, par = 1;  // a fresh barrier passes a wait on the phase "before the first"
+      const int hist_frames = static_cast<int>(a.hist_frames);
+      for (uint32_t tile_no = 0; tile_no < n_tiles_mine; ++tile_no) {
+        const uint32_t w = w_begin + tile_no, t = w / G, g = w - t * G;
+        const int kf0 = tile_kf0(t);
+        const int row0 = static_cast<int>(g * kStreams);
+        for (uint32_t it = 0; it < n_iters; ++it) {
+          WAIT_L(&x_empty[slot], par, 0x08000000u | (slot << 20) | (par << 16) | (tile_no << 8) | it);
+          uint8_t *dst = smem + slot * kXStageBytes;
+          const int f0 = kf0 + static_cast<int>(it) * kStageFrames;
+#ifdef SPXB_DBG_NOLOAD
+          mbar_arrive(&raw_full[slot]);  // timing experiment: no PCM traffic
+#else
+          mbar_arrive_expect_tx(&raw_full[slot], kRawBytes);
+#endif
+          if (f0 >= 0) {
+            tma_box_2d(dst, &maps.in64, f0 * CH * 2, row0, &raw_full[slot]);
+          } else if (f0 + kStageFrames <= 0) {
+            tma_box_2d(dst, &maps.hist64, (hist_frames + f0) * CH * 2, row0, &raw_full[slot]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int f = f0 + 16 * j;
+              if (f < 0) tma_box_2d(dst + j * kQuarterBytes, &maps.hist16, (hist_frames + f) * CH * 2, row0, &raw_full[slot]);
+              else tma_box_2d(dst + j * kQuarterBytes, &maps.in16, f * CH * 2, row0, &raw_full[slot]);
+            }
+          }
+          if (tile_no == 0 && it == 0) TRACE2(u, 2);
+          if (++slot == S) {
+            slot = 0;
+            par ^= 1u;
+          }
+        }
+      }
+    }
   } else {
     // ================= history slide (resample.c:898-899) and the new position =================
     // Runs beside the FIR: it reads the old history and this call's input, writes the other half
@@ -666,8 +718,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t hist_elems = a.hist_frames * CH;
     const size_t shift = static_cast<size_t>(sc.consumed) * CH;
-    const int vshift = (shift % 8 == 0) ? 8 : (shift % 4 == 0) ? 4 : (shift % 2 == 0) ? 2 : 1;
-    const int vw = min(vshift, in_align / 2);
+    const int vw = (shift % 8 == 0) ? 8 : (shift % 4 == 0) ? 4 : (shift % 2 == 0) ? 2 : 1;
     const uint32_t hw = static_cast<uint32_t>(warp - kHistWarp0);  // the history warps take turns at units of 4 streams
     for (uint32_t w = w_begin; w < w_end; ++w) {
       const uint32_t t = w / G, g = w - t * G;
@@ -676,12 +727,12 @@ __global__ void __launch_bounds__(kThreads2, 1)
       const uint32_t in_group = (kStreams - t + T - 1) / T;
       const uint32_t in_batch = first < n_rows ? (n_rows - first + T - 1) / T : 0u;
       const uint32_t n_mine = min(in_group, in_batch);
-      if (vw == 8) slide_streams<uint4, IDS>(a, T, first, n_mine, hist_elems, shift, lane, hw, kHistWarps);
-      else if (vw == 4) slide_streams<uint2, IDS>(a, T, first, n_mine, hist_elems, shift, lane, hw, kHistWarps);
-      else if (vw == 2) slide_streams<uint32_t, IDS>(a, T, first, n_mine, hist_elems, shift, lane, hw, kHistWarps);
-      else slide_streams<uint16_t, IDS>(a, T, first, n_mine, hist_elems, shift, lane, hw, kHistWarps);
+      if (vw == 8) slide_streams<uint4>(a, T, first, n_mine, hist_elems, shift, lane, hw, kHistWarps);
+      else if (vw == 4) slide_streams<uint2>(a, T, first, n_mine, hist_elems, shift, lane, hw, kHistWarps);
+      else if (vw == 2) slide_streams<uint32_t>(a, T, first, n_mine, hist_elems, shift, lane, hw, kHistWarps);
+      else slide_streams<uint16_t>(a, T, first, n_mine, hist_elems, shift, lane, hw, kHistWarps);
       for (uint32_t k = lane + 32 * hw; k < n_mine; k += 32 * kHistWarps) {
-        const size_t s = stream_of(first + k * T);
+        const size_t s = first + static_cast<size_t>(k) * T;
         a.last_sample[s] = sc.ls1;
         a.samp_frac[s] = sc.frac1;
       }
@@ -754,13 +805,66 @@ __global__ void build_packed_tiles_kernel(const int32_t *__restrict__ h, uint32_
 
 void umma2_configure_device() {
   auto big_smem = [](auto kernel) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem2); };
-  big_smem(umma2_fir_kernel<1, false, false>);
-  big_smem(umma2_fir_kernel<2, false, false>);
-  big_smem(umma2_fir_kernel<1, true, false>);
-  big_smem(umma2_fir_kernel<2, true, false>);
-  big_smem(umma2_fir_kernel<1, false, true>);
-  big_smem(umma2_fir_kernel<2, false, true>);
+  big_smem(umma2_fir_kernel<1>);
+  big_smem(umma2_fir_kernel<2>);
 }
+
+// what the TMA-fed kernel needs of a call: the whole batch (no stream subset), an input to read, and
+// every row -- input, output, history -- starting on a 16-byte boundary
+bool umma2_covers(const CallArgs &a) {
+  if (a.ids != nullptr || a.uniform.n_in == 0) return false;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(a.in) | (a.in_stride * 2u) | reinterpret_cast<uintptr_t>(a.out) |
+                         (a.out_stride * 2u) | reinterpret_cast<uintptr_t>(a.hist_src) | (a.hist_stride * 2u);
+  return (bits & 15u) == 0;
+}
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+#ifdef SPXB_UMMA2_WATCHDOG
+unsigned long long *g_wd = nullptr;
+void wd_dump() {
+  static unsigned long long seen = 0;
+  if (!g_wd) return;
+  unsigned long long n = *reinterpret_cast<volatile unsigned long long *>(g_wd);
+  if (n > 500) n = 500;
+  for (; seen < n; ++seen) {
+    const unsigned long long r = g_wd[1 + seen];
+    fprintf(stderr, "watchdog: cta %llu thread %llu (warp %llu) tag %08llx\n", r >> 48, (r >> 32) & 0xffff, ((r >> 32) & 0xffff) / 32, r & 0xffffffffull);
+  }
+}
+#endif
+
+EncodeTiledFn encode_tiled() {
+  static const EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// bytes x rows view of `rows` PCM rows of `row_bytes` valid bytes, `pitch` bytes apart; box = box_bytes x box_rows
+bool pcm_map(CUtensorMap *m, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch, uint32_t box_bytes,
+             uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn || row_bytes == 0 || rows == 0) return false;
+  const cuuint64_t gdim[2] = {row_bytes, rows};
+  const cuuint64_t gstride[1] = {pitch};
+  const cuuint32_t box[2] = {box_bytes, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
 
 // the MMA records and per-stage tables the kernel reads (they travel in the kernel parameters)
 cudaError_t umma2_upload_plan(UmmaContext *c, cudaStream_t) {
@@ -772,10 +876,10 @@ cudaError_t umma2_upload_plan(UmmaContext *c, cudaStream_t) {
   c->stage_mid.assign(kMaxTapStages + 2, 0u);
   for (uint32_t it = 0; it < n_iters; ++it) {
     c->stage_off[it] = c->packed.k[2 * it].off16 * 16u;
-    c->stage_rec[it] = static_cast<uint16_t>(c->recs.size() / 4);
+    c->stage_rec[it] = static_cast<uint16_t>(c->recs.size() / 3);
     for (uint32_t h = 0; h < 2; ++h) {
       const uint32_t k = 2 * it + h;
-      if (h == 1) c->stage_mid[it] = static_cast<uint16_t>(c->recs.size() / 4);
+      if (h == 1) c->stage_mid[it] = static_cast<uint16_t>(c->recs.size() / 3);
       if (k >= c->ksteps) break;
       const UmmaKStep &ks = c->packed.k[k];
       if (k == 0) continue;  // K step 0 has its own code in the kernel
@@ -783,18 +887,17 @@ cudaError_t umma2_upload_plan(UmmaContext *c, cudaStream_t) {
         c->recs.push_back((ks.off16 + ks.ent[e].row) | (static_cast<uint32_t>(ks.rows) << 16));
         c->recs.push_back(umma_idesc_i8(128, ks.ent[e].n, true, true));
         c->recs.push_back(ks.ent[e].dcol | ((h ? a_ks16 : 0u) << 16));
-        c->recs.push_back(0u);
       }
     }
   }
   for (uint32_t it = n_iters; it <= kMaxTapStages; ++it) c->stage_off[it] = c->packed.tile_bytes;
-  for (uint32_t it = n_iters; it < kMaxTapStages + 2; ++it) c->stage_rec[it] = static_cast<uint16_t>(c->recs.size() / 4);
-  return c->recs.size() / 4 <= kMaxRecs ? cudaSuccess : cudaErrorInvalidValue;
+  for (uint32_t it = n_iters; it < kMaxTapStages + 2; ++it) c->stage_rec[it] = static_cast<uint16_t>(c->recs.size() / 3);
+  return c->recs.size() / 3 <= kMaxRecs ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 // x stages the resident kernel would run for this geometry (0: the packed tile does not fit)
 uint32_t umma2_x_stages(uint32_t channels, uint32_t tile_bytes, uint32_t ksteps) {
-  const uint32_t xs = x_stage(static_cast<int>(channels));
+  const uint32_t xs = x_slot(static_cast<int>(channels));
   if (ksteps > kUmmaMaxKsteps || tile_bytes + 2 * xs > kMaxSmem2) return 0;
   const uint32_t n_iters = (ksteps + 1) / 2;
   uint32_t stages = std::min<uint32_t>(kMaxXStages, (kMaxSmem2 - tile_bytes) / xs);
@@ -834,7 +937,6 @@ cudaError_t launch_umma2(UmmaContext *c, const CallArgs &a, cudaStream_t stream,
   u.ksteps = c->ksteps;
   u.x_stages = c->stages;
   u.tmem_cols = c->tmem_cols;
-  u.n_acc = c->n_acc;
   u.dense = 3 * c->nt <= 256 ? 1u : 0u;
   for (uint32_t k = 0; k < c->ksteps && u.dense; ++k) {
     const UmmaKStep &ks = c->packed.k[k];
@@ -842,12 +944,24 @@ cudaError_t launch_umma2(UmmaContext *c, const CallArgs &a, cudaStream_t stream,
       u.dense = 0u;
   }
   u.shift = c->ft.shift;
-  u.n_rec = static_cast<uint32_t>(c->recs.size() / 4);
+  u.n_rec = static_cast<uint32_t>(c->recs.size() / 3);
   std::memcpy(u.rec, c->recs.data(), c->recs.size() * sizeof(uint32_t));
   for (uint32_t i = 0; i <= kMaxTapStages; ++i) u.stage_off[i] = c->stage_off[i];
   for (uint32_t i = 0; i < kMaxTapStages + 2; ++i) u.stage_rec[i] = c->stage_rec[i];
   for (uint32_t i = 0; i < kMaxTapStages + 2; ++i) u.stage_mid[i] = c->stage_mid[i];
   u.trace = nullptr;
+#ifdef SPXB_UMMA2_WATCHDOG
+  {
+    static unsigned long long *d_dbg = nullptr;
+    if (!g_wd && cudaHostAlloc(reinterpret_cast<void **>(&g_wd), 512 * 8, cudaHostAllocMapped) == cudaSuccess) {
+      std::memset(g_wd, 0, 512 * 8);
+      cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_dbg), g_wd, 0);
+      atexit(wd_dump);
+    }
+    wd_dump();
+    u.trace = d_dbg;
+  }
+#endif
 #ifdef SPXB_UMMA2_TRACE
   static const bool want_trace = getenv("SPXB_UMMA_TRACE") != nullptr;
   const uint32_t grid_for_trace = static_cast<uint32_t>(std::min<uint64_t>(work, static_cast<uint64_t>(c->sm_count)));
@@ -880,18 +994,19 @@ cudaError_t launch_umma2(UmmaContext *c, const CallArgs &a, cudaStream_t stream,
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  const uintptr_t row_bits = reinterpret_cast<uintptr_t>(a.in) | (a.in_stride * 2u) |
-                             reinterpret_cast<uintptr_t>(a.out) | (a.out_stride * 2u);
-  const bool fast = (row_bits & 15u) == 0;
-  auto launch = [&](auto kernel) { return cudaLaunchKernelEx(&cfg, kernel, a, u); };
-  cudaError_t e;
-  if (a.ids) {
-    e = a.channels == 2 ? launch(umma2_fir_kernel<2, false, true>) : launch(umma2_fir_kernel<1, false, true>);
-  } else if (a.channels == 2) {
-    e = fast ? launch(umma2_fir_kernel<2, true, false>) : launch(umma2_fir_kernel<2, false, false>);
-  } else {
-    e = fast ? launch(umma2_fir_kernel<1, true, false>) : launch(umma2_fir_kernel<1, false, false>);
-  }
+  if (!umma2_covers(a)) return cudaErrorNotSupported;  // (umma_prepare only plans this kernel for calls it covers)
+  // Tensor maps over this call's input and history rows. Host arithmetic only; they travel in the
+  // kernel parameters, so a captured launch keeps its own.
+  Umma2Maps maps;
+  const uint32_t ch = a.channels, streams = kUmmaRows / ch, row_box = 64 * ch * 2;
+  const uint64_t in_bytes = static_cast<uint64_t>(a.uniform.n_in) * ch * 2, hist_bytes = static_cast<uint64_t>(a.hist_frames) * ch * 2;
+  if (!pcm_map(&maps.in64, a.in, in_bytes, a.n_streams, a.in_stride * 2, row_box, streams) ||
+      !pcm_map(&maps.in16, a.in, in_bytes, a.n_streams, a.in_stride * 2, row_box / 4, streams) ||
+      !pcm_map(&maps.hist64, a.hist_src, hist_bytes, a.n_streams, static_cast<uint64_t>(a.hist_stride) * 2, row_box, streams) ||
+      !pcm_map(&maps.hist16, a.hist_src, hist_bytes, a.n_streams, static_cast<uint64_t>(a.hist_stride) * 2, row_box / 4, streams))
+    return cudaErrorInvalidValue;
+  cudaError_t e = a.channels == 2 ? cudaLaunchKernelEx(&cfg, umma2_fir_kernel<2>, a, u, maps)
+                                  : cudaLaunchKernelEx(&cfg, umma2_fir_kernel<1>, a, u, maps);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e == cudaSuccess) c->fresh_plan = false;
   if (e == cudaSuccess && launches) *launches += 1;

@@ -29,6 +29,8 @@ __host__ __device__ constexpr uint32_t x_lbo(int ch) { return kUmmaRows * 16 + (
 __host__ __device__ constexpr uint32_t x_kstep(int ch) { return 2 * x_lbo(ch) + (ch == 2 ? 16 : 0); }
 __host__ __device__ constexpr uint32_t x_plane(int ch) { return 2 * x_kstep(ch); }
 __host__ __device__ constexpr uint32_t x_stage(int ch) { return 2 * x_plane(ch); }  // hi + lo planes
+// ring slot of the TMA-fed kernel: a converted stage, rounded up so that every slot can take a TMA box
+__host__ __device__ constexpr uint32_t x_slot(int ch) { return (x_stage(ch) + 127u) & ~127u; }
 constexpr uint32_t kMaxSmem = 227u * 1024u - 2048u;              // dynamic part; barriers are static
 
 // 16 bytes of one stream's input, sample by sample: the first `n` int16 samples at p, zeros after
