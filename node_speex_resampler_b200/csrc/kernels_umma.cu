@@ -796,13 +796,17 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
   const uint32_t n_rows = a.ids ? a.n_ids : a.n_streams;
   const uint32_t n_groups = (n_rows * a.channels + kUmmaRows - 1) / kUmmaRows;
   const StreamCall &sc = a.uniform;
-  // the persistent, TMA-fed kernel is opt-in (SPXB_UMMA_RESIDENT=1) and covers whole batches with
-  // 16-byte aligned rows; a call it does not cover re-plans for the one-tile-per-CTA kernel
-  static const bool allow_resident = [] {
+  // Which tensor kernel: the persistent, TMA-fed one (kernels_umma2.cu) for long filters -- 8 or more
+  // 64-frame stages per tile, where a stage's fixed costs and the PCM path dominate (C4 -9 %, C5 -10 %)
+  // -- when the call is one it covers (whole batch, 16-byte aligned rows); the one-tile-per-CTA kernel
+  // otherwise (short filters such as C3 are a single wave of a few stages per CTA; there its shorter
+  // prologue wins, 6.3 vs 6.9 us). SPXB_UMMA_RESIDENT=0 / 1 forces the choice.
+  static const int force_resident = [] {
     const char *e = getenv("SPXB_UMMA_RESIDENT");
-    return e && atoi(e) != 0;
+    return e ? (atoi(e) != 0 ? 1 : 0) : -1;
   }();
-  const bool want_resident = allow_resident && umma2_covers(a);
+  const bool long_filter = umma_ksteps(c->spec.taps, c->spec.num, c->spec.den, 64) >= 15;
+  const bool want_resident = (force_resident == 1 || (force_resident < 0 && long_filter)) && umma2_covers(a);
   if (c->memo && c->m_ls0 == sc.ls0 && c->m_frac0 == sc.frac0 && c->m_n_out == sc.n_out &&
       c->m_hist_frames == a.hist_frames && c->m_groups == n_groups && c->resident_wanted == want_resident) {
     return true;  // steady state: same tiles as the previous call
@@ -844,6 +848,8 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
         return false;
       }
       c->resident = true;
+      c->n_acc = 8 * nt <= 512 ? 2u : 1u;
+      c->tmem_cols = pow2_cols(c->n_acc * 4 * nt);
       c->tile_bytes = c->packed.tile_bytes;
       c->stages = x_stages;
       c->smem_bytes = x_stages * x_slot(static_cast<int>(a.channels)) + c->tile_bytes;

@@ -1,36 +1,42 @@
-// kernels_umma2.cu -- persistent tensor-core FIR for sm_100a: packed tap tiles RESIDENT in shared
-// memory (the second tensor kernel; kernels_umma.cu, one tile per CTA with streamed tap tiles,
-// stays as the path for filters whose packed tile does not fit).
+// kernels_umma2.cu -- persistent, TMA-fed tensor-core FIR for sm_100a: the kernel long filters run
+// (kernels_umma.cu, one tile per CTA with streamed tap tiles and LDG-fed converters, stays as the
+// path for short filters, ragged cohorts, unaligned rows and tap tiles that do not fit).
 //
 // Same arithmetic as kernels_umma.cu -- the whole hot path of speex_resampler_process_interleaved_int
 // (deps/speex/resample.c:1061-1082 over :968-1036 and the four resampler_basic_* kernels :331-558)
 // as an EXACT integer banded GEMM on tcgen05.mma.kind::i8, one rounding at the end (WORD2INT,
-// arch.h:208-209) -- but organised around what the round-1 profile showed to bind the long-filter
-// shapes: bytes from L2 into the SM (tap tiles re-streamed by every CTA, 57 % of the traffic) and
-// per-tile fixed cost (prologue + epilogue = 30 % of a CTA's life).
+// arch.h:208-209) -- organised around what the measurements of round 2 showed to bound a 64-frame
+// stage of the long-filter shapes:
+//   * PCM reaches the SM through the copy engine. LDG.128 into registers delivers 13-14 B/clk/SM
+//     from 8 warps and 22 from 16, whatever is in flight and whatever L1 is left (csrc/ldg_rate.cu);
+//     that alone is ~1200 cycles per 16 KB stage -- the stage time of every earlier version.
+//     cp.async 16 B does 25.6, 1-D bulk copies cost ~61 cycles of issue EACH (4 B/clk for 256-byte
+//     row pieces), one tensor-map box of 64 rows x 256 B does 42 B/clk/SM = 387 cycles per stage.
+//     A loader lane issues one box per stage into the ring slot; a converter group splits the bytes
+//     IN PLACE (raw rows -> the two byte planes in UMMA layout) behind a group barrier. No thread
+//     computes a PCM address, no registers hold loads in flight, the ragged end of the input and the
+//     rows past the end of the batch are the tensor map's zero fill.
 //   * One CTA per SM, persistent: CTA b walks the contiguous share [b*W/grid, (b+1)*W/grid) of the
 //     tile list ordered tile-index-major (w = t * groups + g), so consecutive tiles of a CTA share
 //     their output tile index t and with it the tap tile. Barriers, TMEM and the instruction cache
 //     are set up once per CTA instead of once per tile.
-//   * The tap tile of t stays in shared memory for the whole run of tiles that share it and is
-//     loaded once per run (one bulk copy per K stage, each with its own mbarrier, so the first
-//     tile's MMAs start as the stages arrive). PCM is then the only per-tile stream into the SM.
+//   * The tap tile of t stays in shared memory for the whole run of tiles that share it (one bulk
+//     copy per K stage, each with its own mbarrier, so the first tile's MMAs start as the stages
+//     arrive): every CTA re-streaming its tap tile was 57 % of the L2 -> SM traffic.
 //   * The tile is PACKED (umma_plan.h): per K step only the 16-column blocks of each tap digit
-//     that can be non-zero are stored -- the band's corners, the high digit outside the main lobe
-//     and the middle digit near the filter's ends are skipped -- which cuts the tap bytes to
-//     ~0.6 and the MMA columns with them. The MMA warp walks a per-K-step table of at most three
-//     entries (B rows, D columns) carried in the kernel parameters.
-// Warp roles (352 threads):
-//   0-7  converters + epilogue: PCM (history for frames < 0, the call's input after) -> byte planes
-//        in UMMA layout through a ring of 64-frame stages; two stages of loads in flight in
-//        registers, also ACROSS tile boundaries (the next tile's first loads fly during the
-//        epilogue); epilogue straight from TMEM to the interleaved int16 output;
-//   8    lane 0 owns the mbarriers and loads the tap tile of each run;
-//   9    owns TMEM; one elected lane issues the MMAs, releases PCM stages with tcgen05.commit,
-//        hands the accumulator to the epilogue (acc_full) and takes it back (acc_empty);
-//   10   slides the history (resample.c:898-899) of this CTA's share of streams beside the FIR and
-//        publishes the new stream position.
-// One instantiation per (CH, FAST, IDS); the schedule is written down, not induced by probes.
+//     that can be non-zero are stored, ~0.6 of the dense bytes. The MMA lane walks a per-K-step
+//     table of at most three records carried in the kernel parameters, one record ahead of the
+//     MMAs it issues.
+// Warp roles (384 threads; 512 in the instantiation with two accumulator sets):
+//   0-7   converters, two groups of four on alternate stages; they also run the epilogue (straight
+//         from TMEM to the interleaved int16 output) when there is one accumulator set;
+//   8     owns TMEM and the barriers, loads the tap tile of each run; one elected lane issues the
+//         MMAs, releases ring slots with tcgen05.commit, hands the accumulator over (acc_full) and
+//         takes it back (acc_empty);
+//   9     lane 0: the TMA boxes;
+//   10-11 slide the history (resample.c:898-899) of this CTA's share of streams beside the FIR and
+//         publish the new stream position;
+//   12-15 (8 nt <= 512: two accumulator sets) the epilogue of a tile under the next tile's MMAs.
 #include <cuda.h>
 
 #include <algorithm>
@@ -63,6 +69,10 @@ constexpr int kMaxXStages = 6;
 constexpr int kConvWarps2 = 8, kGroupWarps = 4;
 constexpr int kMmaWarp2 = 8, kLoadWarp = 9, kHistWarp0 = 10, kHistWarps = 2;
 constexpr int kThreads2 = 12 * 32;
+// DB instantiation (two accumulator sets, 8 nt <= 512): four more warps, 12-15, run the epilogue of a
+// tile under the next tile's MMAs (warp % 4 = TMEM lane quarter); 128 registers per thread
+constexpr int kEpiWarp0 = 12, kEpiWarps = 4;
+constexpr int kThreadsDB = 16 * 32;
 constexpr uint32_t kMaxTapStages = kUmmaMaxKsteps / 2;
 constexpr uint32_t kInlineTiles2 = 32;
 // dynamic shared memory this kernel may ask for: 227 KB minus its static part (barriers, 1 KB with
@@ -121,6 +131,10 @@ struct Umma2Args {
   MmaRec rec[kMaxRecs + 1];
 };
 
+#ifndef SPXB_PF_DIST
+#define SPXB_PF_DIST 0
+#endif
+
 #ifdef SPXB_UMMA2_TRACE
 constexpr int kTraceSlots2 = 128;
 #define TRACE2(u, slot)                                                                                       \
@@ -169,6 +183,13 @@ __device__ __forceinline__ void tma_box_2d(void *dst, const CUtensorMap *map, in
           "r"(smem_u32(dst)),
       "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
+#endif
+}
+
+// the same box, only as far as L2 (no shared memory, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int x, int y) {
+#ifndef SPXB_DBG_NOLOAD
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
 #endif
 }
 
@@ -229,13 +250,13 @@ __device__ __forceinline__ void slide_streams(const CallArgs &a, uint32_t step, 
 // csrc/ldg_rate.cu) instead of LDG.128 into registers (13-14 B/clk/SM from 8 warps, whatever is in
 // flight -- what bounded the earlier kernels at ~1100 cycles per stage), no registers hold loads in
 // flight, and the converters never compute a global address.
-template <int CH>
-__global__ void __launch_bounds__(kThreads2, 1)
+template <int CH, bool DB>
+__global__ void __launch_bounds__(DB ? kThreadsDB : kThreads2, 1)
     umma2_fir_kernel(const __grid_constant__ CallArgs a, const __grid_constant__ Umma2Args u,
                      const __grid_constant__ Umma2Maps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t raw_full[kMaxXStages], x_full[kMaxXStages], x_empty[kMaxXStages], tap_full[kMaxTapStages];
-  __shared__ uint64_t taps_free, acc_full, acc_empty, tmem_ready;
+  __shared__ uint64_t taps_free, acc_full[2], acc_empty[2], tmem_ready;
   __shared__ uint32_t tmem_slot;
 #ifdef SPXB_UMMA2_WATCHDOG
   __shared__ volatile uint32_t wd_prog[16];
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
   // griddepcontrol.wait below until this grid has completed, before it touches PCM, history or output.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) TRACE2(u, 0);
-  if (tid == kThreads2 - 64) {
+  if (tid == 11 * 32) {
 #ifdef SPXB_UMMA2_TRACE
     if (u.trace) {
       unsigned long long gt;
@@ -289,15 +310,15 @@ __global__ void __launch_bounds__(kThreads2, 1)
 
   // ---- prologue: the barriers, one per lane of the MMA warp; then everybody may proceed ----
   if (warp == kMmaWarp2) {
-    const uint32_t n_bar = 3 * S + n_iters + 4;
+    const uint32_t n_bar = 3 * S + n_iters + 6;
     for (uint32_t i = lane; i < n_bar; i += 32) {
       if (i < S) mbar_init(&raw_full[i], 1);                        // the loader's arrive + the box's bytes
       else if (i < 2 * S) mbar_init(&x_full[i - S], kGroupWarps);   // one elected arrival per warp of a group
       else if (i < 3 * S) mbar_init(&x_empty[i - 2 * S], 1);
       else if (i < 3 * S + n_iters) mbar_init(&tap_full[i - 3 * S], 1);
       else if (i == 3 * S + n_iters) mbar_init(&taps_free, 1);
-      else if (i == 3 * S + n_iters + 1) mbar_init(&acc_full, 1);
-      else if (i == 3 * S + n_iters + 2) mbar_init(&acc_empty, kConvWarps2);
+      else if (i <= 3 * S + n_iters + 2) mbar_init(&acc_full[i - (3 * S + n_iters + 1)], 1);
+      else if (i <= 3 * S + n_iters + 4) mbar_init(&acc_empty[i - (3 * S + n_iters + 3)], DB ? kEpiWarps : kConvWarps2);
       else mbar_init(&tmem_ready, 1);
     }
     fence_mbar_init();
@@ -313,6 +334,98 @@ __global__ void __launch_bounds__(kThreads2, 1)
       mbar_arrive_expect_tx(&tap_full[lane], bytes);
       bulk_g2s(tap_smem + off, src + off, bytes, &tap_full[lane]);
     }
+  };
+
+  // ---- epilogue of one tile: straight from TMEM to the interleaved int16 output ----
+  // a lane owns one series (TMEM lane) and 16 consecutive outputs per column group; mono packs them
+  // into 32 contiguous bytes, stereo first swaps halves with the neighbouring lane (the other
+  // channel of the same stream) so that each lane of the pair holds 8 whole frames = 32 bytes.
+  // Without the DB warps the two converter warps of a TMEM lane quarter (one of each group) share the
+  // column groups of a tile; with them, one epilogue warp per quarter takes them all.
+  const uint32_t gw_e = static_cast<uint32_t>(warp) & 3u;
+  const uint32_t row = gw_e * 32 + lane;  // TMEM lane = series of the tile
+  const uint32_t sl_out = CH == 2 ? row >> 1 : row, ch_out = CH == 2 ? (row & 1u) : 0u;
+  uint32_t tmem = 0;
+  // (cg0, cg_step): this warp's column groups; (buf, par): accumulator set of the tile and the parity
+  // of its `full` phase
+  auto epilogue = [&](uint32_t tile_no, uint32_t cg0, uint32_t cg_step, uint32_t buf, uint32_t par) {
+    const uint32_t w = w_begin + tile_no, t = w / G, g = w - t * G;
+    const uint32_t m0 = t * nt;
+    const uint32_t n_valid = min(nt, sc.n_out - m0);
+    const uint32_t s_out = g * kStreams + sl_out;
+    const bool live_out = s_out < n_rows;
+    int16_t *out_row = a.out + static_cast<size_t>(live_out ? s_out : 0) * a.out_stride + static_cast<size_t>(m0) * CH;
+    if (tile_no == 0) {
+      WAIT(&tmem_ready, 0, 0x01000000u);
+      tc_fence_after_sync();
+      tmem = tmem_slot;
+    }
+    PROG(5u, tile_no);
+    if (tid == 0) TRACE2(u, 16 + 8 * min(tile_no, 4u) + 1);
+    WAIT(&acc_full[buf], par, 0x02000000u | tile_no);
+    tc_fence_after_sync();
+    const uint32_t lane_addr = tmem + ((gw_e * 32u) << 16) + buf * 4u * nt;
+    const uint32_t cg_end = (n_valid + 15) / 16;
+    for (uint32_t cg = cg0; cg < cg_end; cg += cg_step) {
+      uint32_t p0[16], p1[16], p2[16], p3[16];
+      tmem_ld16(lane_addr + cg * 16, p0);
+      tmem_ld16(lane_addr + nt + cg * 16, p1);
+      tmem_ld16(lane_addr + 2 * nt + cg * 16, p2);
+      tmem_ld16(lane_addr + 3 * nt + cg * 16, p3);
+      tmem_ld_wait();
+      if (cg + cg_step >= cg_end) {
+        // this warp's last read of the accumulator: hand it back before the arithmetic and the
+        // stores of this group, so the next tile's MMAs start underneath them
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+      int r16[16];
+      combine16(p0, p1, p2, p3, u.shift, r16);  // rounded, not yet saturated
+      uint32_t wv[8];       // this lane's 16 int16 values = 32 contiguous output bytes
+      uint32_t first_elem;  // their position in the stream's row, in int16 elements from m0
+      if (CH == 2) {
+        // lane pair (left, right): left keeps frames [0,8), right keeps frames [8,16)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int send = ch_out == 0 ? r16[8 + j] : r16[j];
+          const int recv = __shfl_xor_sync(0xffffffffu, send, 1);
+          wv[j] = ch_out == 0 ? pack_sat_s16x2(recv, r16[j]) : pack_sat_s16x2(r16[8 + j], recv);
+        }
+        first_elem = (cg * 16 + ch_out * 8) * 2;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wv[j] = pack_sat_s16x2(r16[2 * j + 1], r16[2 * j]);
+        first_elem = cg * 16;
+      }
+      if (!live_out) continue;
+      const uint32_t total = n_valid * CH;
+      const uint32_t n_here = first_elem >= total ? 0u : min(16u, total - first_elem);  // int16 elements
+      int16_t *dst = out_row + first_elem;
+      if (n_here == 16) {
+        reinterpret_cast<uint4 *>(dst)[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        reinterpret_cast<uint4 *>(dst)[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+      } else {
+        // the ragged end of the call's output: rows are 16-byte aligned, so whole 32-bit words, then
+        // possibly one last int16
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (2u * j + 1 < n_here) reinterpret_cast<uint32_t *>(dst)[j] = wv[j];
+        if (n_here & 1u) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (2u * j + 1 == n_here) dst[2 * j] = static_cast<int16_t>(wv[j] & 0xffffu);
+        }
+      }
+    }
+    if (cg0 >= cg_end) {
+      // (a warp with no column group in this tile still owes its arrival)
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    PROG(6u, tile_no);
+    if (tid == 0) TRACE2(u, 16 + 8 * min(tile_no, 4u) + 3);
   };
 
   if (warp < kConvWarps2) {
@@ -344,94 +457,6 @@ __global__ void __launch_bounds__(kThreads2, 1)
       return (j >> 1) * x_kstep(CH) + (j & 1) * x_lbo(CH) + sl0 * (16 * CH) + byte_in_row;
     }();
     const uint32_t total_stages = n_tiles_mine * n_iters;
-
-    // ---- epilogue of one tile: straight from TMEM to the interleaved int16 output ----
-    // a lane owns one series (TMEM lane) and 16 consecutive outputs per column group; mono packs them
-    // into 32 contiguous bytes, stereo first swaps halves with the neighbouring lane (the other
-    // channel of the same stream) so that each lane of the pair holds 8 whole frames = 32 bytes.
-    // The two warps of a TMEM lane quarter (one of each group) share the column groups.
-    const uint32_t row = gw * 32 + lane;  // TMEM lane = series of the tile
-    const uint32_t sl_out = CH == 2 ? row >> 1 : row, ch_out = CH == 2 ? (row & 1u) : 0u;
-    uint32_t tmem = 0;
-    auto epilogue = [&](uint32_t tile_no) {
-      const uint32_t w = w_begin + tile_no, t = w / G, g = w - t * G;
-      const uint32_t m0 = t * nt;
-      const uint32_t n_valid = min(nt, sc.n_out - m0);
-      const uint32_t s_out = g * kStreams + sl_out;
-      const bool live_out = s_out < n_rows;
-      int16_t *out_row = a.out + static_cast<size_t>(live_out ? s_out : 0) * a.out_stride + static_cast<size_t>(m0) * CH;
-      if (tile_no == 0) {
-        WAIT(&tmem_ready, 0, 0x01000000u);
-        tc_fence_after_sync();
-        tmem = tmem_slot;
-      }
-      PROG(5u, tile_no);
-      if (tid == 0) TRACE2(u, 16 + 8 * min(tile_no, 4u) + 1);
-      WAIT(&acc_full, tile_no & 1u, 0x02000000u | tile_no);
-      tc_fence_after_sync();
-      const uint32_t lane_addr = tmem + ((gw * 32u) << 16);
-      const uint32_t cg_end = (n_valid + 15) / 16;
-      for (uint32_t cg = group; cg < cg_end; cg += 2) {
-        uint32_t p0[16], p1[16], p2[16], p3[16];
-        tmem_ld16(lane_addr + cg * 16, p0);
-        tmem_ld16(lane_addr + nt + cg * 16, p1);
-        tmem_ld16(lane_addr + 2 * nt + cg * 16, p2);
-        tmem_ld16(lane_addr + 3 * nt + cg * 16, p3);
-        tmem_ld_wait();
-        if (cg + 2 >= cg_end) {
-          // this warp's last read of the accumulator: hand it back before the arithmetic and the
-          // stores of this group, so the next tile's MMAs start underneath them
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty);
-        }
-        int r16[16];
-        combine16(p0, p1, p2, p3, u.shift, r16);  // rounded, not yet saturated
-        uint32_t wv[8];       // this lane's 16 int16 values = 32 contiguous output bytes
-        uint32_t first_elem;  // their position in the stream's row, in int16 elements from m0
-        if (CH == 2) {
-          // lane pair (left, right): left keeps frames [0,8), right keeps frames [8,16)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int send = ch_out == 0 ? r16[8 + j] : r16[j];
-            const int recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            wv[j] = ch_out == 0 ? pack_sat_s16x2(recv, r16[j]) : pack_sat_s16x2(r16[8 + j], recv);
-          }
-          first_elem = (cg * 16 + ch_out * 8) * 2;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) wv[j] = pack_sat_s16x2(r16[2 * j + 1], r16[2 * j]);
-          first_elem = cg * 16;
-        }
-        if (!live_out) continue;
-        const uint32_t total = n_valid * CH;
-        const uint32_t n_here = first_elem >= total ? 0u : min(16u, total - first_elem);  // int16 elements
-        int16_t *dst = out_row + first_elem;
-        if (n_here == 16) {
-          reinterpret_cast<uint4 *>(dst)[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-          reinterpret_cast<uint4 *>(dst)[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
-        } else {
-          // the ragged end of the call's output: rows are 16-byte aligned, so whole 32-bit words, then
-          // possibly one last int16
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (2u * j + 1 < n_here) reinterpret_cast<uint32_t *>(dst)[j] = wv[j];
-          if (n_here & 1u) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (2u * j + 1 == n_here) dst[2 * j] = static_cast<int16_t>(wv[j] & 0xffffu);
-          }
-        }
-      }
-      if (group >= cg_end) {
-        // (a warp with no column group in this tile still owes its arrival)
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty);
-      }
-      PROG(6u, tile_no);
-      if (tid == 0) TRACE2(u, 16 + 8 * min(tile_no, 4u) + 3);
-    };
 
     // The previous call's grid may still be writing the output rows this call overwrites.
     if (tid == 0) TRACE2(u, 3);
@@ -473,7 +498,8 @@ __global__ void __launch_bounds__(kThreads2, 1)
       }
       // every stage of the tiles before c_tile is stored: their epilogues are due (the MMAs of
       // c_tile cannot start before the accumulator of c_tile - 1 has been read out)
-      while (done_tile < c_tile) epilogue(done_tile++);
+      if (!DB)
+        for (; done_tile < c_tile; ++done_tile) epilogue(done_tile, group, 2, 0, done_tile & 1u);
       if (!have_kf0) {
         c_kf0 = tile_kf0((w_begin + c_tile) / G);
         have_kf0 = true;
@@ -539,7 +565,8 @@ __global__ void __launch_bounds__(kThreads2, 1)
         par ^= 1u;
       }
     }
-    while (done_tile < n_tiles_mine) epilogue(done_tile++);
+    if (!DB)
+      for (; done_tile < n_tiles_mine; ++done_tile) epilogue(done_tile, group, 2, 0, done_tile & 1u);
     if (tid == 0) TRACE2(u, 10);
   } else if (warp == kMmaWarp2) {
     // ================= MMA issue =================
@@ -555,7 +582,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_ready);
     tc_fence_after_sync();
-    const uint32_t acc = tmem_slot;
+    const uint32_t acc0 = tmem_slot;
     const uint32_t n3 = 3 * nt;
     const uint32_t np0 = min(n3, 256u), np1 = n3 - np0;            // [0, 3nt)
     const uint32_t nq0 = min(2 * nt, 256u), nq1 = 2 * nt - nq0;    // [0, 2nt) (first K step, lo plane)
@@ -585,11 +612,13 @@ __global__ void __launch_bounds__(kThreads2, 1)
       }
       const bool run_ends = w + 1 == w_end || (w + 1) / G != t;
       const uint32_t tr = 16 + 8 * min(tile_no, 4u);  // trace slots of this tile
-      if (tile_no) {
-        // the epilogue has read the previous tile's accumulator out of TMEM
-        WAIT(&acc_empty, (tile_no - 1) & 1u, 0x05000000u | tile_no);
+      const uint32_t buf = DB ? (tile_no & 1u) : 0u, buf_use = DB ? (tile_no >> 1) : tile_no;
+      if (buf_use) {
+        // the epilogue has read this set's previous tile out of TMEM
+        WAIT(&acc_empty[buf], (buf_use - 1) & 1u, 0x05000000u | tile_no);
         tc_fence_after_sync();
       }
+      const uint32_t acc = acc0 + buf * 4u * nt;
       if (lane == 0) TRACE2(u, tr + 4);
       for (uint32_t it = 0; it < n_iters; ++it) {
         if (tile_no == 1 && it < 16 && lane == 0) TRACE2(u, 64 + 3 * it);
@@ -653,7 +682,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
           }
           umma_commit(&x_empty[slot]);
           if (last) {
-            umma_commit(&acc_full);
+            umma_commit(&acc_full[buf]);
             if (run_ends) umma_commit(&taps_free);
           }
         }
@@ -682,6 +711,13 @@ __global__ void __launch_bounds__(kThreads2, 1)
         const int kf0 = tile_kf0(t);
         const int row0 = static_cast<int>(g * kStreams);
         for (uint32_t it = 0; it < n_iters; ++it) {
+          // Ask L2 for the input of a stage several slots ahead (SPXB_PF_DIST stages; the frames a call
+          // brings in come from HBM, and a ring slot is too precious to sit through that latency)
+          if (SPXB_PF_DIST) {
+            const int fp = kf0 + static_cast<int>(it + SPXB_PF_DIST) * kStageFrames;
+            if (it + SPXB_PF_DIST < n_iters && fp >= 0 && fp < static_cast<int>(sc.n_in))
+              tma_prefetch_2d(&maps.in64, fp * CH * 2, row0);
+          }
           WAIT_L(&x_empty[slot], par, 0x08000000u | (slot << 20) | (par << 16) | (tile_no << 8) | it);
           uint8_t *dst = smem + slot * kXStageBytes;
           const int f0 = kf0 + static_cast<int>(it) * kStageFrames;
@@ -710,6 +746,11 @@ __global__ void __launch_bounds__(kThreads2, 1)
         }
       }
     }
+  } else if (DB && warp >= kEpiWarp0) {
+    // ================= epilogue warps (two accumulator sets) =================
+    // the previous call's grid may still be writing the output rows this call overwrites
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (uint32_t tile_no = 0; tile_no < n_tiles_mine; ++tile_no) epilogue(tile_no, 0, 1, tile_no & 1u, (tile_no >> 1) & 1u);
   } else {
     // ================= history slide (resample.c:898-899) and the new position =================
     // Runs beside the FIR: it reads the old history and this call's input, writes the other half
@@ -805,8 +846,10 @@ __global__ void build_packed_tiles_kernel(const int32_t *__restrict__ h, uint32_
 
 void umma2_configure_device() {
   auto big_smem = [](auto kernel) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem2); };
-  big_smem(umma2_fir_kernel<1>);
-  big_smem(umma2_fir_kernel<2>);
+  big_smem(umma2_fir_kernel<1, false>);
+  big_smem(umma2_fir_kernel<2, false>);
+  big_smem(umma2_fir_kernel<1, true>);
+  big_smem(umma2_fir_kernel<2, true>);
 }
 
 // what the TMA-fed kernel needs of a call: the whole batch (no stream subset), an input to read, and
@@ -1005,8 +1048,15 @@ cudaError_t launch_umma2(UmmaContext *c, const CallArgs &a, cudaStream_t stream,
       !pcm_map(&maps.hist64, a.hist_src, hist_bytes, a.n_streams, static_cast<uint64_t>(a.hist_stride) * 2, row_box, streams) ||
       !pcm_map(&maps.hist16, a.hist_src, hist_bytes, a.n_streams, static_cast<uint64_t>(a.hist_stride) * 2, row_box / 4, streams))
     return cudaErrorInvalidValue;
-  cudaError_t e = a.channels == 2 ? cudaLaunchKernelEx(&cfg, umma2_fir_kernel<2>, a, u, maps)
-                                  : cudaLaunchKernelEx(&cfg, umma2_fir_kernel<1>, a, u, maps);
+  cudaError_t e;
+  if (c->n_acc == 2) {
+    cfg.blockDim = dim3(kThreadsDB);
+    e = a.channels == 2 ? cudaLaunchKernelEx(&cfg, umma2_fir_kernel<2, true>, a, u, maps)
+                        : cudaLaunchKernelEx(&cfg, umma2_fir_kernel<1, true>, a, u, maps);
+  } else {
+    e = a.channels == 2 ? cudaLaunchKernelEx(&cfg, umma2_fir_kernel<2, false>, a, u, maps)
+                        : cudaLaunchKernelEx(&cfg, umma2_fir_kernel<1, false>, a, u, maps);
+  }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e == cudaSuccess) c->fresh_plan = false;
   if (e == cudaSuccess && launches) *launches += 1;

@@ -26,6 +26,7 @@ struct UmmaContext {
   // resident: the persistent kernel (kernels_umma2.cu) with packed tap tiles serves this geometry;
   // otherwise the one-tile-per-CTA kernel with dense, streamed tap tiles (kernels_umma.cu)
   bool resident = false;
+  uint32_t n_acc = 1;  // accumulator sets of the persistent kernel in TMEM (2 when 8 nt <= 512)
   bool resident_wanted = false;  // what the call that fixed the geometry asked for (kernels_umma2.cu: umma2_covers)
   UmmaPackedPlan packed;
   UmmaKStep *d_kplan = nullptr;  // the packed plan in HBM (tile builder)

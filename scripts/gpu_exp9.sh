@@ -14,9 +14,9 @@ for l in sys.stdin:
 B="timeout 200 python bench.py --kernel tensor --steps 192 --warmup 10 --no-cpu-baseline --no-also --lean --min-seconds 0.3"
 for V in "" _noload _nomma _skel; do
   L=$PWD/node_speex_resampler_b200/libspeexb200$V.so
-  for WL in C5 C4; do
+  for WL in C5; do
     run "v3$V $WL packed default nt" SPXB_LIB_PATH=$L SPXB_UMMA_RESIDENT=1 $B --workload $WL
-    run "v3$V $WL dense nt64 xs3" SPXB_LIB_PATH=$L SPXB_UMMA_RESIDENT=1 SPXB_UMMA_DENSE=1 SPXB_UMMA_NT=64 SPXB_UMMA2_XSTAGES=3 $B --workload $WL
+    run "v3$V $WL dense nt64 xs3" SPXB_LIB_PATH=$L SPXB_UMMA_RESIDENT=1 SPXB_UMMA_DENSE=1 SPXB_UMMA_NT=64 $B --workload $WL
   done
-  run "v3$V C3 packed default nt" SPXB_LIB_PATH=$L SPXB_UMMA_RESIDENT=1 $B --workload C3
+  true
 done

@@ -1,7 +1,7 @@
-"""Run by tests/test_parity_gpu.py::test_persistent_kernel_parity in a subprocess with
-SPXB_UMMA_RESIDENT=1 (the choice between the two tensor kernels is read once per process): the
-persistent kernel with packed, shared-memory-resident tap tiles (csrc/kernels_umma2.cu) against the
-oracle -- a batch large enough that CTAs walk several tiles and change tap tile on the way."""
+"""Run by tests/test_parity_gpu.py (test_persistent_kernel_parity, test_long_filter_on_either_tensor_kernel)
+in a subprocess whose environment picks the tensor kernel and its geometry (SPXB_UMMA_RESIDENT, _NT,
+_DENSE, SPXB_UMMA2_XSTAGES are read once per process): the tensor kernel against the oracle -- a batch
+large enough that persistent CTAs walk several tiles and change tap tile on the way."""
 import sys
 
 import numpy as np

@@ -1018,9 +1018,10 @@ def test_empty_chunks_return_empty_buffers():
     ("q0", 200, 2, 44100, 48000, 0, 441, 2),      # shortest filter: a single stage per tile
 ], ids=lambda s: s[0])
 def test_persistent_kernel_parity(shape):
-    """The persistent tensor kernel with packed, resident tap tiles (csrc/kernels_umma2.cu) is opt-in
-    (SPXB_UMMA_RESIDENT=1; measured slower than the one-tile-per-CTA kernel): it must
-    still meet the bar -- <= 1 LSB, >= 90 dB, lengths and device state equal to the oracle's."""
+    """The persistent, TMA-fed tensor kernel (csrc/kernels_umma2.cu) is what long filters run by default
+    (8 or more 64-frame stages per tile). Forced on (SPXB_UMMA_RESIDENT=1) it must meet the
+    bar on every shape, short filters and single-stage tiles included -- <= 1 LSB, >= 90 dB, lengths and
+    device state equal to the oracle's."""
     import subprocess
     import sys
     env = dict(os.environ, SPXB_UMMA_RESIDENT="1", PYTHONPATH=ROOT)
@@ -1028,6 +1029,24 @@ def test_persistent_kernel_parity(shape):
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "resident ok" in r.stdout and "'stages'" in r.stdout
+
+
+@pytest.mark.parametrize("env", [
+    {"SPXB_UMMA_RESIDENT": "0"},                                                   # the one-tile-per-CTA kernel on a long filter
+    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_NT": "64", "SPXB_UMMA_DENSE": "1"},     # two accumulator sets, dedicated epilogue warps
+    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_NT": "96"},                             # an even ring
+    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA2_XSTAGES": "3"},                        # an odd ring: slots change converter group
+], ids=lambda e: "_".join(f"{k[5:].lower()}{v}" for k, v in e.items()))
+def test_long_filter_on_either_tensor_kernel(env):
+    """The long-filter shapes through the kernel they do NOT get by default, and through the
+    persistent kernel's other configurations (ring sizes, one or two accumulator sets): same bar."""
+    import subprocess
+    import sys
+    for shape in (("C5x", 700, 2, 96000, 44100, 10, 1920, 3), ("C4x", 600, 1, 48000, 16000, 10, 960, 2)):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "resident_check.py")] + [str(v) for v in shape],
+                           capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONPATH=ROOT, **env), cwd=ROOT)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        assert "resident ok" in r.stdout
 
 
 @pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not present")
