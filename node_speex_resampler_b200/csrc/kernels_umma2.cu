@@ -255,8 +255,13 @@ __global__ void __launch_bounds__(DB ? kThreadsDB : kThreads2, 1)
     umma2_fir_kernel(const __grid_constant__ CallArgs a, const __grid_constant__ Umma2Args u,
                      const __grid_constant__ Umma2Maps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t raw_full[kMaxXStages], x_full[kMaxXStages], x_empty[kMaxXStages], tap_full[kMaxTapStages];
-  __shared__ uint64_t taps_free, acc_full[2], acc_empty[2], tmem_ready;
+  // all barriers in one array, at fixed offsets, so that one convergent instruction initialises 32 of them
+  constexpr uint32_t kBarTap = 3 * kMaxXStages, kBarMisc = kBarTap + kMaxTapStages, kBars = kBarMisc + 6;
+  __shared__ uint64_t bars[kBars];
+  uint64_t *const raw_full = bars, *const x_full = bars + kMaxXStages, *const x_empty = bars + 2 * kMaxXStages;
+  uint64_t *const tap_full = bars + kBarTap;
+  uint64_t &taps_free = bars[kBarMisc], &tmem_ready = bars[kBarMisc + 5];
+  uint64_t *const acc_full = bars + kBarMisc + 1, *const acc_empty = bars + kBarMisc + 3;
   __shared__ uint32_t tmem_slot;
 #ifdef SPXB_UMMA2_WATCHDOG
   __shared__ volatile uint32_t wd_prog[16];
@@ -310,20 +315,21 @@ __global__ void __launch_bounds__(DB ? kThreadsDB : kThreads2, 1)
 
   // ---- prologue: the barriers, one per lane of the MMA warp; then everybody may proceed ----
   if (warp == kMmaWarp2) {
-    const uint32_t n_bar = 3 * S + n_iters + 6;
-    for (uint32_t i = lane; i < n_bar; i += 32) {
-      if (i < S) mbar_init(&raw_full[i], 1);                        // the loader's arrive + the box's bytes
-      else if (i < 2 * S) mbar_init(&x_full[i - S], kGroupWarps);   // one elected arrival per warp of a group
-      else if (i < 3 * S) mbar_init(&x_empty[i - 2 * S], 1);
-      else if (i < 3 * S + n_iters) mbar_init(&tap_full[i - 3 * S], 1);
-      else if (i == 3 * S + n_iters) mbar_init(&taps_free, 1);
-      else if (i <= 3 * S + n_iters + 2) mbar_init(&acc_full[i - (3 * S + n_iters + 1)], 1);
-      else if (i <= 3 * S + n_iters + 4) mbar_init(&acc_empty[i - (3 * S + n_iters + 3)], DB ? kEpiWarps : kConvWarps2);
-      else mbar_init(&tmem_ready, 1);
+    if (lane == 0) TRACE2(u, 5);
+    // Lane i initialises barriers i and i + 32: two convergent mbarrier.init instructions, ~130 cycles
+    // each (a chain of per-lane branches over the barrier kinds cost ~1700 cycles of every CTA's
+    // prologue, one lane looping over them 60-90 cycles per barrier; csrc/mbar_probe.cu).
+#pragma unroll
+    for (uint32_t i = lane; i < kBars; i += 32) {
+      const bool group_arrivals = i >= kMaxXStages && i < 2 * kMaxXStages;          // x_full
+      const bool epi_arrivals = i == kBarMisc + 3 || i == kBarMisc + 4;             // acc_empty
+      mbar_init(&bars[i], group_arrivals ? kGroupWarps : epi_arrivals ? (DB ? kEpiWarps : kConvWarps2) : 1u);
     }
     fence_mbar_init();
+    if (lane == 0) TRACE2(u, 6);
   }
   __syncthreads();
+  if (tid == 0) TRACE2(u, 1);
 
   // One bulk copy per K stage of the packed tile, each completing its own barrier: lane `it` of the
   // MMA warp issues stage `it` (offsets and sizes come with the kernel parameters).
@@ -704,6 +710,7 @@ __global__ void __launch_bounds__(DB ? kThreadsDB : kThreads2, 1)
     if (lane == 0) {
       // the previous call's grid wrote the history this call reads
       asm volatile("griddepcontrol.wait;" ::: "memory");
+      TRACE2(u, 7);
       uint32_t slot = 0, par = 1;  // a fresh barrier passes a wait on the phase "before the first"
       const int hist_frames = static_cast<int>(a.hist_frames);
       for (uint32_t tile_no = 0; tile_no < n_tiles_mine; ++tile_no) {

@@ -14,7 +14,7 @@ import node_speex_resampler_b200 as pkg  # noqa: E402
 
 SHAPES = {"C3": (1024, 2, 44100, 48000, 7, 882), "C4": (4096, 1, 48000, 16000, 10, 960),
           "C5": (8192, 2, 96000, 44100, 10, 1920), "X6": (1024, 2, 44100, 48000, 10, 882)}
-NAMES = {0: "start", 1: "setup done", 2: "first fetches issued", 3: "before griddepcontrol.wait", 4: "after griddepcontrol.wait", 12: "tap loads issued", 8: "history done",
+NAMES = {0: "start", 5: "mma warp: before barrier init", 6: "mma warp: barriers initialised", 7: "loader: past griddepcontrol.wait", 1: "past the first __syncthreads", 2: "first fetches issued", 3: "before griddepcontrol.wait", 4: "after griddepcontrol.wait", 12: "tap loads issued", 8: "history done",
          11: "mma: all issued", 10: "converters done", 9: "exit"}
 TILE = ["", "epi: waits for the accumulator", "", "epi: tile stored",
         "mma: accumulator set free", "mma: stage 0 full", "mma: last stage issued"]
@@ -40,7 +40,7 @@ for wl in (sys.argv[1:] or ["C3", "C4", "C5"]):
         col = rel[:, slot][t[:, slot] != 0] if slot else rel[:, slot]
         if col.size:
             print(f"  {name:>28s}: {np.median(col):9.0f} | {np.percentile(col, 10):9.0f} | {np.percentile(col, 90):9.0f}   ({col.size} CTAs)")
-    for slot in (0, 12, 3, 4, 2, 1):
+    for slot in (0, 5, 6, 1, 7, 12, 3, 4, 2):
         show(NAMES[slot], slot)
     for j in range(5):
         for k, nm in enumerate(TILE):
