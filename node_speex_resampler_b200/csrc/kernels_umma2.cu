@@ -41,7 +41,9 @@
 
 #include <algorithm>
 #include <cstddef>
+#include <chrono>
 #include <cstdio>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -133,6 +135,9 @@ struct Umma2Args {
 
 #ifndef SPXB_PF_DIST
 #define SPXB_PF_DIST 0
+#endif
+#ifndef SPXB_DEFER_EPILOGUE
+#define SPXB_DEFER_EPILOGUE 1
 #endif
 
 #ifdef SPXB_UMMA2_TRACE
@@ -803,6 +808,499 @@ __global__ void __launch_bounds__(DB ? kThreadsDB : kThreads2, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Variant with the A operand in TENSOR MEMORY (opt-in: SPXB_UMMA_ATMEM=1; single accumulator set).
+// The byte planes never touch shared memory: a converter thread owns one series (= TMEM lane), reads
+// its stream's raw bytes of a stage from the ring slot, splits them in registers and writes them with
+// tcgen05.st into the A ring behind the accumulator columns; the MMAs take A from there
+// (csrc/atmem_probe.cu: row = lane, column j = K bytes 4j .. 4j+3, little-endian). What that buys:
+//   * a raw slot is free again as soon as its bytes are in registers -- not after the MMAs that consume
+//     the stage, as with the in-place conversion -- so the three slots a 168 KB tap tile leaves cover
+//     the TMA latency; the plane ring that replaces it is TMEM columns, not shared memory;
+//   * the tensor core stops reading the planes from shared memory (43 % of its operand bytes).
+// Raw boxes are 128 bytes wide with the 128-byte swizzle (16-byte chunk c of row r at c ^ (r & 7)), so
+// that 32 lanes reading 32 different rows at the same chunk do not collide: two boxes per stage for
+// stereo (one per K step), one for mono. The stage that straddles the end of the history arrives as
+// four unswizzled quarter boxes, as in the kernel above.
+struct alignas(64) Umma3Maps {
+  CUtensorMap in_sw, hist_sw, in16, hist16;
+};
+
+__device__ __forceinline__ void umma_i8_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+constexpr uint32_t kMaxRawSlots = 6, kMaxASlots = 4, kRawSlotBytes = 16384;
+#ifdef SPXB_UMMA2_WATCHDOG
+#define PROG3(code, v)                                                                                              \
+  do {                                                                                                              \
+    if ((threadIdx.x & 31) == 0 && blockIdx.x < 4 && u.trace)                                                      \
+      reinterpret_cast<volatile unsigned long long *>(u.trace)[600 + blockIdx.x * 16 + (threadIdx.x >> 5)] =        \
+          (static_cast<unsigned long long>(code) << 32) | (v);                                                      \
+  } while (0)
+#else
+#define PROG3(code, v) \
+  do {                 \
+  } while (0)
+#endif
+
+template <int CH>
+__global__ void __launch_bounds__(kThreads2, 1)
+    umma3_fir_kernel(const __grid_constant__ CallArgs a, const __grid_constant__ Umma2Args u,
+                     const __grid_constant__ Umma3Maps maps) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // barriers at fixed offsets: raw_full [12], raw_empty [6], a_full, a_empty [4 each], tap_full [32], 4 more.
+  // Stage q's box lands in raw slot q % R but completes barrier raw_full[q % 2R]: with two converter
+  // groups on alternate stages and 2R even, each of those barriers is waited on by ONE group, which
+  // then sees every one of its phases -- whatever R is. (A parity wait tells a phase only from the one
+  // before it: a barrier whose uses alternate between the groups let a group that met it every other
+  // time be satisfied by a stale phase. Seen as a hang, twice.) The A ring has an even number of slots
+  // for the same reason; raw_empty, a_full, tap_full and the accumulator's have one waiting party.
+  constexpr uint32_t kBarRE = 2 * kMaxRawSlots, kBarA = kBarRE + kMaxRawSlots, kBarTap = kBarA + 2 * kMaxASlots,
+                     kBarMisc = kBarTap + kMaxTapStages, kBars = kBarMisc + 4;
+  static_assert(kBars <= 64, "two init instructions per lane");
+  __shared__ uint64_t bars[kBars];
+  uint64_t *const raw_full = bars, *const raw_empty = bars + kBarRE;
+  uint64_t *const a_full = bars + kBarA, *const a_empty = bars + kBarA + kMaxASlots;
+  uint64_t *const tap_full = bars + kBarTap;
+  uint64_t &taps_free = bars[kBarMisc], &acc_full = bars[kBarMisc + 1], &acc_empty = bars[kBarMisc + 2],
+           &tmem_ready = bars[kBarMisc + 3];
+  __shared__ uint32_t tmem_slot;
+
+  constexpr int kStreams = kUmmaRows / CH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const StreamCall sc = a.uniform;
+  const uint32_t nt = u.nt, G = u.n_groups, T = u.n_tiles;
+  const uint32_t w_begin = static_cast<uint32_t>(static_cast<unsigned long long>(blockIdx.x) * u.n_work / gridDim.x);
+  const uint32_t w_end = static_cast<uint32_t>(static_cast<unsigned long long>(blockIdx.x + 1) * u.n_work / gridDim.x);
+  const uint32_t n_tiles_mine = w_end - w_begin;
+  constexpr int kStageFrames = kStageChunks * kUmmaChunkFrames;  // 64
+  constexpr uint32_t kRowBytes = kStageFrames * CH * 2;          // raw bytes of one stream in a stage
+  constexpr uint32_t kQuarterRow = kRowBytes / 4, kQuarterBytes = kRawSlotBytes / 4;
+  static_assert(kStreams * kRowBytes == kRawSlotBytes, "a raw stage is 16 KB");
+  const uint32_t R = u.x_stages;                     // raw ring slots
+  const uint32_t A = (512u - 4u * nt) / 32u >= 4u ? 4u : 2u;  // A ring slots (32 columns each) behind the accumulator; even
+  const uint32_t a_col0 = 4u * nt;
+  const uint32_t n_iters = (u.ksteps + 1) / 2;
+  uint8_t *const tap_smem = smem + R * kRawSlotBytes;
+  const uint32_t n_rows = a.n_streams;
+  auto tile_kf0 = [&](uint32_t t) -> int { return u.n_inline ? u.inl[t].kf0 : u.tiles[t].kf0; };
+  auto tile_slot = [&](uint32_t t) -> uint32_t { return u.n_inline ? u.inl[t].slot : u.tiles[t].slot; };
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (tid == 0) TRACE2(u, 0);
+#ifdef SPXB_UMMA2_TRACE
+  if (tid == 11 * 32 && u.trace) {
+    unsigned long long gt;
+    uint32_t smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots2 + 14] = gt;
+    u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots2 + 13] = smid;
+  }
+#endif
+  if (warp == kMmaWarp2) {
+#pragma unroll
+    for (uint32_t i = lane; i < kBars; i += 32) {
+      const bool four = (i >= kBarRE && i < kBarA + kMaxASlots);  // raw_empty, a_full: one arrival per warp of a group
+      mbar_init(&bars[i], four ? kGroupWarps : i == kBarMisc + 2 ? kConvWarps2 : 1u);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto load_tap_tile = [&](uint32_t t) {
+    const int8_t *src = u.pool + static_cast<size_t>(tile_slot(t)) * u.tile_bytes;
+    if (static_cast<uint32_t>(lane) < n_iters) {
+      const uint32_t off = u.stage_off[lane], bytes = u.stage_off[lane + 1] - off;
+      mbar_arrive_expect_tx(&tap_full[lane], bytes);
+      bulk_g2s(tap_smem + off, src + off, bytes, &tap_full[lane]);
+    }
+  };
+
+  if (warp < kConvWarps2) {
+    // ================= converters (one series per thread) + epilogue =================
+    const uint32_t group = static_cast<uint32_t>(warp) >> 2, quarter = warp & 3;
+    const uint32_t row = quarter * 32 + lane;                       // series of the tile = TMEM lane
+    const uint32_t sl = CH == 2 ? row >> 1 : row, ch = CH == 2 ? (row & 1u) : 0u;  // stream of the group, channel
+    const uint32_t sw = (sl & 7u) * 16u;                            // the 128-byte swizzle of this stream's row
+    // stereo: selectors that pick this thread's channel out of two (R << 16 | L) words
+    const uint32_t sel = ch ? 0x7632u : 0x5410u;
+    const uint32_t lane_taddr = (quarter * 32u) << 16;
+    const uint32_t total_stages = n_tiles_mine * n_iters;
+    uint32_t tmem = 0;
+
+    // ---- epilogue of one tile (as in the kernel above, the two warps of a lane quarter share the column groups) ----
+    const uint32_t sl_out = sl, ch_out = ch;
+    auto epilogue = [&](uint32_t tile_no) {
+      const uint32_t w = w_begin + tile_no, t = w / G, g = w - t * G;
+      const uint32_t m0 = t * nt;
+      const uint32_t n_valid = min(nt, sc.n_out - m0);
+      const uint32_t s_out = g * kStreams + sl_out;
+      const bool live_out = s_out < n_rows;
+      int16_t *out_row = a.out + static_cast<size_t>(live_out ? s_out : 0) * a.out_stride + static_cast<size_t>(m0) * CH;
+      if (tid == 0) TRACE2(u, 16 + 8 * min(tile_no, 4u) + 1);
+      PROG3(0x20u, tile_no);
+      WAIT(&acc_full, tile_no & 1u, 0x12000000u | tile_no);
+      tc_fence_after_sync();
+      const uint32_t lane_addr = tmem + lane_taddr;
+      const uint32_t cg_end = (n_valid + 15) / 16;
+      for (uint32_t cg = group; cg < cg_end; cg += 2) {
+        uint32_t p0[16], p1[16], p2[16], p3[16];
+        tmem_ld16(lane_addr + cg * 16, p0);
+        tmem_ld16(lane_addr + nt + cg * 16, p1);
+        tmem_ld16(lane_addr + 2 * nt + cg * 16, p2);
+        tmem_ld16(lane_addr + 3 * nt + cg * 16, p3);
+        tmem_ld_wait();
+        if (cg + 2 >= cg_end) {
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty);
+        }
+        int r16[16];
+        combine16(p0, p1, p2, p3, u.shift, r16);
+        uint32_t wv[8];
+        uint32_t first_elem;
+        if (CH == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int send = ch_out == 0 ? r16[8 + j] : r16[j];
+            const int recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            wv[j] = ch_out == 0 ? pack_sat_s16x2(recv, r16[j]) : pack_sat_s16x2(r16[8 + j], recv);
+          }
+          first_elem = (cg * 16 + ch_out * 8) * 2;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) wv[j] = pack_sat_s16x2(r16[2 * j + 1], r16[2 * j]);
+          first_elem = cg * 16;
+        }
+        if (!live_out) continue;
+        const uint32_t total = n_valid * CH;
+        const uint32_t n_here = first_elem >= total ? 0u : min(16u, total - first_elem);
+        int16_t *dst = out_row + first_elem;
+        if (n_here == 16) {
+          reinterpret_cast<uint4 *>(dst)[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          reinterpret_cast<uint4 *>(dst)[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (2u * j + 1 < n_here) reinterpret_cast<uint32_t *>(dst)[j] = wv[j];
+          if (n_here & 1u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (2u * j + 1 == n_here) dst[2 * j] = static_cast<int16_t>(wv[j] & 0xffffu);
+          }
+        }
+      }
+      if (group >= cg_end) {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty);
+      }
+      if (tid == 0) TRACE2(u, 16 + 8 * min(tile_no, 4u) + 3);
+    };
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    WAIT(&tmem_ready, 0, 0x11000000u);
+    tc_fence_after_sync();
+    tmem = tmem_slot;
+
+    // this group's stages: q = group, group + 2, ...; raw slot q % R, raw_full barrier q % 2R, A slot q % A
+    uint32_t rs = group % R, rb = group, rpar = 0;  // (2R >= 4 > group)
+    uint32_t as = group, apar = 1;                  // (A >= 2; a fresh barrier passes a wait on the phase before the first)
+    uint32_t c_tile = 0, c_it = group, done_tile = 0;
+    int c_kf0 = 0;
+    bool have_kf0 = false;
+    for (uint32_t q = group; q < total_stages; q += 2, c_it += 2) {
+      // The epilogue of tile t is due once this group has stored its last stage of t. It is put off by
+      // ONE stage when that is possible: this group's first stage of tile t + 1 goes into the A ring
+      // first (its slot is released by MMAs of tile t, not by the epilogue), so that the next tile's
+      // MMAs find their operands the moment the accumulator is handed back.
+      bool epilogue_after = false;
+      while (c_it >= n_iters) {
+        c_it -= n_iters;
+        ++c_tile;
+        have_kf0 = false;
+      }
+      if (SPXB_DEFER_EPILOGUE && done_tile + 1 == c_tile && c_it < 2 && n_iters >= 2) epilogue_after = true;
+      else
+        for (; done_tile < c_tile; ++done_tile) epilogue(done_tile);
+      if (!have_kf0) {
+        c_kf0 = tile_kf0((w_begin + c_tile) / G);
+        have_kf0 = true;
+      }
+      PROG3(0x21u, q);
+      WAIT(&raw_full[rb], rpar, 0x13000000u | (rb << 20) | (rpar << 16) | q);
+      PROG3(0x22u, q);
+      {
+        if (quarter == 0 && lane == 0 && c_tile == 1 && c_it < 12) TRACE2(u, 100 + c_it);
+        const int f0 = c_kf0 + static_cast<int>(c_it) * kStageFrames;
+        const bool quarters = f0 < 0 && f0 + kStageFrames > 0;
+        const uint8_t *slot = smem + rs * kRawSlotBytes;
+        // this thread's series, 64 frames: hi and lo bytes, 16 words each (8 per K step)
+        uint32_t hi[16], lo[16];
+        if (CH == 2) {
+          // a 16-byte chunk = 4 frames of (L, R); 8 chunks per K step
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            uint4 v;
+            if (!quarters) {
+              // box h = c / 8 (K step), row sl of 128 bytes, chunk c % 8 swizzled
+              v = *reinterpret_cast<const uint4 *>(slot + (c >> 3) * (kRawSlotBytes / 2) + sl * 128 + (((c & 7) * 16) ^ sw));
+            } else {
+              // quarter box c / 4: rows of 64 bytes, not swizzled
+              v = *reinterpret_cast<const uint4 *>(slot + (c >> 2) * kQuarterBytes + sl * kQuarterRow + (c & 3) * 16);
+            }
+            const uint32_t p01 = __byte_perm(v.x, v.y, sel), p23 = __byte_perm(v.z, v.w, sel);
+            hi[c] = __byte_perm(p01, p23, 0x7531);
+            lo[c] = __byte_perm(p01, p23, 0x6420);
+          }
+        } else {
+          // a 16-byte chunk = 8 frames; 4 chunks per K step, two words per plane and chunk
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 v;
+            if (!quarters) v = *reinterpret_cast<const uint4 *>(slot + sl * 128 + ((c * 16) ^ sw));
+            else v = *reinterpret_cast<const uint4 *>(slot + (c >> 1) * kQuarterBytes + sl * kQuarterRow + (c & 1) * 16);
+            hi[2 * c] = __byte_perm(v.x, v.y, 0x7531);
+            hi[2 * c + 1] = __byte_perm(v.z, v.w, 0x7531);
+            lo[2 * c] = __byte_perm(v.x, v.y, 0x6420);
+            lo[2 * c + 1] = __byte_perm(v.z, v.w, 0x6420);
+          }
+        }
+        // the raw bytes are in registers (hi / lo depend on every load): the slot can be refilled
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);
+        // the MMAs that read this A slot last have completed
+        PROG3(0x23u, q);
+        WAIT(&a_empty[as], apar, 0x14000000u | (as << 20) | (apar << 16) | q);
+        tc_fence_after_sync();
+        PROG3(0x24u, q);
+        const uint32_t ta = tmem + lane_taddr + a_col0 + as * 32u;
+        uint32_t r8[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r8[j] = hi[8 * h + j];
+          tmem_st8(ta + 16 * h, r8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r8[j] = lo[8 * h + j];
+          tmem_st8(ta + 16 * h + 8, r8);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[as]);
+        PROG3(0x25u, q);
+        if (epilogue_after)
+          for (; done_tile < c_tile; ++done_tile) epilogue(done_tile);
+      }
+      rs += 2;
+      if (rs >= R) rs -= R;
+      rb += 2;
+      if (rb >= 2 * R) {
+        rb -= 2 * R;
+        rpar ^= 1u;
+      }
+      as += 2;
+      if (as >= A) {
+        as -= A;
+        apar ^= 1u;
+      }
+    }
+    PROG3(0x26u, done_tile);
+    for (; done_tile < n_tiles_mine; ++done_tile) epilogue(done_tile);
+    PROG3(0x27u, done_tile);
+  } else if (warp == kMmaWarp2) {
+    // ================= MMA issue =================
+    PROG3(0x33u, 0);
+    load_tap_tile(w_begin / G);
+    tmem_alloc(&tmem_slot, 512);
+    PROG3(0x34u, 0);
+    tmem_relinquish();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_ready);
+    tc_fence_after_sync();
+    const uint32_t acc = tmem_slot;
+    const uint32_t n3 = 3 * nt;
+    const uint32_t np0 = min(n3, 256u), np1 = n3 - np0;
+    const uint32_t nq0 = min(2 * nt, 256u), nq1 = 2 * nt - nq0;
+    const uint32_t id_hi = umma_idesc_i8(128, 0, true, true), id_lo = umma_idesc_i8(128, 0, false, true);
+    auto with_n = [](uint32_t idesc, uint32_t n) { return idesc | ((n >> 3) << 17); };
+    const uint64_t b_fixed = umma_smem_desc(smem_u32(tap_smem), 0, 128);
+    // A ring: group g = stage parity owns slots [a_base[g], a_base[g] + a_n[g])
+    uint32_t as = 0, apar = 0, tile_no = 0, run = 0;
+    uint32_t cur_t = 0xffffffffu;
+    for (uint32_t w = w_begin; w < w_end; ++w, ++tile_no) {
+      const uint32_t t = w / G;
+      const bool new_run = t != cur_t;
+      uint32_t tap_par = 0;
+      if (new_run) {
+        if (run) {
+          WAIT(&taps_free, (run - 1) & 1u, 0x16000000u | run);
+          load_tap_tile(t);
+        }
+        cur_t = t;
+        tap_par = run & 1u;
+        ++run;
+      }
+      const bool run_ends = w + 1 == w_end || (w + 1) / G != t;
+      if (tile_no) {
+        WAIT(&acc_empty, (tile_no - 1) & 1u, 0x17000000u | tile_no);
+        tc_fence_after_sync();
+      }
+      const uint32_t tr = 16 + 8 * min(tile_no, 4u);
+      if (lane == 0) TRACE2(u, tr + 4);
+      for (uint32_t it = 0; it < n_iters; ++it) {
+        if (tile_no == 1 && it < 12 && lane == 0) TRACE2(u, 64 + 3 * it);
+        if (new_run) WAIT(&tap_full[it], tap_par, 0x18000000u | (it << 8) | run);
+        PROG3(0x30u, (tile_no << 8) | it);
+        WAIT(&a_full[as], apar, 0x19000000u | (as << 20) | (apar << 16) | (tile_no << 8) | it);
+        PROG3(0x31u, (tile_no << 8) | it);
+        tc_fence_after_sync();
+        if (tile_no == 1 && it < 12 && lane == 0) TRACE2(u, 65 + 3 * it);
+        if (it == 0 && lane == 0) TRACE2(u, tr + 5);
+        const bool last = it + 1 == n_iters;
+        const uint32_t a_st = acc + a_col0 + as * 32u;  // [K step 0: hi 8 cols, lo 8 cols][K step 1: hi, lo]
+        if (elect_one()) {
+          if (it == 0) {
+            const uint64_t b_k = b_fixed + (static_cast<uint64_t>(n3) << 16);
+            umma_i8_ta(acc, a_st, b_k, with_n(id_hi, np0), 0u);
+            if (np1) umma_i8_ta(acc + 256, a_st, b_k + 256, with_n(id_hi, np1), 0u);
+            umma_i8_ta(acc + nt, a_st + 8, b_k, with_n(id_lo, nq0), 1u);
+            if (nq1) umma_i8_ta(acc + nt + 256, a_st + 8, b_k + 256, with_n(id_lo, nq1), 1u);
+            umma_i8_ta(acc + 3 * nt, a_st + 8, b_k + 2 * nt, with_n(id_lo, nt), 0u);
+          }
+          const uint32_t m_end = u.stage_rec[it + 1];
+          uint32_t m = u.stage_rec[it];
+          uint32_t rb = u.rec[m].b, ri = u.rec[m].idesc_hi, rd = u.rec[m].d_a;
+#pragma unroll 1
+          for (; m < m_end; ++m) {
+            const uint32_t nb = u.rec[m + 1].b, ni = u.rec[m + 1].idesc_hi, nd = u.rec[m + 1].d_a;
+            const uint64_t b = b_fixed + rb;
+            const uint32_t a_hi = a_st + ((rd >> 16) ? 16u : 0u);
+            const uint32_t d_hi = acc + (rd & 0xffffu);
+            umma_i8_ta(d_hi, a_hi, b, ri, 1u);
+            umma_i8_ta(d_hi + nt, a_hi + 8, b, ri & ~(1u << 7), 1u);
+            rb = nb;
+            ri = ni;
+            rd = nd;
+          }
+          umma_commit(&a_empty[as]);
+          if (last) {
+            umma_commit(&acc_full);
+            if (run_ends) umma_commit(&taps_free);
+          }
+        }
+        __syncwarp();
+        if (tile_no == 1 && it < 12 && lane == 0) TRACE2(u, 66 + 3 * it);
+        if (last && lane == 0) TRACE2(u, tr + 6);
+        if (++as == A) {
+          as = 0;
+          apar ^= 1u;
+        }
+      }
+    }
+    PROG3(0x32u, tile_no);
+    if (lane == 0) TRACE2(u, 11);
+  } else if (warp == kLoadWarp) {
+    // ================= loader: the raw boxes of one stage per ring slot =================
+    if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      uint32_t rs = 0, rb = 0, rpar = 1;  // raw slot, raw_full barrier; a fresh barrier passes a wait on the phase before the first
+      const int hist_frames = static_cast<int>(a.hist_frames);
+      constexpr int kBoxes = CH;                       // 128-byte boxes per stage
+      constexpr int kBoxFrames = kStageFrames / kBoxes;
+      for (uint32_t tile_no = 0; tile_no < n_tiles_mine; ++tile_no) {
+        const uint32_t w = w_begin + tile_no, t = w / G, g = w - t * G;
+        const int kf0 = tile_kf0(t);
+        const int row0 = static_cast<int>(g * kStreams);
+        for (uint32_t it = 0; it < n_iters; ++it) {
+          PROG3(0x40u, (tile_no << 8) | it);
+          WAIT(&raw_empty[rs], rpar, 0x1a000000u | (rs << 20) | (rpar << 16) | (tile_no << 8) | it);
+          uint8_t *dst = smem + rs * kRawSlotBytes;
+          const int f0 = kf0 + static_cast<int>(it) * kStageFrames;
+          if (tile_no == 1 && it < 12) TRACE2(u, 112 + it);
+          mbar_arrive_expect_tx(&raw_full[rb], kRawSlotBytes);
+          if (f0 >= 0 || f0 + kStageFrames <= 0) {
+#pragma unroll
+            for (int k = 0; k < kBoxes; ++k) {
+              const int f = f0 + k * kBoxFrames;
+              if (f0 >= 0) tma_box_2d(dst + k * (kRawSlotBytes / kBoxes), &maps.in_sw, f * CH * 2, row0, &raw_full[rb]);
+              else tma_box_2d(dst + k * (kRawSlotBytes / kBoxes), &maps.hist_sw, (hist_frames + f) * CH * 2, row0, &raw_full[rb]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int f = f0 + 16 * j;
+              if (f < 0) tma_box_2d(dst + j * kQuarterBytes, &maps.hist16, (hist_frames + f) * CH * 2, row0, &raw_full[rb]);
+              else tma_box_2d(dst + j * kQuarterBytes, &maps.in16, f * CH * 2, row0, &raw_full[rb]);
+            }
+          }
+          if (++rs == R) {
+            rs = 0;
+            rpar ^= 1u;
+          }
+          if (++rb == 2 * R) rb = 0;
+        }
+      }
+    }
+  } else {
+    // ================= history slide (resample.c:898-899) and the new position =================
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const uint32_t hist_elems = a.hist_frames * CH;
+    const size_t shift = static_cast<size_t>(sc.consumed) * CH;
+    const int vw = (shift % 8 == 0) ? 8 : (shift % 4 == 0) ? 4 : (shift % 2 == 0) ? 2 : 1;
+    const uint32_t hw = static_cast<uint32_t>(warp - kHistWarp0);
+    for (uint32_t w = w_begin; w < w_end; ++w) {
+      const uint32_t t = w / G, g = w - t * G;
+      if (t >= static_cast<uint32_t>(kStreams)) continue;
+      const uint32_t first = g * kStreams + t;
+      const uint32_t in_group = (kStreams - t + T - 1) / T;
+      const uint32_t in_batch = first < n_rows ? (n_rows - first + T - 1) / T : 0u;
+      const uint32_t n_mine = min(in_group, in_batch);
+      if (vw == 8) slide_streams<uint4>(a, T, first, n_mine, hist_elems, shift, lane, hw, kHistWarps);
+      else if (vw == 4) slide_streams<uint2>(a, T, first, n_mine, hist_elems, shift, lane, hw, kHistWarps);
+      else if (vw == 2) slide_streams<uint32_t>(a, T, first, n_mine, hist_elems, shift, lane, hw, kHistWarps);
+      else slide_streams<uint16_t>(a, T, first, n_mine, hist_elems, shift, lane, hw, kHistWarps);
+      for (uint32_t k = lane + 32 * hw; k < n_mine; k += 32 * kHistWarps) {
+        const size_t s = first + static_cast<size_t>(k) * T;
+        a.last_sample[s] = sc.ls1;
+        a.samp_frac[s] = sc.frac1;
+      }
+    }
+  }
+
+  PROG3(0x50u, 0);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp2) tmem_dealloc(tmem_slot, 512);
+  PROG3(0x51u, 0);
+  if (tid == 0) {
+    TRACE2(u, 9);
+#ifdef SPXB_UMMA2_TRACE
+    if (u.trace) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      u.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots2 + 15] = gt;
+    }
+#endif
+  }
+}
+
 // One thread per 16-byte cell of the packed tile. jobs[i] = {slot, phase0, delta}; `plan` is the
 // host's UmmaKStep table (umma_plan.h) in HBM.
 __global__ void build_packed_tiles_kernel(const int32_t *__restrict__ h, uint32_t num, uint32_t den, uint32_t taps,
@@ -857,6 +1355,8 @@ void umma2_configure_device() {
   big_smem(umma2_fir_kernel<2, false>);
   big_smem(umma2_fir_kernel<1, true>);
   big_smem(umma2_fir_kernel<2, true>);
+  big_smem(umma3_fir_kernel<1>);
+  big_smem(umma3_fir_kernel<2>);
 }
 
 // what the TMA-fed kernel needs of a call: the whole batch (no stream subset), an input to read, and
@@ -902,7 +1402,7 @@ EncodeTiledFn encode_tiled() {
 
 // bytes x rows view of `rows` PCM rows of `row_bytes` valid bytes, `pitch` bytes apart; box = box_bytes x box_rows
 bool pcm_map(CUtensorMap *m, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch, uint32_t box_bytes,
-             uint32_t box_rows) {
+             uint32_t box_rows, bool swizzle128 = false) {
   EncodeTiledFn fn = encode_tiled();
   if (!fn || row_bytes == 0 || rows == 0) return false;
   const cuuint64_t gdim[2] = {row_bytes, rows};
@@ -910,7 +1410,8 @@ bool pcm_map(CUtensorMap *m, const void *base, uint64_t row_bytes, uint64_t rows
   const cuuint32_t box[2] = {box_bytes, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), gdim, gstride, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -1003,8 +1504,16 @@ cudaError_t launch_umma2(UmmaContext *c, const CallArgs &a, cudaStream_t stream,
 #ifdef SPXB_UMMA2_WATCHDOG
   {
     static unsigned long long *d_dbg = nullptr;
-    if (!g_wd && cudaHostAlloc(reinterpret_cast<void **>(&g_wd), 512 * 8, cudaHostAllocMapped) == cudaSuccess) {
-      std::memset(g_wd, 0, 512 * 8);
+    if (!g_wd && cudaHostAlloc(reinterpret_cast<void **>(&g_wd), 1024 * 8, cudaHostAllocMapped) == cudaSuccess) {
+      std::memset(g_wd, 0, 1024 * 8);
+      std::thread([] {
+        std::this_thread::sleep_for(std::chrono::seconds(25));
+        wd_dump();
+        for (int cta = 0; cta < 4; ++cta)
+          for (int w = 0; w < 12; ++w)
+            fprintf(stderr, "progress: cta %d warp %d code %02llx value %llu\n", cta, w, g_wd[600 + cta * 16 + w] >> 32, g_wd[600 + cta * 16 + w] & 0xffffffffull);
+        fflush(stderr);
+      }).detach();
       cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_dbg), g_wd, 0);
       atexit(wd_dump);
     }
@@ -1056,7 +1565,25 @@ cudaError_t launch_umma2(UmmaContext *c, const CallArgs &a, cudaStream_t stream,
       !pcm_map(&maps.hist16, a.hist_src, hist_bytes, a.n_streams, static_cast<uint64_t>(a.hist_stride) * 2, row_box / 4, streams))
     return cudaErrorInvalidValue;
   cudaError_t e;
-  if (c->n_acc == 2) {
+  static const bool a_in_tmem = [] {
+    const char *e2 = getenv("SPXB_UMMA_ATMEM");
+    return !e2 || atoi(e2) != 0;
+  }();
+  if (a_in_tmem && c->n_acc == 1 && 4 * c->nt + 64 <= 512) {
+    // raw ring: as many 16 KB slots as fit beside the tap tile
+    const uint32_t slots = std::min<uint32_t>(kMaxRawSlots, (kMaxSmem2 - c->tile_bytes) / kRawSlotBytes);
+    if (slots < 2) return cudaErrorInvalidConfiguration;
+    u.x_stages = slots;
+    cfg.dynamicSmemBytes = slots * kRawSlotBytes + c->tile_bytes;
+    Umma3Maps m3;
+    if (!pcm_map(&m3.in_sw, a.in, in_bytes, a.n_streams, a.in_stride * 2, 128, streams, true) ||
+        !pcm_map(&m3.hist_sw, a.hist_src, hist_bytes, a.n_streams, static_cast<uint64_t>(a.hist_stride) * 2, 128, streams, true))
+      return cudaErrorInvalidValue;
+    m3.in16 = maps.in16;
+    m3.hist16 = maps.hist16;
+    e = a.channels == 2 ? cudaLaunchKernelEx(&cfg, umma3_fir_kernel<2>, a, u, m3)
+                        : cudaLaunchKernelEx(&cfg, umma3_fir_kernel<1>, a, u, m3);
+  } else if (c->n_acc == 2) {
     cfg.blockDim = dim3(kThreadsDB);
     e = a.channels == 2 ? cudaLaunchKernelEx(&cfg, umma2_fir_kernel<2, true>, a, u, maps)
                         : cudaLaunchKernelEx(&cfg, umma2_fir_kernel<1, true>, a, u, maps);

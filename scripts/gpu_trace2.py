@@ -48,9 +48,12 @@ for wl in (sys.argv[1:] or ["C3", "C4", "C5"]):
                 show(f"tile {j} {nm}", 16 + 8 * j + k)
     for k, nm in enumerate(("step: enter", "step: slot empty", "step: converted + stored", "step: fenced + arrived", "step: next loads issued")):
         show(f"converter step n_iters+3 {nm}", 56 + k)
-    for it in range(16):
+    for it in range(12):
         for k, nm in enumerate(("wait", "full", "issued")):
             show(f"mma tile 1 stage {it} {nm}", 64 + 3 * it + k)
+    for it in range(12):
+        show(f"tile 1 stage {it}: box issued", 112 + it)
+        show(f"tile 1 stage {it}: raw bytes seen by its converter group", 100 + it)
     for slot in (8, 10, 11, 9):
         show(NAMES[slot], slot)
     gt0, gt1 = t[:, 14], t[:, 15]
