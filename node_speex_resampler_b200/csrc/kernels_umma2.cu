@@ -136,6 +136,9 @@ struct Umma2Args {
 #ifndef SPXB_PF_DIST
 #define SPXB_PF_DIST 0
 #endif
+#ifndef SPXB_PREFETCH_MAPS
+#define SPXB_PREFETCH_MAPS 0
+#endif
 #ifndef SPXB_DEFER_EPILOGUE
 #define SPXB_DEFER_EPILOGUE 1
 #endif
@@ -877,7 +880,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
   uint64_t *const tap_full = bars + kBarTap;
   uint64_t &taps_free = bars[kBarMisc], &acc_full = bars[kBarMisc + 1], &acc_empty = bars[kBarMisc + 2],
            &tmem_ready = bars[kBarMisc + 3];
-  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t tmem_slot, raw_seen[kConvWarps2];
 
   constexpr int kStreams = kUmmaRows / CH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -901,6 +904,11 @@ __global__ void __launch_bounds__(kThreads2, 1)
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) TRACE2(u, 0);
+#if SPXB_PREFETCH_MAPS
+  // the first box of a launch otherwise waits for its (cold) descriptor
+  if (warp == kLoadWarp && lane < 4)
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<const char *>(&maps) + lane * sizeof(CUtensorMap)) : "memory");
+#endif
 #ifdef SPXB_UMMA2_TRACE
   if (tid == 11 * 32 && u.trace) {
     unsigned long long gt;
@@ -1080,9 +1088,20 @@ __global__ void __launch_bounds__(kThreads2, 1)
             lo[2 * c + 1] = __byte_perm(v.z, v.w, 0x6420);
           }
         }
-        // the raw bytes are in registers (hi / lo depend on every load): the slot can be refilled
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[rs]);
+        // The slot can be refilled once every lane's raw bytes are IN registers. Having issued the loads
+        // is not enough (one row of one tile came out wrong in ~2 % of the launches: a chunk of the NEXT
+        // box read in place of this one's). Lane 0 stores a value reduced over words that depend on every
+        // load of every lane before it arrives: the store cannot issue until those loads have completed.
+        {
+          uint32_t seen = 0;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) seen ^= hi[c] ^ lo[c];
+          seen = __reduce_xor_sync(0xffffffffu, seen);
+          if (lane == 0) {
+            *reinterpret_cast<volatile uint32_t *>(&raw_seen[warp]) = seen;
+            mbar_arrive(&raw_empty[rs]);
+          }
+        }
         // the MMAs that read this A slot last have completed
         PROG3(0x23u, q);
         WAIT(&a_empty[as], apar, 0x14000000u | (as << 20) | (apar << 16) | q);

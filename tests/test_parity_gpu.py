@@ -1033,13 +1033,16 @@ def test_persistent_kernel_parity(shape):
 
 @pytest.mark.parametrize("env", [
     {"SPXB_UMMA_RESIDENT": "0"},                                                   # the one-tile-per-CTA kernel on a long filter
-    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_NT": "64", "SPXB_UMMA_DENSE": "1"},     # two accumulator sets, dedicated epilogue warps
-    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_NT": "96"},                             # an even ring
-    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA2_XSTAGES": "3"},                        # an odd ring: slots change converter group
+    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_NT": "64", "SPXB_UMMA_DENSE": "1"},     # two accumulator sets, dedicated epilogue warps (planes in shared memory)
+    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_NT": "96"},                             # planes in TMEM, 4 A slots, even raw ring
+    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_NT": "112"},                            # planes in TMEM, 2 A slots, odd raw ring
+    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_ATMEM": "0"},                           # planes converted in place in shared memory
+    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_ATMEM": "0", "SPXB_UMMA2_XSTAGES": "3"},  # ... with an odd ring: slots change converter group
 ], ids=lambda e: "_".join(f"{k[5:].lower()}{v}" for k, v in e.items()))
 def test_long_filter_on_either_tensor_kernel(env):
     """The long-filter shapes through the kernel they do NOT get by default, and through the
-    persistent kernel's other configurations (ring sizes, one or two accumulator sets): same bar."""
+    persistent kernel's other configurations (byte planes in tensor memory or in shared memory, ring
+    sizes, one or two accumulator sets): same bar."""
     import subprocess
     import sys
     for shape in (("C5x", 700, 2, 96000, 44100, 10, 1920, 3), ("C4x", 600, 1, 48000, 16000, 10, 960, 2)):
