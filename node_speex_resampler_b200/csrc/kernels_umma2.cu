@@ -1,4 +1,6 @@
-// kernels_umma2.cu -- persistent, TMA-fed tensor-core FIR for sm_100a: the kernel long filters run
+// kernels_umma2.cu -- persistent, TMA-fed tensor-core FIR for sm_100a: the kernels long filters run
+// (umma3_fir_kernel, byte planes in tensor memory, is the default; umma2_fir_kernel converts in place in
+// shared memory and carries the variant with two accumulator sets -- SPXB_UMMA_ATMEM=0)
 // (kernels_umma.cu, one tile per CTA with streamed tap tiles and LDG-fed converters, stays as the
 // path for short filters, ragged cohorts, unaligned rows and tap tiles that do not fit).
 //
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(DB ? kThreadsDB : kThreads2, 1)
   uint64_t *const tap_full = bars + kBarTap;
   uint64_t &taps_free = bars[kBarMisc], &tmem_ready = bars[kBarMisc + 5];
   uint64_t *const acc_full = bars + kBarMisc + 1, *const acc_empty = bars + kBarMisc + 3;
-  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t tmem_slot, raw_seen[kConvWarps2];
 #ifdef SPXB_UMMA2_WATCHDOG
   __shared__ volatile uint32_t wd_prog[16];
 #define PROG(code, v) \
@@ -548,6 +550,15 @@ __global__ void __launch_bounds__(DB ? kThreadsDB : kThreads2, 1)
         }
       }
       PROG(2u, q);
+      {
+        // (a store of a value that depends on every word: the warp cannot reach the barrier with loads
+        // from the slot still in flight, whatever the compiler does with the byte splitting above)
+        uint32_t seen = 0;
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) seen ^= w[i].x ^ w[i].y ^ w[i].z ^ w[i].w;
+        seen = __reduce_xor_sync(0xffffffffu, seen);
+        if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&raw_seen[warp]) = seen;
+      }
       group_sync(group);  // every thread of the group holds its share of the slot in registers
       STEP_MARK(2);
       PROG(3u, q);

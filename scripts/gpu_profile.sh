@@ -15,7 +15,7 @@ timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $O
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 5 -c 200 --csv --log-file $OUT/launches_$TAG.csv \
   python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-also --lean --min-seconds 0.001 > /dev/null 2>&1
 for WL in C3 C4 C5; do
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:umma2?_fir -s 8 -c 1 -f -o $OUT/prof_umma_${WL}_$TAG \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:umma[23]?_fir -s 8 -c 1 -f -o $OUT/prof_umma_${WL}_$TAG \
     python bench.py --workload $WL --kernel tensor --steps 10 --warmup 3 --no-cpu-baseline --no-also --min-seconds 0.001 > /dev/null 2>&1
 done
 for SL in 2 3 4; do
