@@ -243,6 +243,12 @@ def measure(cx, wl, S, K, W, min_seconds, lean, kernel):
     torch.cuda.synchronize()
     est = max(e0.elapsed_time(e1) * 1e-3, 1e-6)
     reps = int(min(400, max(3, math.ceil(min_seconds / est))))
+    if world > 1:
+        # every repetition is bracketed by barriers: the ranks must agree on how many there are (each
+        # rank's own estimate can differ by one, which left one rank alone in a collective for ten minutes)
+        t = torch.tensor([reps], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        reps = int(t.item())
 
     sampler = ClockSampler(local)
     if rank == 0:

@@ -963,6 +963,8 @@ __global__ void __launch_bounds__(kThreads2, 1)
 
     // ---- epilogue of one tile (as in the kernel above, the two warps of a lane quarter share the column groups) ----
     const uint32_t sl_out = sl, ch_out = ch;
+    const uint32_t out_bits = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(a.out)) | (static_cast<uint32_t>(a.out_stride) * 2u);
+    const int out_align = (out_bits & 15u) == 0 ? 16 : (out_bits & 3u) == 0 ? 4 : 2;
     auto epilogue = [&](uint32_t tile_no) {
       const uint32_t w = w_begin + tile_no, t = w / G, g = w - t * G;
       const uint32_t m0 = t * nt;
@@ -1009,10 +1011,12 @@ __global__ void __launch_bounds__(kThreads2, 1)
         const uint32_t total = n_valid * CH;
         const uint32_t n_here = first_elem >= total ? 0u : min(16u, total - first_elem);
         int16_t *dst = out_row + first_elem;
-        if (n_here == 16) {
+        if (n_here == 16 && out_align == 16) {
           reinterpret_cast<uint4 *>(dst)[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
           reinterpret_cast<uint4 *>(dst)[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
-        } else {
+        } else if (out_align >= 4) {
+          // the ragged end of the call's output, or output rows that are only 4-byte aligned (e.g. 882
+          // stereo frames per row): whole 32-bit words, then possibly one last int16
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (2u * j + 1 < n_here) reinterpret_cast<uint32_t *>(dst)[j] = wv[j];
@@ -1020,6 +1024,12 @@ __global__ void __launch_bounds__(kThreads2, 1)
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               if (2u * j + 1 == n_here) dst[2 * j] = static_cast<int16_t>(wv[j] & 0xffffu);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (2u * j < n_here) dst[2 * j] = static_cast<int16_t>(wv[j] & 0xffffu);
+            if (2u * j + 1 < n_here) dst[2 * j + 1] = static_cast<int16_t>(wv[j] >> 16);
           }
         }
       }
@@ -1391,10 +1401,21 @@ void umma2_configure_device() {
 
 // what the TMA-fed kernel needs of a call: the whole batch (no stream subset), an input to read, and
 // every row -- input, output, history -- starting on a 16-byte boundary
+bool umma2_planes_in_tmem() {
+  static const bool v = [] {
+    const char *e = getenv("SPXB_UMMA_ATMEM");
+    return !e || atoi(e) != 0;
+  }();
+  return v;
+}
+
 bool umma2_covers(const CallArgs &a) {
   if (a.ids != nullptr || a.uniform.n_in == 0) return false;
-  const uintptr_t bits = reinterpret_cast<uintptr_t>(a.in) | (a.in_stride * 2u) | reinterpret_cast<uintptr_t>(a.out) |
-                         (a.out_stride * 2u) | reinterpret_cast<uintptr_t>(a.hist_src) | (a.hist_stride * 2u);
+  // TMA needs the input and history rows on 16-byte boundaries; the output rows only matter to the kernel
+  // that stores whole vectors unconditionally (planes in shared memory)
+  uintptr_t bits = reinterpret_cast<uintptr_t>(a.in) | (a.in_stride * 2u) | reinterpret_cast<uintptr_t>(a.hist_src) |
+                   (a.hist_stride * 2u);
+  if (!umma2_planes_in_tmem()) bits |= reinterpret_cast<uintptr_t>(a.out) | (a.out_stride * 2u);
   return (bits & 15u) == 0;
 }
 
@@ -1595,11 +1616,10 @@ cudaError_t launch_umma2(UmmaContext *c, const CallArgs &a, cudaStream_t stream,
       !pcm_map(&maps.hist16, a.hist_src, hist_bytes, a.n_streams, static_cast<uint64_t>(a.hist_stride) * 2, row_box / 4, streams))
     return cudaErrorInvalidValue;
   cudaError_t e;
-  static const bool a_in_tmem = [] {
-    const char *e2 = getenv("SPXB_UMMA_ATMEM");
-    return !e2 || atoi(e2) != 0;
-  }();
-  if (a_in_tmem && c->n_acc == 1 && 4 * c->nt + 64 <= 512) {
+  const bool out_rows_aligned = ((reinterpret_cast<uintptr_t>(a.out) | (a.out_stride * 2u)) & 15u) == 0;
+  // planes in tensor memory: wide tiles (one accumulator set), and any tile whose output rows are not on
+  // 16-byte boundaries (the kernels with planes in shared memory store whole vectors)
+  if (umma2_planes_in_tmem() && (c->n_acc == 1 || !out_rows_aligned) && 4 * c->nt + 64 <= 512) {
     // raw ring: as many 16 KB slots as fit beside the tap tile
     const uint32_t slots = std::min<uint32_t>(kMaxRawSlots, (kMaxSmem2 - c->tile_bytes) / kRawSlotBytes);
     if (slots < 2) return cudaErrorInvalidConfiguration;
@@ -1613,6 +1633,8 @@ cudaError_t launch_umma2(UmmaContext *c, const CallArgs &a, cudaStream_t stream,
     m3.hist16 = maps.hist16;
     e = a.channels == 2 ? cudaLaunchKernelEx(&cfg, umma3_fir_kernel<2>, a, u, m3)
                         : cudaLaunchKernelEx(&cfg, umma3_fir_kernel<1>, a, u, m3);
+  } else if (!out_rows_aligned) {
+    return cudaErrorNotSupported;  // (the kernels below store whole vectors)
   } else if (c->n_acc == 2) {
     cfg.blockDim = dim3(kThreadsDB);
     e = a.channels == 2 ? cudaLaunchKernelEx(&cfg, umma2_fir_kernel<2, true>, a, u, maps)
