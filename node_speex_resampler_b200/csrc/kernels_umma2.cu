@@ -127,7 +127,6 @@ struct Umma2Args {
   uint32_t n_rec;
   uint32_t stage_off[kMaxTapStages + 1];  // byte offset of each 64-frame stage inside the packed tile
   uint16_t stage_rec[kMaxTapStages + 2];  // first MMA record of each stage (K step 0 has its own code)
-  uint16_t stage_mid[kMaxTapStages + 2];  // first record of the stage's second K step
   // The MMA records live in the kernel parameters (constant bank): the issuing lane reads them with
   // uniform loads straight into uniform registers. (From shared memory every operand of a
   // tcgen05.mma went through a register-to-uniform move: ~150 cycles of issue per MMA, three times
@@ -1475,13 +1474,11 @@ cudaError_t umma2_upload_plan(UmmaContext *c, cudaStream_t) {
   c->recs.clear();
   c->stage_off.assign(kMaxTapStages + 1, 0u);
   c->stage_rec.assign(kMaxTapStages + 2, 0u);
-  c->stage_mid.assign(kMaxTapStages + 2, 0u);
   for (uint32_t it = 0; it < n_iters; ++it) {
     c->stage_off[it] = c->packed.k[2 * it].off16 * 16u;
     c->stage_rec[it] = static_cast<uint16_t>(c->recs.size() / 3);
     for (uint32_t h = 0; h < 2; ++h) {
       const uint32_t k = 2 * it + h;
-      if (h == 1) c->stage_mid[it] = static_cast<uint16_t>(c->recs.size() / 3);
       if (k >= c->ksteps) break;
       const UmmaKStep &ks = c->packed.k[k];
       if (k == 0) continue;  // K step 0 has its own code in the kernel
@@ -1550,7 +1547,6 @@ cudaError_t launch_umma2(UmmaContext *c, const CallArgs &a, cudaStream_t stream,
   std::memcpy(u.rec, c->recs.data(), c->recs.size() * sizeof(uint32_t));
   for (uint32_t i = 0; i <= kMaxTapStages; ++i) u.stage_off[i] = c->stage_off[i];
   for (uint32_t i = 0; i < kMaxTapStages + 2; ++i) u.stage_rec[i] = c->stage_rec[i];
-  for (uint32_t i = 0; i < kMaxTapStages + 2; ++i) u.stage_mid[i] = c->stage_mid[i];
   u.trace = nullptr;
 #ifdef SPXB_UMMA2_WATCHDOG
   {

@@ -34,7 +34,6 @@ struct UmmaContext {
   std::vector<uint32_t> recs;       // MMA records of the persistent kernel, 4 words each (kernels_umma2.cu: MmaRec)
   std::vector<uint32_t> stage_off;  // per 64-frame stage: byte offset inside the packed tile (+ end)
   std::vector<uint16_t> stage_rec;  // per stage: first MMA record (+ end)
-  std::vector<uint16_t> stage_mid;  // per stage: first record of its second K step
   int8_t *d_pool = nullptr;
   size_t pool_cap = 0;  // tiles
   std::unordered_map<uint64_t, uint32_t> slot_of;
