@@ -813,7 +813,9 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
   }
   const uint64_t ops_before = c->stream_ops;
 
-  const uint32_t nt = pick_nt(*c, n_groups, sc.n_out);
+  uint32_t nt = pick_nt(*c, n_groups, sc.n_out);
+  // the persistent kernel keeps its A ring behind the accumulator: 4 nt + 64 columns of the 512
+  if (want_resident && umma2_planes_in_tmem() && nt > 112) nt = 112;
   if ((nt != c->nt || want_resident != c->resident_wanted) && c->frozen) {
     *err = cudaErrorNotSupported;
     return false;
@@ -848,7 +850,9 @@ bool umma_prepare(UmmaContext *c, const CallArgs &a, cudaStream_t stream, cudaEr
         return false;
       }
       c->resident = true;
-      c->n_acc = 8 * nt <= 512 ? 2u : 1u;
+      // two accumulator sets only in the variant with the byte planes in shared memory (SPXB_UMMA_ATMEM=0);
+      // the default kernel keeps one set and the A ring in the remaining TMEM columns
+      c->n_acc = (!umma2_planes_in_tmem() && 8 * nt <= 512) ? 2u : 1u;
       c->tmem_cols = pow2_cols(c->n_acc * 4 * nt);
       c->tile_bytes = c->packed.tile_bytes;
       c->stages = x_stages;

@@ -52,6 +52,7 @@ uint64_t umma_pool_generation(const UmmaContext *c);
 // persistent kernel with resident packed tap tiles (kernels_umma2.cu), chosen by umma_prepare when
 // the packed tile of the geometry fits shared memory
 void umma2_configure_device();
+bool umma2_planes_in_tmem();  // SPXB_UMMA_ATMEM (default on)
 bool umma2_covers(const CallArgs &a);  // whole batch, rows on 16-byte boundaries, an input to read
 cudaError_t umma2_upload_plan(UmmaContext *c, cudaStream_t stream);
 uint32_t umma2_x_stages(uint32_t channels, uint32_t tile_bytes, uint32_t ksteps);
