@@ -1,23 +1,30 @@
-// kernels_umma2.cu -- persistent, TMA-fed tensor-core FIR for sm_100a: the kernels long filters run
-// (umma3_fir_kernel, byte planes in tensor memory, is the default; umma2_fir_kernel converts in place in
-// shared memory and carries the variant with two accumulator sets -- SPXB_UMMA_ATMEM=0)
+// kernels_umma2.cu -- persistent, TMA-fed tensor-core FIR kernels for sm_100a: what long filters run
 // (kernels_umma.cu, one tile per CTA with streamed tap tiles and LDG-fed converters, stays as the
-// path for short filters, ragged cohorts, unaligned rows and tap tiles that do not fit).
+// path for short filters, ragged cohorts, input rows off 16-byte boundaries and tap tiles that do
+// not fit). Two kernels live here:
+//   umma3_fir_kernel  (default)  the byte planes go to TENSOR MEMORY as the MMA's A operand;
+//   umma2_fir_kernel  (SPXB_UMMA_ATMEM=0)  the byte planes are converted in place in the ring slot in
+//                     shared memory; with two accumulator sets for tiles of <= 64 outputs.
 //
 // Same arithmetic as kernels_umma.cu -- the whole hot path of speex_resampler_process_interleaved_int
 // (deps/speex/resample.c:1061-1082 over :968-1036 and the four resampler_basic_* kernels :331-558)
 // as an EXACT integer banded GEMM on tcgen05.mma.kind::i8, one rounding at the end (WORD2INT,
 // arch.h:208-209) -- organised around what the measurements of round 2 showed to bound a 64-frame
-// stage of the long-filter shapes:
+// stage of the long-filter shapes (DESIGN.md 4.6):
 //   * PCM reaches the SM through the copy engine. LDG.128 into registers delivers 13-14 B/clk/SM
 //     from 8 warps and 22 from 16, whatever is in flight and whatever L1 is left (csrc/ldg_rate.cu);
 //     that alone is ~1200 cycles per 16 KB stage -- the stage time of every earlier version.
 //     cp.async 16 B does 25.6, 1-D bulk copies cost ~61 cycles of issue EACH (4 B/clk for 256-byte
 //     row pieces), one tensor-map box of 64 rows x 256 B does 42 B/clk/SM = 387 cycles per stage.
-//     A loader lane issues one box per stage into the ring slot; a converter group splits the bytes
-//     IN PLACE (raw rows -> the two byte planes in UMMA layout) behind a group barrier. No thread
-//     computes a PCM address, no registers hold loads in flight, the ragged end of the input and the
-//     rows past the end of the batch are the tensor map's zero fill.
+//     A loader lane issues the boxes of a stage into a ring slot. No thread computes a PCM address,
+//     no registers hold loads in flight, the ragged end of the input and the rows past the end of
+//     the batch are the tensor map's zero fill.
+//   * The raw bytes become the A operand without a plane ring in shared memory (umma3): a converter
+//     thread owns one series = one TMEM lane, splits its row's bytes in registers and writes them with
+//     tcgen05.st behind the accumulator columns. The raw slot is free as soon as it has been read, the
+//     tensor core stops re-reading the planes from shared memory, and the shared memory the plane ring
+//     took is ring depth for the boxes. (umma2: the group splits the bytes in place in the slot,
+//     behind a group barrier; the slot is held until the MMAs that read it have completed.)
 //   * One CTA per SM, persistent: CTA b walks the contiguous share [b*W/grid, (b+1)*W/grid) of the
 //     tile list ordered tile-index-major (w = t * groups + g), so consecutive tiles of a CTA share
 //     their output tile index t and with it the tap tile. Barriers, TMEM and the instruction cache
@@ -29,16 +36,19 @@
 //     that can be non-zero are stored, ~0.6 of the dense bytes. The MMA lane walks a per-K-step
 //     table of at most three records carried in the kernel parameters, one record ahead of the
 //     MMAs it issues.
-// Warp roles (384 threads; 512 in the instantiation with two accumulator sets):
+//   * Every mbarrier has exactly ONE waiting party (a parity wait tells a phase only from the one
+//     before it), and a slot is handed back only after the loads from it have completed -- both
+//     learnt from launches that hung or were wrong in one row out of thousands.
+// Warp roles (384 threads; 512 in umma2's instantiation with two accumulator sets):
 //   0-7   converters, two groups of four on alternate stages; they also run the epilogue (straight
 //         from TMEM to the interleaved int16 output) when there is one accumulator set;
 //   8     owns TMEM and the barriers, loads the tap tile of each run; one elected lane issues the
-//         MMAs, releases ring slots with tcgen05.commit, hands the accumulator over (acc_full) and
-//         takes it back (acc_empty);
+//         MMAs, releases slots with tcgen05.commit, hands the accumulator over (acc_full) and takes
+//         it back (acc_empty);
 //   9     lane 0: the TMA boxes;
 //   10-11 slide the history (resample.c:898-899) of this CTA's share of streams beside the FIR and
 //         publish the new stream position;
-//   12-15 (8 nt <= 512: two accumulator sets) the epilogue of a tile under the next tile's MMAs.
+//   12-15 (umma2, 8 nt <= 512: two accumulator sets) the epilogue of a tile under the next tile's MMAs.
 #include <cuda.h>
 
 #include <algorithm>
