@@ -1031,6 +1031,41 @@ def test_persistent_kernel_parity(shape):
     assert "resident ok" in r.stdout and "'stages'" in r.stdout
 
 
+@pytest.mark.parametrize("ch,i,o", [(2, 96000, 44100), (1, 48000, 16000)], ids=["stereo", "mono"])
+def test_persistent_kernel_takes_calls_shorter_than_the_row_pitch(ch, i, o):
+    """The persistent kernel reads PCM through tensor maps whose extent is the call's length, not the row
+    pitch: calls of varying length inside rows of a fixed (16-byte aligned) pitch -- odd lengths, a box
+    that ends inside the input, boxes entirely past its end, the straddle of history and input moving
+    from call to call -- must match the oracle, lengths, samples and state."""
+    q, pitch, S = 10, 1920, 300
+    b = StreamBatch(S, ch, i, o, q)
+    pick = [0, 1, 63, 64, 150, S - 1]
+    refs = {s: O.OracleResampler(ch, i, o, q) for s in pick}
+    want, got = {s: [] for s in pick}, {s: [] for s in pick}
+    pos = 0
+    for k, n in enumerate((1001, 1920, 333, 64, 1500, 17, 1919)):
+        pcm = np.zeros((S, pitch * ch), np.int16)
+        pcm[:, : n * ch] = synth_pcm(S, ch, n, i, seed=0xABBA, start_frame=pos)
+        pcm[:, n * ch:] = 12345      # bytes past the call's length must not be read
+        pos += n
+        cap = -(-n * o // i) + 1
+        out, used, made = b.process(pcm, n, cap)
+        assert b.last_kernel() == KERNEL_TENSOR
+        for s in pick:
+            y, u_, m = refs[s].process(pcm[s, : n * ch], cap)
+            assert (u_, m) == (int(used[s]), int(made[s])), (k, s)
+            d = np.abs(y.astype(np.int32) - out[s, : m * ch].astype(np.int32))
+            assert d.max(initial=0) <= 1, (k, s, int(d.max()))        # per hop: 1 LSB
+            want[s].append(y)
+            got[s].append(out[s, : m * ch].copy())
+    for s in pick:  # the SNR bar over the stream (a 16-sample hop with one LSB off is below 90 dB by itself)
+        assert O.snr_db(np.concatenate(want[s]), np.concatenate(got[s])) >= 90.0, s
+    ls, fr, mg, hist = b.get_state(pick[-1])
+    rls, rfr, rhist = refs[pick[-1]].state(0)
+    assert (ls, fr) == (rls, rfr) and np.array_equal(hist.reshape(-1, ch)[:, 0].astype(np.float32), rhist)
+    b.close()
+
+
 @pytest.mark.parametrize("S,ch,i,o,q,n", [
     (4096, 1, 48000, 16000, 10, 960),     # C4: mono, 16 stages per tile, one tile per CTA
     (4096, 2, 96000, 48000, 10, 1920),    # stereo long filter with 16-byte aligned output rows, several tiles per CTA
