@@ -424,14 +424,19 @@ def test_speex_c_api_getters_and_skip_zeros():
     L.speex_resampler_destroy(st)
 
 
-@pytest.mark.parametrize("kernel", [KERNEL_TENSOR, KERNEL_STRICT], ids=["tensor", "strict"])
-def test_device_ring_graph_replay_equals_single_hops(kernel):
+@pytest.mark.parametrize("kernel,shape", [
+    (KERNEL_TENSOR, (70, 2, 44100, 48000, 7, 882, 960)),
+    (KERNEL_TENSOR, (200, 1, 48000, 16000, 10, 960, 320)),    # long filter: the persistent kernel, its tensor maps captured
+    (KERNEL_TENSOR, (150, 2, 96000, 48000, 10, 1920, 960)),   # ... stereo, several tiles per CTA
+    (KERNEL_STRICT, (70, 2, 44100, 48000, 7, 882, 960)),
+], ids=["tensor", "tensor_long_mono", "tensor_long_stereo", "strict"])
+def test_device_ring_graph_replay_equals_single_hops(kernel, shape):
     """spxb_batch_process_device_ring captures a repeating hop sequence into a CUDA graph (second
     unchanged sighting) and replays it afterwards. Every round -- launch by launch, captured,
     replayed -- must leave the same outputs and the same stream state as single uniform hops."""
     torch = pytest.importorskip("torch")
     L = lib()
-    S, ch, i, o, q, n, cap = 70, 2, 44100, 48000, 7, 882, 960
+    S, ch, i, o, q, n, cap = shape
     ring, steps, rounds = 4, 8, 5
     a, b = StreamBatch(S, ch, i, o, q), StreamBatch(S, ch, i, o, q)
     a.set_kernel(kernel)
