@@ -1094,14 +1094,23 @@ def test_persistent_kernel_is_deterministic_under_repetition(S, ch, i, o, q, n):
     b_.close()
 
 
+# The variant with the byte planes in shared memory (SPXB_UMMA_ATMEM=0) is an experiment kept for the record:
+# its converters still follow every phase of barriers that both groups share, which tests/test_ring_protocol.py
+# shows can deadlock when a group falls a slot cycle behind. It has passed these cases every time they ran,
+# but a hang costs ten minutes per case, so they run only on request (SPXB_TEST_INPLACE=1).
+INPLACE = [
+    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_ATMEM": "0"},                                             # planes converted in place in shared memory
+    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_ATMEM": "0", "SPXB_UMMA2_XSTAGES": "3"},                  # ... with an odd ring: slots change converter group
+    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_ATMEM": "0", "SPXB_UMMA_NT": "64", "SPXB_UMMA_DENSE": "1"},  # ... two accumulator sets, dedicated epilogue warps
+] if os.environ.get("SPXB_TEST_INPLACE") else []
+
+
 @pytest.mark.parametrize("env", [
     {"SPXB_UMMA_RESIDENT": "0"},                                                   # the one-tile-per-CTA kernel on a long filter
-    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_NT": "64", "SPXB_UMMA_DENSE": "1"},     # two accumulator sets, dedicated epilogue warps (planes in shared memory)
+    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_NT": "64", "SPXB_UMMA_DENSE": "1"},     # planes in TMEM, narrow dense tiles
     {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_NT": "96"},                             # planes in TMEM, 4 A slots, even raw ring
     {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_NT": "112"},                            # planes in TMEM, 2 A slots, odd raw ring
-    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_ATMEM": "0"},                           # planes converted in place in shared memory
-    {"SPXB_UMMA_RESIDENT": "1", "SPXB_UMMA_ATMEM": "0", "SPXB_UMMA2_XSTAGES": "3"},  # ... with an odd ring: slots change converter group
-], ids=lambda e: "_".join(f"{k[5:].lower()}{v}" for k, v in e.items()))
+] + INPLACE, ids=lambda e: "_".join(f"{k[5:].lower()}{v}" for k, v in e.items()))
 def test_long_filter_on_either_tensor_kernel(env):
     """The long-filter shapes through the kernel they do NOT get by default, and through the
     persistent kernel's other configurations (byte planes in tensor memory or in shared memory, ring
